@@ -1,0 +1,548 @@
+// capi.cu -- the extern "C" boundary declared in include/gasr.h: context, memory, and the module entry points.
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace gasr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int ws_reserve(gasr_ctx *ctx, Workspace &ws, size_t bytes) {
+    if (bytes <= ws.bytes) return GASR_OK;
+    if (ws.ptr) {
+        GASR_CUDA(cudaStreamSynchronize(ctx->stream));
+        GASR_CUDA(cudaFree(ws.ptr));
+        ctx->device_bytes -= ws.bytes;
+        ws.ptr = nullptr; ws.bytes = 0;
+    }
+    bytes = align_up(bytes, 1 << 20);
+    cudaError_t e = cudaMalloc(&ws.ptr, bytes);
+    if (e != cudaSuccess) {
+        set_error("workspace allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        ws.ptr = nullptr;
+        return GASR_ERR_NOMEM;
+    }
+    ws.bytes = bytes;
+    ctx->device_bytes += bytes;
+    return GASR_OK;
+}
+
+int pinned_reserve(gasr_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_out_bytes) return GASR_OK;
+    if (ctx->pinned_out) {
+        GASR_CUDA(cudaStreamSynchronize(ctx->stream));
+        GASR_CUDA(cudaFreeHost(ctx->pinned_out));
+        ctx->host_bytes -= ctx->pinned_out_bytes;
+        ctx->pinned_out = nullptr; ctx->pinned_out_bytes = 0;
+    }
+    bytes = align_up(bytes, 1 << 16);
+    cudaError_t e = cudaHostAlloc(&ctx->pinned_out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        set_error("pinned staging allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        ctx->pinned_out = nullptr;
+        return GASR_ERR_NOMEM;
+    }
+    ctx->pinned_out_bytes = bytes;
+    ctx->host_bytes += bytes;
+    return GASR_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace gasr
+
+using namespace gasr;
+
+#define GASR_ENTER(ctx)                                              \
+    if ((ctx) == nullptr) { set_error("null gasr_ctx"); return GASR_ERR_INVALID; } \
+    DeviceGuard guard__((ctx)->device)
+
+extern "C" {
+
+int gasr_version(void) { return 100; }
+const char *gasr_last_error(void) { return g_err; }
+
+int gasr_device_count(int *count) {
+    GASR_CHECK(count != nullptr, "gasr_device_count: null output");
+    *count = 0;
+    GASR_CUDA(cudaGetDeviceCount(count));
+    return GASR_OK;
+}
+
+int gasr_ctx_create(int device, gasr_ctx **out) {
+    GASR_CHECK(out != nullptr, "gasr_ctx_create: null output");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error("no usable CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+        return GASR_ERR_CUDA;
+    }
+    GASR_CHECK(device >= 0 && device < n, "gasr_ctx_create: device %d out of range (0..%d)", device, n - 1);
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    GASR_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return GASR_ERR_UNSUPPORTED;
+    }
+    gasr_ctx *ctx = new gasr_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    int cl = 0;
+    cudaDeviceGetAttribute(&cl, cudaDevAttrClusterLaunch, device);
+    ctx->cluster_ok = cl;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev_start) != cudaSuccess || cudaEventCreate(&ctx->ev_stop) != cudaSuccess) {
+        set_error("gasr_ctx_create: stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete ctx;
+        return GASR_ERR_CUDA;
+    }
+    for (int i = 0; i < 4; i++) cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking);
+    *out = ctx;
+    return GASR_OK;
+}
+
+int gasr_ctx_destroy(gasr_ctx *ctx) {
+    GASR_ENTER(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->dev_blocks) cudaFree(kv.first);
+    for (auto &kv : ctx->host_blocks) cudaFreeHost(kv.first);
+    Workspace *wss[] = {&ctx->ws_ctc, &ctx->ws_rnn, &ctx->ws_misc, &ctx->ws_out};
+    for (Workspace *w : wss) if (w->ptr) cudaFree(w->ptr);
+    if (ctx->pinned_out) cudaFreeHost(ctx->pinned_out);
+    for (int i = 0; i < 4; i++) if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+    cudaEventDestroy(ctx->ev_start);
+    cudaEventDestroy(ctx->ev_stop);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return GASR_OK;
+}
+
+int gasr_ctx_sync(gasr_ctx *ctx) {
+    GASR_ENTER(ctx);
+    GASR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GASR_OK;
+}
+
+int gasr_ctx_sm_count(gasr_ctx *ctx, int *sms) {
+    GASR_ENTER(ctx);
+    GASR_CHECK(sms != nullptr, "null output");
+    *sms = ctx->sm_count;
+    return GASR_OK;
+}
+
+int gasr_timer_start(gasr_ctx *ctx) {
+    GASR_ENTER(ctx);
+    GASR_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
+    return GASR_OK;
+}
+
+int gasr_timer_stop(gasr_ctx *ctx, float *ms) {
+    GASR_ENTER(ctx);
+    GASR_CHECK(ms != nullptr, "null output");
+    GASR_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
+    GASR_CUDA(cudaEventSynchronize(ctx->ev_stop));
+    GASR_CUDA(cudaEventElapsedTime(ms, ctx->ev_start, ctx->ev_stop));
+    return GASR_OK;
+}
+
+int gasr_ctx_launch_count(gasr_ctx *ctx, long long *launches) {
+    GASR_ENTER(ctx);
+    GASR_CHECK(launches != nullptr, "null output");
+    *launches = ctx->launches;
+    return GASR_OK;
+}
+
+/* ---- memory ---------------------------------------------------------------------------------------- */
+int gasr_malloc_device(gasr_ctx *ctx, size_t bytes, void **ptr) {
+    GASR_ENTER(ctx);
+    GASR_CHECK(ptr != nullptr, "gasr_malloc_device: null output");
+    *ptr = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e != cudaSuccess) {
+        set_error("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        *ptr = nullptr;
+        return GASR_ERR_NOMEM;
+    }
+    GASR_CUDA(cudaMemsetAsync(*ptr, 0, bytes, ctx->stream));
+    ctx->dev_blocks[*ptr] = bytes;
+    ctx->device_bytes += bytes;
+    return GASR_OK;
+}
+
+int gasr_free_device(gasr_ctx *ctx, void *ptr) {
+    GASR_ENTER(ctx);
+    auto it = ctx->dev_blocks.find(ptr);
+    if (it == ctx->dev_blocks.end()) return GASR_OK;   // MemoryMonitor::freeGpuMemory ignores unknown pointers
+    GASR_CUDA(cudaStreamSynchronize(ctx->stream));
+    GASR_CUDA(cudaFree(ptr));
+    ctx->device_bytes -= it->second;
+    ctx->dev_blocks.erase(it);
+    return GASR_OK;
+}
+
+int gasr_malloc_host(gasr_ctx *ctx, size_t bytes, void **ptr) {
+    GASR_ENTER(ctx);
+    GASR_CHECK(ptr != nullptr, "gasr_malloc_host: null output");
+    *ptr = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocPortable);   // MemoryMonitor.cpp:12
+    if (e != cudaSuccess) {
+        set_error("pinned host allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        *ptr = nullptr;
+        return GASR_ERR_NOMEM;
+    }
+    memset(*ptr, 0, bytes);
+    ctx->host_blocks[*ptr] = bytes;
+    ctx->host_bytes += bytes;
+    return GASR_OK;
+}
+
+int gasr_free_host(gasr_ctx *ctx, void *ptr) {
+    GASR_ENTER(ctx);
+    auto it = ctx->host_blocks.find(ptr);
+    if (it == ctx->host_blocks.end()) return GASR_OK;
+    GASR_CUDA(cudaStreamSynchronize(ctx->stream));
+    GASR_CUDA(cudaFreeHost(ptr));
+    ctx->host_bytes -= it->second;
+    ctx->host_blocks.erase(it);
+    return GASR_OK;
+}
+
+int gasr_matrix_alloc(gasr_ctx *ctx, int rows, int cols, int elem_bytes, void **dev, int *ld) {
+    GASR_CHECK(rows >= 0 && cols >= 0 && (elem_bytes == 1 || elem_bytes == 2 || elem_bytes == 4 || elem_bytes == 8) &&
+                   dev != nullptr && ld != nullptr, "gasr_matrix_alloc: bad arguments");
+    const int per16 = 16 / elem_bytes;
+    *ld = (cols + per16 - 1) / per16 * per16;
+    return gasr_malloc_device(ctx, (size_t)rows * (size_t)*ld * elem_bytes, dev);
+}
+
+int gasr_memcpy_h2d(gasr_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    GASR_ENTER(ctx);
+    GASR_CHECK(bytes == 0 || (dst && src), "gasr_memcpy_h2d: null pointer");
+    if (bytes == 0) return GASR_OK;
+    GASR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    GASR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GASR_OK;
+}
+
+int gasr_memcpy_d2h(gasr_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    GASR_ENTER(ctx);
+    GASR_CHECK(bytes == 0 || (dst && src), "gasr_memcpy_d2h: null pointer");
+    if (bytes == 0) return GASR_OK;
+    GASR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    GASR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GASR_OK;
+}
+
+int gasr_memcpy_h2d_async(gasr_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    GASR_ENTER(ctx);
+    GASR_CHECK(bytes == 0 || (dst && src), "gasr_memcpy_h2d_async: null pointer");
+    if (bytes == 0) return GASR_OK;
+    GASR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return GASR_OK;
+}
+
+int gasr_memcpy_d2h_async(gasr_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    GASR_ENTER(ctx);
+    GASR_CHECK(bytes == 0 || (dst && src), "gasr_memcpy_d2h_async: null pointer");
+    if (bytes == 0) return GASR_OK;
+    GASR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return GASR_OK;
+}
+
+int gasr_memset_device(gasr_ctx *ctx, void *dst, int value, size_t bytes) {
+    GASR_ENTER(ctx);
+    GASR_CHECK(bytes == 0 || dst, "gasr_memset_device: null pointer");
+    if (bytes == 0) return GASR_OK;
+    GASR_CUDA(cudaMemsetAsync(dst, value, bytes, ctx->stream));
+    return GASR_OK;
+}
+
+int gasr_memory_stats(gasr_ctx *ctx, size_t *device_bytes, size_t *host_bytes) {
+    GASR_ENTER(ctx);
+    if (device_bytes) *device_bytes = ctx->device_bytes;
+    if (host_bytes) *host_bytes = ctx->host_bytes;
+    return GASR_OK;
+}
+
+/* ---- dense math -------------------------------------------------------------------------------------- */
+int gasr_matmul(gasr_ctx *ctx, const float *x, int ldx, int trans_x, const float *y, int ldy, int trans_y, float *z,
+                int ldz, int m, int k, int n) {
+    GASR_ENTER(ctx);
+    return launch_matmul(ctx, x, ldx, trans_x, y, ldy, trans_y, z, ldz, m, k, n, nullptr, ctx->stream);
+}
+
+int gasr_matadd(gasr_ctx *ctx, const float *x, int ldx, const float *y, int ldy, float *z, int ldz, int rows, int cols,
+                float lambda) {
+    GASR_ENTER(ctx);
+    return launch_matadd(ctx, x, ldx, y, ldy, z, ldz, rows, cols, lambda, ctx->stream);
+}
+
+int gasr_linear_forward(gasr_ctx *ctx, const float *x, int ldx, const float *W, const float *b, float *y, int ldy,
+                        int rows, int in, int out, int act) {
+    GASR_ENTER(ctx);
+    return launch_linear(ctx, x, ldx, W, b, y, ldy, rows, in, out, act, ctx->stream);
+}
+
+int gasr_log_softmax(gasr_ctx *ctx, const float *x, int ldx, float *y, int ldy, int rows, int cols) {
+    GASR_ENTER(ctx);
+    return launch_log_softmax(ctx, x, ldx, y, ldy, rows, cols, ctx->stream);
+}
+
+int gasr_rnn_cell_forward(gasr_ctx *ctx, const float *x, const float *h_prev, const float *w_ih, const float *w_hh,
+                          const float *b_ih, const float *b_hh, float *out, int batch, int in, int hidden) {
+    GASR_ENTER(ctx);
+    return launch_rnn_cell(ctx, x, h_prev, w_ih, w_hh, b_ih, b_hh, out, batch, in, hidden, ctx->stream);
+}
+
+}  // extern "C"
+
+namespace gasr {
+
+// One layer, one direction: xproj = src*W_ih + bias (all timesteps), then the persistent recurrence.
+static int rnn_layer_direction(gasr_ctx *ctx, int cell, int T, int N, int in_l, int H, const float *src, int ld_src,
+                               const float *w_ih, const float *w_hh, const float *b_ih, const float *b_hh, int reverse,
+                               float *out, int ldo, int col0, int precision, float *xproj, float *bias,
+                               cudaStream_t st) {
+    (void)precision;
+    const int G = cell == GASR_CELL_GRU ? 3 : 1;
+    if (cell == GASR_CELL_TANH) {
+        GASR_TRY(launch_matadd(ctx, b_ih, H, b_hh, H, bias, H, 1, H, 1.0f, st));   // (b_hh + b_ih), RNN_Cell.cu:10
+    } else {
+        GASR_CUDA(cudaMemcpyAsync(bias, b_ih, sizeof(float) * G * H, cudaMemcpyDeviceToDevice, st));
+    }
+    GASR_TRY(launch_matmul(ctx, src, ld_src, 0, w_ih, G * H, 0, xproj, G * H, T * N, in_l, G * H, bias, st));
+    RnnLayerArgs a;
+    a.cell = cell; a.T = T; a.N = N; a.H = H; a.reverse = reverse;
+    a.xproj = xproj; a.ldxp = G * H; a.w_hh = w_hh; a.b_hh = b_hh; a.out = out; a.ldo = ldo; a.col0 = col0;
+    return launch_rnn_recurrence(ctx, a, st);
+}
+
+int rnn_forward_impl(gasr_ctx *ctx, int cell, int bidir, int T, int N, int in, int H, int L, const float *const *w_ih,
+                     const float *const *w_hh, const float *const *b_ih, const float *const *b_hh, const float *x,
+                     float *const *hiddens, int precision, cudaStream_t st) {
+    GASR_CHECK(cell == GASR_CELL_TANH || cell == GASR_CELL_GRU, "rnn_forward: unknown cell type %d", cell);
+    GASR_CHECK(T >= 0 && N >= 0 && in >= 1 && H >= 1 && L >= 1, "rnn_forward: bad shape");
+    GASR_CHECK(w_ih && w_hh && b_ih && b_hh && x && hiddens, "rnn_forward: null argument");
+    GASR_CHECK((long long)T * N < (1ll << 31) / 4, "rnn_forward: T*N too large");
+    const int D = bidir ? 2 : 1, G = cell == GASR_CELL_GRU ? 3 : 1;
+    if (T == 0 || N == 0) return GASR_OK;
+    const size_t xp_bytes = align_up(sizeof(float) * (size_t)T * N * G * H, 256);
+    GASR_TRY(ws_reserve(ctx, ctx->ws_rnn, xp_bytes + align_up(sizeof(float) * G * H, 256)));
+    float *xproj = static_cast<float *>(ctx->ws_rnn.ptr);
+    float *bias = reinterpret_cast<float *>(static_cast<unsigned char *>(ctx->ws_rnn.ptr) + xp_bytes);
+    for (int l = 0; l < L; l++) {
+        const int in_l = l == 0 ? in : D * H;
+        const float *src = l == 0 ? x : hiddens[l - 1];
+        for (int d = 0; d < D; d++) {
+            const int i = l * D + d;
+            GASR_CHECK(w_ih[i] && w_hh[i] && b_ih[i] && b_hh[i] && hiddens[l], "rnn_forward: null layer parameter");
+            GASR_TRY(rnn_layer_direction(ctx, cell, T, N, in_l, H, src, in_l, w_ih[i], w_hh[i], b_ih[i], b_hh[i], d,
+                                         hiddens[l], D * H, d * H, precision, xproj, bias, st));
+        }
+    }
+    return GASR_OK;
+}
+
+}  // namespace gasr
+
+extern "C" {
+
+int gasr_rnn_forward(gasr_ctx *ctx, int cell, int bidirectional, int T, int N, int in, int H, int L,
+                     const float *const *w_ih, const float *const *w_hh, const float *const *b_ih,
+                     const float *const *b_hh, const float *x, float *const *hiddens, int precision) {
+    GASR_ENTER(ctx);
+    return rnn_forward_impl(ctx, cell, bidirectional, T, N, in, H, L, w_ih, w_hh, b_ih, b_hh, x, hiddens, precision,
+                            ctx->stream);
+}
+
+int gasr_ctc_decode(gasr_ctx *ctx, const float *scores, int domain, int T, int N, int V, int ld, int beam, int blank,
+                    const char *vocab, int max_len, int nbest, char *out_paths, int *out_lens, float *out_scores,
+                    int *out_counts) {
+    GASR_ENTER(ctx);
+    GASR_CHECK(out_paths && out_lens && out_scores, "ctc_decode: null output buffer");
+    CtcArgs a = {scores, domain, T, N, V, ld, beam, blank, vocab, max_len, nbest, out_paths, out_lens, out_scores, out_counts};
+    GASR_TRY(ctc_decode_launch(ctx, a, ctx->stream));
+    GASR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ctc_decode_finish(ctx, a);
+}
+
+int gasr_ctc_decode_host(gasr_ctx *ctx, const float *scores_host, int domain, int T, int N, int V, int beam, int blank,
+                         const char *vocab, int max_len, int nbest, char *out_paths, int *out_lens, float *out_scores,
+                         int *out_counts) {
+    GASR_ENTER(ctx);
+    GASR_CHECK(scores_host != nullptr && T >= 1 && N >= 0 && V >= 1, "ctc_decode_host: bad arguments");
+    const size_t bytes = sizeof(float) * (size_t)T * N * V;
+    GASR_TRY(ws_reserve(ctx, ctx->ws_misc, bytes + 256));
+    GASR_CUDA(cudaMemcpyAsync(ctx->ws_misc.ptr, scores_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return gasr_ctc_decode(ctx, static_cast<const float *>(ctx->ws_misc.ptr), domain, T, N, V, V, beam, blank, vocab,
+                           max_len, nbest, out_paths, out_lens, out_scores, out_counts);
+}
+
+}  // extern "C"
+
+/* ---- fused pipeline ------------------------------------------------------------------------------------ */
+struct gasr_asr {
+    gasr_ctx *ctx = nullptr;
+    gasr_asr_config cfg;
+    std::vector<char> vocab;
+    int D = 1, G = 1, ldp = 0;
+    std::vector<float *> w_ih, w_hh, b_ih, b_hh, hiddens;
+    float *fc_w = nullptr, *fc_b = nullptr, *x_dev = nullptr, *logp = nullptr;
+    bool have_weights = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float stage_ms[4] = {0, 0, 0, 0};
+};
+
+extern "C" {
+
+int gasr_asr_create(gasr_ctx *ctx, const gasr_asr_config *cfg, const char *vocab, gasr_asr **out) {
+    GASR_ENTER(ctx);
+    GASR_CHECK(cfg && vocab && out, "gasr_asr_create: null argument");
+    GASR_CHECK(cfg->T >= 1 && cfg->N >= 1 && cfg->in >= 1 && cfg->H >= 1 && cfg->L >= 1 && cfg->V >= 1 &&
+                   cfg->beam >= 1 && cfg->blank >= 0 && cfg->blank < cfg->V && cfg->nbest >= 1 && cfg->max_len >= 0,
+               "gasr_asr_create: bad configuration");
+    GASR_CHECK(cfg->cell == GASR_CELL_TANH || cfg->cell == GASR_CELL_GRU, "gasr_asr_create: unknown cell");
+    gasr_asr *a = new gasr_asr();
+    a->ctx = ctx; a->cfg = *cfg;
+    a->vocab.assign(vocab, vocab + cfg->V);
+    a->D = cfg->bidirectional ? 2 : 1;
+    a->G = cfg->cell == GASR_CELL_GRU ? 3 : 1;
+    a->ldp = (cfg->V + 3) / 4 * 4;
+    const int D = a->D, G = a->G, H = cfg->H;
+    const size_t rows = (size_t)cfg->T * cfg->N;
+    int st = GASR_OK;
+    auto alloc = [&](float **p, size_t n) { if (st == GASR_OK) st = gasr_malloc_device(ctx, sizeof(float) * n, (void **)p); };
+    a->w_ih.assign(cfg->L * D, nullptr); a->w_hh.assign(cfg->L * D, nullptr);
+    a->b_ih.assign(cfg->L * D, nullptr); a->b_hh.assign(cfg->L * D, nullptr);
+    a->hiddens.assign(cfg->L, nullptr);
+    for (int l = 0; l < cfg->L; l++) {
+        const int in_l = l == 0 ? cfg->in : D * H;
+        for (int d = 0; d < D; d++) {
+            alloc(&a->w_ih[l * D + d], (size_t)in_l * G * H);
+            alloc(&a->w_hh[l * D + d], (size_t)H * G * H);
+            alloc(&a->b_ih[l * D + d], (size_t)G * H);
+            alloc(&a->b_hh[l * D + d], (size_t)G * H);
+        }
+        alloc(&a->hiddens[l], rows * D * H);
+    }
+    alloc(&a->fc_w, (size_t)D * H * cfg->V);
+    alloc(&a->fc_b, (size_t)cfg->V);
+    alloc(&a->x_dev, rows * cfg->in);
+    alloc(&a->logp, rows * a->ldp);
+    for (int i = 0; i < 5 && st == GASR_OK; i++)
+        if (cudaEventCreate(&a->ev[i]) != cudaSuccess) { set_error("event creation failed"); st = GASR_ERR_CUDA; }
+    if (st != GASR_OK) { gasr_asr_destroy(a); return st; }
+    *out = a;
+    return GASR_OK;
+}
+
+int gasr_asr_destroy(gasr_asr *a) {
+    if (a == nullptr) return GASR_OK;
+    gasr_ctx *ctx = a->ctx;
+    GASR_ENTER(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto v : {&a->w_ih, &a->w_hh, &a->b_ih, &a->b_hh, &a->hiddens})
+        for (float *p : *v) if (p) gasr_free_device(ctx, p);
+    for (float *p : {a->fc_w, a->fc_b, a->x_dev, a->logp}) if (p) gasr_free_device(ctx, p);
+    for (int i = 0; i < 5; i++) if (a->ev[i]) cudaEventDestroy(a->ev[i]);
+    delete a;
+    return GASR_OK;
+}
+
+int gasr_asr_set_weights(gasr_asr *a, const float *const *w_ih, const float *const *w_hh, const float *const *b_ih,
+                         const float *const *b_hh, const float *fc_w, const float *fc_b) {
+    GASR_CHECK(a != nullptr, "null gasr_asr");
+    gasr_ctx *ctx = a->ctx;
+    GASR_ENTER(ctx);
+    GASR_CHECK(w_ih && w_hh && b_ih && b_hh && fc_w && fc_b, "gasr_asr_set_weights: null argument");
+    const gasr_asr_config &c = a->cfg;
+    const int D = a->D, G = a->G, H = c.H;
+    for (int l = 0; l < c.L; l++) {
+        const int in_l = l == 0 ? c.in : D * H;
+        for (int d = 0; d < D; d++) {
+            const int i = l * D + d;
+            GASR_CHECK(w_ih[i] && w_hh[i] && b_ih[i] && b_hh[i], "gasr_asr_set_weights: null layer parameter %d", i);
+            GASR_TRY(gasr_memcpy_h2d(ctx, a->w_ih[i], w_ih[i], sizeof(float) * in_l * G * H));
+            GASR_TRY(gasr_memcpy_h2d(ctx, a->w_hh[i], w_hh[i], sizeof(float) * H * G * H));
+            GASR_TRY(gasr_memcpy_h2d(ctx, a->b_ih[i], b_ih[i], sizeof(float) * G * H));
+            GASR_TRY(gasr_memcpy_h2d(ctx, a->b_hh[i], b_hh[i], sizeof(float) * G * H));
+        }
+    }
+    GASR_TRY(gasr_memcpy_h2d(ctx, a->fc_w, fc_w, sizeof(float) * D * H * c.V));
+    GASR_TRY(gasr_memcpy_h2d(ctx, a->fc_b, fc_b, sizeof(float) * c.V));
+    a->have_weights = true;
+    return GASR_OK;
+}
+
+int gasr_asr_run_device(gasr_asr *a, const float *x_dev, char *out_paths, int *out_lens, float *out_scores) {
+    GASR_CHECK(a != nullptr, "null gasr_asr");
+    gasr_ctx *ctx = a->ctx;
+    GASR_ENTER(ctx);
+    GASR_CHECK(a->have_weights, "gasr_asr_run: weights not set");
+    GASR_CHECK(x_dev && out_paths && out_lens && out_scores, "gasr_asr_run: null argument");
+    const gasr_asr_config &c = a->cfg;
+    cudaStream_t st = ctx->stream;
+    const int rows = c.T * c.N;
+    GASR_CUDA(cudaEventRecord(a->ev[0], st));
+    GASR_TRY(rnn_forward_impl(ctx, c.cell, c.bidirectional, c.T, c.N, c.in, c.H, c.L, a->w_ih.data(), a->w_hh.data(),
+                              a->b_ih.data(), a->b_hh.data(), x_dev, a->hiddens.data(), c.precision, st));
+    GASR_CUDA(cudaEventRecord(a->ev[1], st));
+    GASR_TRY(launch_linear(ctx, a->hiddens[c.L - 1], a->D * c.H, a->fc_w, a->fc_b, a->logp, a->ldp, rows, a->D * c.H,
+                           c.V, GASR_ACT_LOGSOFTMAX, st));
+    GASR_CUDA(cudaEventRecord(a->ev[2], st));
+    CtcArgs ca = {a->logp, GASR_DOMAIN_LOG, c.T, c.N, c.V, a->ldp, c.beam, c.blank, a->vocab.data(), c.max_len,
+                  c.nbest, out_paths, out_lens, out_scores, nullptr};
+    GASR_TRY(ctc_decode_launch(ctx, ca, st));
+    GASR_CUDA(cudaEventRecord(a->ev[3], st));
+    GASR_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a->ev[0], a->ev[1]); a->stage_ms[0] = 0; a->stage_ms[1] = ms;
+    cudaEventElapsedTime(&ms, a->ev[1], a->ev[2]); a->stage_ms[2] = ms;
+    cudaEventElapsedTime(&ms, a->ev[2], a->ev[3]); a->stage_ms[3] = ms;
+    return ctc_decode_finish(ctx, ca);
+}
+
+int gasr_asr_run_host(gasr_asr *a, const float *x_host, char *out_paths, int *out_lens, float *out_scores) {
+    GASR_CHECK(a != nullptr, "null gasr_asr");
+    gasr_ctx *ctx = a->ctx;
+    GASR_ENTER(ctx);
+    GASR_CHECK(x_host != nullptr, "gasr_asr_run_host: null input");
+    const gasr_asr_config &c = a->cfg;
+    GASR_CUDA(cudaMemcpyAsync(a->x_dev, x_host, sizeof(float) * (size_t)c.T * c.N * c.in, cudaMemcpyHostToDevice,
+                              ctx->stream));
+    return gasr_asr_run_device(a, a->x_dev, out_paths, out_lens, out_scores);
+}
+
+int gasr_asr_logprobs(gasr_asr *a, const float **logp_dev, int *ldp) {
+    GASR_CHECK(a && logp_dev && ldp, "gasr_asr_logprobs: null argument");
+    *logp_dev = a->logp;
+    *ldp = a->ldp;
+    return GASR_OK;
+}
+
+int gasr_asr_stage_times(gasr_asr *a, float *ms4) {
+    GASR_CHECK(a && ms4, "gasr_asr_stage_times: null argument");
+    for (int i = 0; i < 4; i++) ms4[i] = a->stage_ms[i];
+    return GASR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+// common.cuh -- context, error plumbing and launch helpers shared by the kernels of libgasr.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <map>
+#include <string>
+
+#include "gasr.h"
+
+namespace gasr {
+
+void set_error(const char *fmt, ...);
+
+#define GASR_CUDA(expr)                                                                          \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            gasr::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return GASR_ERR_CUDA;                                                                \
+        }                                                                                        \
+    } while (0)
+
+#define GASR_CHECK(cond, ...)                                                                    \
+    do {                                                                                         \
+        if (!(cond)) {                                                                           \
+            gasr::set_error(__VA_ARGS__);                                                        \
+            return GASR_ERR_INVALID;                                                             \
+        }                                                                                        \
+    } while (0)
+
+#define GASR_TRY(expr)                                                                           \
+    do {                                                                                         \
+        int s__ = (expr);                                                                        \
+        if (s__ != GASR_OK) return s__;                                                          \
+    } while (0)
+
+// A grow-only device scratch block (reused across calls; freed with the ctx).
+struct Workspace {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace gasr
+
+struct gasr_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    int cluster_ok = 0;
+    cudaStream_t stream = nullptr;       // main stream: every kernel of the C ABI is launched here
+    cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};  // pipeline side streams
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    long long launches = 0;
+    size_t device_bytes = 0, host_bytes = 0;
+    std::map<void *, size_t> dev_blocks, host_blocks;
+    gasr::Workspace ws_ctc, ws_rnn, ws_misc, ws_out;
+    void *pinned_out = nullptr;          // pinned staging for decode results
+    size_t pinned_out_bytes = 0;
+};
+
+namespace gasr {
+
+int ws_reserve(gasr_ctx *ctx, Workspace &ws, size_t bytes);
+int pinned_reserve(gasr_ctx *ctx, size_t bytes);
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// kernels (one translation unit each) -----------------------------------------------------------------
+int launch_matmul(gasr_ctx *ctx, const float *x, int ldx, int tx, const float *y, int ldy, int ty, float *z, int ldz,
+                  int m, int k, int n, const float *bias, cudaStream_t st);
+int launch_matadd(gasr_ctx *ctx, const float *x, int ldx, const float *y, int ldy, float *z, int ldz, int rows,
+                  int cols, float lambda, cudaStream_t st);
+int launch_linear(gasr_ctx *ctx, const float *x, int ldx, const float *W, const float *b, float *y, int ldy, int rows,
+                  int in, int out, int act, cudaStream_t st);
+int launch_log_softmax(gasr_ctx *ctx, const float *x, int ldx, float *y, int ldy, int rows, int cols, cudaStream_t st);
+int launch_rnn_cell(gasr_ctx *ctx, const float *x, const float *h_prev, const float *w_ih, const float *w_hh,
+                    const float *b_ih, const float *b_hh, float *out, int batch, int in, int hidden, cudaStream_t st);
+
+struct RnnLayerArgs {
+    int cell, T, N, H, reverse;
+    const float *xproj;   // [T*N, ldxp]: x*W_ih + (b_ih [+ b_hh for tanh]) for this direction
+    int ldxp;
+    const float *w_hh;    // [H, G*H]
+    const float *b_hh;    // [G*H] (GRU only: b_hn stays inside the reset product)
+    float *out;           // [T*N, ldo] written at column offset col0
+    int ldo, col0;
+};
+int launch_rnn_recurrence(gasr_ctx *ctx, const RnnLayerArgs &a, cudaStream_t st);
+
+struct CtcArgs {
+    const float *scores; int domain, T, N, V, ld, beam, blank; const char *vocab_host; int max_len, nbest;
+    char *out_paths; int *out_lens; float *out_scores; int *out_counts;   // host
+};
+int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st);   // enqueue kernel + D2H into pinned staging
+int ctc_decode_finish(gasr_ctx *ctx, const CtcArgs &a);                    // after stream sync: unpack to caller buffers
+
+}  // namespace gasr

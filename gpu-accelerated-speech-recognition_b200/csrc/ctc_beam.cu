@@ -1,0 +1,528 @@
+// ctc_beam.cu -- CTC prefix beam search, one CTA per utterance, candidates resident in shared memory.
+//
+// Stands behind CTCBeamSearch::decode (reference CTCBeamSearch.cu:262-312) and implements the CTC-REF
+// contract of SURVEY.md 8c / DESIGN.md: the reference's extension rules (CTCBeamSearch.cu:404-458), merge of
+// equal paths (:460-489) with the summation order fixed to ascending (raw string, candidate index), stable
+// descending prune (:174-196, :103-112), result = rank-0 state (:290-298).
+//
+// What is different from the reference's ~40 launches + Thrust sorts per frame:
+//   * a kept state is (X, eb) = (label prefix, ends-in-blank); X is a node of a per-utterance prefix trie in HBM
+//     (parent / char / depth + a child table so node ids are canonical over time) -- no 264-byte BeamState,
+//     no string sort, no 31-hash (equal paths merge by identity, never by hash collision);
+//   * duplicates are found structurally: a candidate can only coincide with its twin state's candidate
+//     ((X,0) and (X,1)) or with the "stay" candidate of a kept child state, so every merged candidate is
+//     produced once, by one thread, with its <=3 (<=5 on the last frame) addends summed in canonical order;
+//   * prune = one in-shared-memory bitonic sort of 64-bit keys (ordered score | ~candidate index); exact score
+//     ties are re-ordered by raw-string order (trie walk to the lowest common ancestor), as the reference's
+//     stable sort on top of the string sort does.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace gasr {
+
+// Deterministic fp32 log-add-exp (DESIGN.md "log-add-exp"): only correctly rounded IEEE operations, so the CPU
+// oracle evaluates the same bits.
+__device__ __forceinline__ float logaddexp_det(float a, float b) {
+    const float mx = a > b ? a : b;
+    const float mn = a > b ? b : a;
+    if (mn == -INFINITY) return mx;
+    const float d = __fsub_rn(mn, mx);
+    if (d < -17.5f) return mx;
+    const float n = rintf(__fmul_rn(d, 1.44269504088896341f));
+    float r = __fmaf_rn(n, -0.693359375f, d);
+    r = __fmaf_rn(n, 2.12194440e-4f, r);
+    float p = 1.9875691500e-4f;
+    p = __fmaf_rn(p, r, 1.3981999507e-3f);
+    p = __fmaf_rn(p, r, 8.3334519073e-3f);
+    p = __fmaf_rn(p, r, 4.1665795894e-2f);
+    p = __fmaf_rn(p, r, 1.6666665459e-1f);
+    p = __fmaf_rn(p, r, 5.0000001201e-1f);
+    const float r2 = __fmul_rn(r, r);
+    const float ex = __fadd_rn(__fmaf_rn(p, r2, r), 1.0f);
+    const float scale = __int_as_float(((int)n + 127) << 23);
+    const float e = __fmul_rn(ex, scale);
+    const float t = __fdiv_rn(e, __fadd_rn(2.0f, e));
+    const float w = __fmul_rn(t, t);
+    float q = 1.0f / 13.0f;
+    q = __fmaf_rn(q, w, 1.0f / 11.0f);
+    q = __fmaf_rn(q, w, 1.0f / 9.0f);
+    q = __fmaf_rn(q, w, 1.0f / 7.0f);
+    q = __fmaf_rn(q, w, 1.0f / 5.0f);
+    q = __fmaf_rn(q, w, 1.0f / 3.0f);
+    q = __fmaf_rn(q, w, 1.0f);
+    const float l = __fmul_rn(__fmul_rn(2.0f, t), q);
+    return __fadd_rn(mx, l);
+}
+
+// order-preserving float -> uint32 (larger float => larger key); every real score maps to a key > 0
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+struct CtcParams {
+    const float *scores;
+    int T, N, V, ld, beam, blank;
+    int Vp;        // child-table row pitch (ints)
+    int n_pad;     // power of two >= beam * V
+    int cap;       // trie nodes per utterance
+    int max_len, nbest;
+    const char *vocab;   // device copy
+    int *parent;         // [N, cap]
+    int *meta;           // [N, cap]  depth << 8 | vocab id of the node's last label
+    int *child;          // [N, cap, Vp] 0 = absent
+    char *out_paths;     // [N, nbest, max_len]
+    int *out_lens;       // [N, nbest]
+    float *out_scores;   // [N, nbest]
+    int *out_counts;     // [N]
+};
+
+constexpr int kNone = -1;
+constexpr uint16_t kNoRedir = 0xffffu;
+
+struct BeamView {
+    float *score;
+    int *node;
+    int *pnode;
+    short *last;          // vocab id of the last label of X, -1 for the empty prefix
+    unsigned char *eb;    // 1 = raw path ends in the blank
+};
+
+template <int DOMAIN>
+__device__ __forceinline__ float comb(float s, float p) {
+    return DOMAIN ? __fadd_rn(s, p) : __fmul_rn(s, p);
+}
+template <int DOMAIN>
+__device__ __forceinline__ float mrg(float a, float b) {
+    return DOMAIN ? logaddexp_det(a, b) : __fadd_rn(a, b);
+}
+
+// raw-string order of two candidates = (trie node, optional suffix char): walk both up to the lowest common
+// ancestor and compare the first characters after it (reference operator<, CTCBeamSearch.cu:137-147).
+__device__ bool raw_less(const int *__restrict__ parent, const int *__restrict__ meta, const char *vocab, int na,
+                         int sufa, int nb, int sufb) {
+    int da = meta[na] >> 8, db = meta[nb] >> 8;
+    const int lena = da + (sufa ? 1 : 0), lenb = db + (sufb ? 1 : 0);
+    int a = na, b = nb, la = 0, lb = 0;  // la/lb: char stepped over last (0 = never stepped)
+    while (da > db) { la = vocab[meta[a] & 0xff]; a = parent[a]; da--; }
+    while (db > da) { lb = vocab[meta[b] & 0xff]; b = parent[b]; db--; }
+    while (a != b) {
+        la = vocab[meta[a] & 0xff]; a = parent[a];
+        lb = vocab[meta[b] & 0xff]; b = parent[b];
+        da--;
+    }
+    const int ca = la ? la : sufa, cb = lb ? lb : sufb;   // 0 = end of string
+    if (ca != cb) return (signed char)ca < (signed char)cb;
+    if (ca == 0) return false;
+    // same char right after the common ancestor: the string that ends there is a prefix of the other
+    const int end = da + 1;
+    return lena == end && lenb > end;
+}
+
+template <int DOMAIN, int MAXT>
+__global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int utt = blockIdx.x;
+    const int V = p.V, B = p.beam, blank = p.blank, Vp = p.Vp, n_pad = p.n_pad;
+
+    // ---- shared-memory carve-up --------------------------------------------------------------------
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);
+    unsigned char *sp = smem_raw + sizeof(unsigned long long) * n_pad;
+    float *lp = reinterpret_cast<float *>(sp); sp += sizeof(float) * Vp;
+    float *sc2 = reinterpret_cast<float *>(sp); sp += sizeof(float) * 2 * B;
+    int *node2 = reinterpret_cast<int *>(sp); sp += sizeof(int) * 2 * B;
+    int *pnode2 = reinterpret_cast<int *>(sp); sp += sizeof(int) * 2 * B;
+    int *newflag = reinterpret_cast<int *>(sp); sp += sizeof(int) * B;
+    short *twin = reinterpret_cast<short *>(sp); sp += sizeof(short) * B;
+    short *P0 = reinterpret_cast<short *>(sp); sp += sizeof(short) * B;
+    short *P1 = reinterpret_cast<short *>(sp); sp += sizeof(short) * B;
+    short *last2 = reinterpret_cast<short *>(sp); sp += sizeof(short) * 2 * B;
+    uint16_t *redir0 = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * B * V;
+    uint16_t *redir1 = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * B * V;
+    char *vch = reinterpret_cast<char *>(sp); sp += (V + 3) / 4 * 4;
+    unsigned char *eb2 = sp; sp += 2 * B;
+    // the two beam buffers (current / next) are halves of the arrays above; no dynamically indexed struct array
+    auto beam_view = [&](int w) {
+        BeamView v;
+        v.score = sc2 + w * B; v.node = node2 + w * B; v.pnode = pnode2 + w * B; v.last = last2 + w * B;
+        v.eb = eb2 + w * B;
+        return v;
+    };
+    __shared__ int s_kept, s_nodes, s_tie;
+
+    int *parent = p.parent + (size_t)utt * p.cap;
+    int *meta = p.meta + (size_t)utt * p.cap;
+    int *child = p.child + (size_t)utt * p.cap * Vp;
+    const float *S = p.scores + (size_t)utt * p.ld;
+    const size_t frame_stride = (size_t)p.N * p.ld;
+
+    // ---- init: one virtual parent (empty prefix, "ends in blank", unit score); frame 0 then yields the
+    //      reference's t = 0 states (kernelInitialPath, CTCBeamSearch.cu:337-364) -------------------------
+    for (int v = tid; v < V; v += NT) vch[v] = p.vocab[v];
+    for (int v = tid; v < Vp; v += NT) child[v] = 0;   // root's child row
+    if (tid == 0) {
+        parent[0] = -1; meta[0] = 0 | 0xff;
+        sc2[0] = DOMAIN ? 0.0f : 1.0f;
+        node2[0] = 0; pnode2[0] = kNone; last2[0] = -1; eb2[0] = 1;
+        s_kept = 1; s_nodes = 1;
+    }
+    float next_lp = 0.0f;
+    if (tid < V) next_lp = S[tid];
+    __syncthreads();
+
+    int cur = 0;
+    for (int t = 0; t < p.T; t++) {
+        const BeamView st = beam_view(cur), nx = beam_view(cur ^ 1);
+        const int k = s_kept;
+        const int ncand = k * V;
+        const bool last_frame = (t == p.T - 1) && (t > 0);
+
+        // ---- A: this frame's scores to smem, prefetch the next row, beam-level relations ----------------
+        if (tid < V) {
+            lp[tid] = next_lp;
+            if (t + 1 < p.T) next_lp = S[(size_t)(t + 1) * frame_stride + tid];
+        }
+        for (int c = tid; c < ncand; c += NT) { redir0[c] = kNoRedir; redir1[c] = kNoRedir; }
+        if (tid == 0) s_tie = 0;
+        if (tid < k) {
+            const int nd = st.node[tid], pn = st.pnode[tid];
+            int tw = kNone, p0 = kNone, p1 = kNone;
+            for (int j = 0; j < k; j++) {
+                const int nj = st.node[j];
+                if (nj == nd && j != tid) tw = j;
+                if (nj == pn) { if (st.eb[j]) p1 = j; else p0 = j; }
+            }
+            twin[tid] = (short)tw; P0[tid] = (short)p0; P1[tid] = (short)p1;
+        }
+        __syncthreads();
+        // ---- B: kept child states claim the extend candidates that land on them --------------------------
+        if (tid < k && st.last[tid] >= 0) {
+            const int lv = st.last[tid];
+            uint16_t *rd = st.eb[tid] ? redir1 : redir0;
+            if (P0[tid] >= 0) rd[P0[tid] * V + lv] = (uint16_t)tid;
+            if (P1[tid] >= 0) rd[P1[tid] * V + lv] = (uint16_t)tid;
+        }
+        __syncthreads();
+        // ---- C: merged candidates -> sort keys ------------------------------------------------------------
+        for (int c = tid; c < n_pad; c += NT) {
+            unsigned long long key = 0ull;
+            if (c < ncand) {
+                const int i = c / V, v = c - i * V;
+                const float pv = lp[v];
+                const float s = comb<DOMAIN>(st.score[i], pv);
+                const int tw = twin[i];
+                const int ebi = st.eb[i], lasti = st.last[i];
+                bool host = true;
+                float acc = s;
+                if (v == blank) {
+                    if (!last_frame) {
+                        if (tw >= 0) {
+                            if (tw < i) host = false;
+                            else acc = mrg<DOMAIN>(s, comb<DOMAIN>(st.score[tw], pv));
+                        }
+                    } else {
+                        if (ebi == 0 || tw >= 0) host = false;   // the (X,0) "stay" slot hosts the whole group
+                        else if (lasti >= 0) {
+                            const int p0 = P0[i], p1 = P1[i];
+                            if (p1 >= 0 || (p0 >= 0 && st.last[p0] != lasti)) host = false;  // an extend slot hosts
+                        }
+                    }
+                } else if (ebi == 0 && v == lasti) {
+                    // stay on X: plus the extends of X's parent states that spell X again
+                    int m0 = P0[i], m1 = P1[i], m2 = i;
+                    if (m0 >= 0 && st.last[m0] == v) m0 = kNone;   // (P,0)+v with last(P)==v stays on P
+                    // ascending state index == ascending candidate index (same v)
+                    int a0 = m0, a1 = m1, a2 = m2, tmp;
+                    if (a0 > a1) { tmp = a0; a0 = a1; a1 = tmp; }
+                    if (a1 > a2) { tmp = a1; a1 = a2; a2 = tmp; }
+                    if (a0 > a1) { tmp = a0; a0 = a1; a1 = tmp; }
+                    bool have = false;
+                    acc = 0.0f;
+                    const int order[3] = {a0, a1, a2};
+#pragma unroll
+                    for (int q = 0; q < 3; q++) {
+                        const int j = order[q];
+                        if (j < 0) continue;
+                        const float sj = comb<DOMAIN>(st.score[j], pv);
+                        acc = have ? mrg<DOMAIN>(acc, sj) : sj;
+                        have = true;
+                    }
+                    if (last_frame) {
+                        const float pb = lp[blank];
+                        int b0 = i, b1 = tw;
+                        if (b1 >= 0 && b1 < b0) { b0 = tw; b1 = i; }
+                        acc = mrg<DOMAIN>(acc, comb<DOMAIN>(st.score[b0], pb));
+                        if (b1 >= 0) acc = mrg<DOMAIN>(acc, comb<DOMAIN>(st.score[b1], pb));
+                    }
+                } else {
+                    // extend to X.v
+                    if (redir0[c] != kNoRedir) host = false;         // kept state (X.v, 0) hosts it
+                    else {
+                        const bool tw_member = (tw >= 0) && (st.eb[tw] == 1 || v != st.last[tw]);
+                        if (tw_member) {
+                            if (tw < i) host = false;
+                            else acc = mrg<DOMAIN>(s, comb<DOMAIN>(st.score[tw], pv));
+                        }
+                        if (host && last_frame) {
+                            const int j = redir1[c];                 // kept (X.v, 1): its blank candidate strips to X.v
+                            if (j != kNoRedir) acc = mrg<DOMAIN>(acc, comb<DOMAIN>(st.score[j], lp[blank]));
+                        }
+                    }
+                }
+                if (host) key = ((unsigned long long)f2ord(acc) << 32) | (unsigned)(0xffffffffu - (unsigned)c);
+            }
+            keys[c] = key;
+        }
+        __syncthreads();
+        // ---- D: bitonic sort, descending ------------------------------------------------------------------
+        for (int size = 2; size <= n_pad; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int idx = tid; idx < (n_pad >> 1); idx += NT) {
+                    const int pos = 2 * idx - (idx & (stride - 1));
+                    const unsigned long long a = keys[pos], b = keys[pos + stride];
+                    const bool desc = (pos & size) == 0;
+                    if ((a < b) == desc) { keys[pos] = b; keys[pos + stride] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        // ---- E: exact score ties inside the kept window -> raw-string order (rare slow path) ---------------
+        if (t > 0) {
+            for (int r = tid; r < B && r + 1 < n_pad; r += NT) {
+                const unsigned long long a = keys[r], b = keys[r + 1];
+                if (a != 0ull && b != 0ull && (uint32_t)(a >> 32) == (uint32_t)(b >> 32)) s_tie = 1;
+            }
+            __syncthreads();
+            if (s_tie && tid == 0) {
+                int r = 0;
+                while (r < B && keys[r] != 0ull) {
+                    const uint32_t sc = (uint32_t)(keys[r] >> 32);
+                    int e = r + 1;
+                    while (e < n_pad && keys[e] != 0ull && (uint32_t)(keys[e] >> 32) == sc) e++;
+                    if (e - r > 1) {
+                        // insertion sort of keys[r:e) by raw string, ascending
+                        for (int x = r + 1; x < e; x++) {
+                            const unsigned long long kx = keys[x];
+                            const int cx = (int)(0xffffffffu - (uint32_t)kx);
+                            const int ix = cx / V, vx = cx - ix * V;
+                            const int sufx = (vx == blank) ? vch[blank]
+                                             : ((st.eb[ix] == 0 && vx == st.last[ix]) ? 0 : vch[vx]);
+                            int y = x - 1;
+                            while (y >= r) {
+                                const int cy = (int)(0xffffffffu - (uint32_t)keys[y]);
+                                const int iy = cy / V, vy = cy - iy * V;
+                                const int sufy = (vy == blank) ? vch[blank]
+                                                 : ((st.eb[iy] == 0 && vy == st.last[iy]) ? 0 : vch[vy]);
+                                if (!raw_less(parent, meta, vch, st.node[ix], sufx, st.node[iy], sufy)) break;
+                                keys[y + 1] = keys[y];
+                                y--;
+                            }
+                            keys[y + 1] = kx;
+                        }
+                    }
+                    r = e;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- F: the top-B merged candidates become the next kept states -----------------------------------
+        int my_new = 0, my_i = 0, my_v = 0;
+        bool valid = false;
+        if (tid < B) {
+            const unsigned long long key = keys[tid];
+            valid = key != 0ull;
+            if (valid) {
+                const int c = (int)(0xffffffffu - (uint32_t)key);
+                my_i = c / V; my_v = c - my_i * V;
+                nx.score[tid] = ord2f((uint32_t)(key >> 32));
+                const bool stay = (my_v == blank) || (st.eb[my_i] == 0 && my_v == st.last[my_i]);
+                if (stay) {
+                    nx.node[tid] = st.node[my_i]; nx.pnode[tid] = st.pnode[my_i]; nx.last[tid] = st.last[my_i];
+                    nx.eb[tid] = (my_v == blank) ? 1 : 0;
+                } else {
+                    const int pn = st.node[my_i];
+                    const int nd = child[(size_t)pn * Vp + my_v];
+                    nx.pnode[tid] = pn; nx.last[tid] = (short)my_v; nx.eb[tid] = 0;
+                    nx.node[tid] = nd;            // 0 = not created yet
+                    my_new = (nd == 0);
+                }
+            }
+            newflag[tid] = my_new;
+        }
+        __syncthreads();
+        if (tid < B && valid) {
+            if (my_new) {
+                int off = 0;
+                for (int j = 0; j < tid; j++) off += newflag[j];
+                const int nd = s_nodes + off;
+                const int pn = st.node[my_i];
+                parent[nd] = pn;
+                meta[nd] = (((meta[pn] >> 8) + 1) << 8) | my_v;
+                child[(size_t)pn * Vp + my_v] = nd;
+                int4 *row = reinterpret_cast<int4 *>(child + (size_t)nd * Vp);
+                for (int q = 0; q < Vp / 4; q++) row[q] = make_int4(0, 0, 0, 0);
+                nx.node[tid] = nd;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int cnt = 0, kept = 0;
+            for (int j = 0; j < B; j++) { cnt += newflag[j]; kept += (keys[j] != 0ull); }
+            s_nodes += cnt;
+            s_kept = kept;
+        }
+        cur ^= 1;
+        __syncthreads();
+    }
+
+    // ---- result: kept states best first; path = labels of X (blank stripped), CTCBeamSearch.cu:290-298 ------
+    const BeamView st = beam_view(cur);
+    const int kept = s_kept;
+    if (tid == 0 && p.out_counts) p.out_counts[utt] = kept;
+    for (int r = tid; r < p.nbest; r += NT) {
+        char *out = p.out_paths + ((size_t)utt * p.nbest + r) * p.max_len;
+        int len = 0;
+        float sc = 0.0f;
+        if (r < kept) {
+            int nd = st.node[r];
+            const int depth = meta[nd] >> 8;
+            len = depth;
+            // T == 1: the reference returns the initial path as is, blank included
+            if (p.T == 1 && st.eb[r]) { if (len < p.max_len) out[len] = vch[blank]; len += 1; }
+            for (int pos = depth - 1; pos >= 0; pos--) {
+                if (pos < p.max_len) out[pos] = vch[meta[nd] & 0xff];
+                nd = parent[nd];
+            }
+            sc = st.score[r];
+        }
+        p.out_lens[(size_t)utt * p.nbest + r] = len;
+        p.out_scores[(size_t)utt * p.nbest + r] = sc;
+    }
+}
+
+static size_t ctc_smem_bytes(int B, int V, int Vp, int n_pad) {
+    size_t s = sizeof(unsigned long long) * n_pad + sizeof(float) * Vp;
+    s += (sizeof(float) + 2 * sizeof(int)) * 2 * B;   // score, node, pnode (x2 buffers)
+    s += sizeof(int) * B;                             // newflag
+    s += 3 * sizeof(short) * B;                       // twin, P0, P1
+    s += sizeof(short) * 2 * B;                       // last (x2)
+    s += 2 * sizeof(uint16_t) * (size_t)B * V;        // redir0/1
+    s += (V + 3) / 4 * 4;                             // vocab chars
+    s += 2 * B;                                       // eb (x2)
+    return s + 16;
+}
+
+struct CtcLayout {
+    int Vp, n_pad, cap, threads;
+    size_t smem, off_vocab, off_parent, off_meta, off_child, off_paths, off_lens, off_scores, off_counts, total;
+    size_t out_bytes;
+};
+
+static int ctc_layout(const CtcArgs &a, CtcLayout &L) {
+    L.Vp = (a.V + 3) / 4 * 4;
+    L.n_pad = 32;
+    while (L.n_pad < a.beam * a.V) L.n_pad <<= 1;
+    L.cap = 1 + a.beam * a.T;
+    L.threads = L.n_pad / 2;
+    if (L.threads < 128) L.threads = 128;
+    if (L.threads > 1024) L.threads = 1024;
+    L.smem = ctc_smem_bytes(a.beam, a.V, L.Vp, L.n_pad);
+    size_t o = 0;
+    L.off_vocab = o; o = align_up(o + a.V, 256);
+    L.off_parent = o; o = align_up(o + sizeof(int) * (size_t)a.N * L.cap, 256);
+    L.off_meta = o; o = align_up(o + sizeof(int) * (size_t)a.N * L.cap, 256);
+    L.off_child = o; o = align_up(o + sizeof(int) * (size_t)a.N * L.cap * L.Vp, 256);
+    L.total = o;
+    size_t q = 0;
+    L.off_paths = q; q = align_up(q + (size_t)a.N * a.nbest * a.max_len, 256);
+    L.off_lens = q; q = align_up(q + sizeof(int) * (size_t)a.N * a.nbest, 256);
+    L.off_scores = q; q = align_up(q + sizeof(float) * (size_t)a.N * a.nbest, 256);
+    L.off_counts = q; q = align_up(q + sizeof(int) * (size_t)a.N, 256);
+    L.out_bytes = q;
+    return GASR_OK;
+}
+
+int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
+    GASR_CHECK(a.scores != nullptr && a.vocab_host != nullptr, "ctc_decode: null scores/vocab");
+    GASR_CHECK(a.T >= 1 && a.N >= 0, "ctc_decode: T must be >= 1 and N >= 0 (T=%d N=%d)", a.T, a.N);
+    GASR_CHECK(a.V >= 1 && a.V <= 255 && a.ld >= a.V, "ctc_decode: vocabulary size %d / ld %d unsupported", a.V, a.ld);
+    GASR_CHECK(a.beam >= 1 && a.beam <= 1024, "ctc_decode: beam %d out of range", a.beam);
+    GASR_CHECK(a.blank >= 0 && a.blank < a.V, "ctc_decode: blank id %d outside the vocabulary", a.blank);
+    GASR_CHECK(a.nbest >= 1 && a.nbest <= a.beam && a.max_len >= 0, "ctc_decode: nbest/max_len out of range");
+    GASR_CHECK(a.domain == GASR_DOMAIN_PROB || a.domain == GASR_DOMAIN_LOG, "ctc_decode: unknown score domain");
+    for (int v = 0; v < a.V; v++) {
+        GASR_CHECK(a.vocab_host[v] > 0, "ctc_decode: vocab chars must be in 1..127 (entry %d)", v);
+        for (int u = 0; u < v; u++)
+            GASR_CHECK(a.vocab_host[u] != a.vocab_host[v], "ctc_decode: duplicate vocab char at %d and %d", u, v);
+    }
+    if (a.N == 0) return GASR_OK;
+    CtcLayout L;
+    ctc_layout(a, L);
+    if (L.smem > (size_t)ctx->max_smem_optin) {
+        set_error("ctc_decode: beam %d x vocab %d needs %zu B of shared memory (> %d)", a.beam, a.V, L.smem,
+                  ctx->max_smem_optin);
+        return GASR_ERR_UNSUPPORTED;
+    }
+    GASR_TRY(ws_reserve(ctx, ctx->ws_ctc, L.total));
+    GASR_TRY(ws_reserve(ctx, ctx->ws_out, L.out_bytes));
+    GASR_TRY(pinned_reserve(ctx, L.out_bytes));
+    unsigned char *ws = static_cast<unsigned char *>(ctx->ws_ctc.ptr);
+    unsigned char *wo = static_cast<unsigned char *>(ctx->ws_out.ptr);
+    GASR_CUDA(cudaMemcpyAsync(ws + L.off_vocab, a.vocab_host, a.V, cudaMemcpyHostToDevice, st));
+
+    CtcParams p;
+    p.scores = a.scores; p.T = a.T; p.N = a.N; p.V = a.V; p.ld = a.ld; p.beam = a.beam; p.blank = a.blank;
+    p.Vp = L.Vp; p.n_pad = L.n_pad; p.cap = L.cap; p.max_len = a.max_len; p.nbest = a.nbest;
+    p.vocab = reinterpret_cast<const char *>(ws + L.off_vocab);
+    p.parent = reinterpret_cast<int *>(ws + L.off_parent);
+    p.meta = reinterpret_cast<int *>(ws + L.off_meta);
+    p.child = reinterpret_cast<int *>(ws + L.off_child);
+    p.out_paths = reinterpret_cast<char *>(wo + L.off_paths);
+    p.out_lens = reinterpret_cast<int *>(wo + L.off_lens);
+    p.out_scores = reinterpret_cast<float *>(wo + L.off_scores);
+    p.out_counts = reinterpret_cast<int *>(wo + L.off_counts);
+
+    GASR_CUDA(cudaMemsetAsync(wo + L.off_paths, 0, (size_t)a.N * a.nbest * a.max_len, st));
+#define GASR_CTC_LAUNCH(DOM, MT)                                                                                  \
+    do {                                                                                                          \
+        GASR_CUDA(cudaFuncSetAttribute(ctc_beam_kernel<DOM, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                       (int)L.smem));                                                             \
+        ctc_beam_kernel<DOM, MT><<<a.N, L.threads, L.smem, st>>>(p);                                              \
+    } while (0)
+    if (a.domain == GASR_DOMAIN_LOG) {
+        if (L.threads <= 256) GASR_CTC_LAUNCH(1, 256); else GASR_CTC_LAUNCH(1, 1024);
+    } else {
+        if (L.threads <= 256) GASR_CTC_LAUNCH(0, 256); else GASR_CTC_LAUNCH(0, 1024);
+    }
+#undef GASR_CTC_LAUNCH
+    GASR_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    GASR_CUDA(cudaMemcpyAsync(ctx->pinned_out, wo, L.out_bytes, cudaMemcpyDeviceToHost, st));
+    return GASR_OK;
+}
+
+int ctc_decode_finish(gasr_ctx *ctx, const CtcArgs &a) {
+    if (a.N == 0) return GASR_OK;
+    CtcLayout L;
+    ctc_layout(a, L);
+    const unsigned char *h = static_cast<const unsigned char *>(ctx->pinned_out);
+    memcpy(a.out_paths, h + L.off_paths, (size_t)a.N * a.nbest * a.max_len);
+    memcpy(a.out_lens, h + L.off_lens, sizeof(int) * (size_t)a.N * a.nbest);
+    memcpy(a.out_scores, h + L.off_scores, sizeof(float) * (size_t)a.N * a.nbest);
+    if (a.out_counts) memcpy(a.out_counts, h + L.off_counts, sizeof(int) * (size_t)a.N);
+    int status = GASR_OK;
+    for (size_t i = 0; i < (size_t)a.N * a.nbest; i++)
+        if (a.out_lens[i] > a.max_len) status = GASR_ERR_TRUNCATED;
+    if (status != GASR_OK) set_error("ctc_decode: at least one path is longer than max_len=%d", a.max_len);
+    return status;
+}
+
+}  // namespace gasr

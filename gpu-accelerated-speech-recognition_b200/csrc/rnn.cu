@@ -1,0 +1,268 @@
+// rnn.cu -- recurrent part of RNN_Cell / RNN (reference RNN_Cell.cu:5-13,65-74, RNN.cu:9-30) and the GRU of cfg3.
+//
+// The reference runs, per (timestep, layer), 2 cublasSgemm + 1 cublasSgeam + 1 bias/tanh kernel with a host sync
+// after each -- 12 000 device round trips at cfg2.  Here a layer is split into
+//   (1) x*W_ih (+ both biases) for ALL timesteps at once -- a dense GEMM (gemm_simt.cu / xproj_gemm_tc.cu), and
+//   (2) the recurrence h_t = tanh(xproj_t + h_{t-1}*W_hh): ONE persistent kernel for all T steps.
+//
+// rnn_tanh_cluster_kernel: one thread-block cluster (CS = H/64 CTAs, <= 8) per group of 16 utterances.  CTA c
+// keeps the 64-column slice W_hh[:, 64c:64c+64] resident in shared memory for the whole sequence (128 KB at
+// H = 512) plus a double-buffered copy of the group's full h (16 x H fp32).  Per step each CTA computes its
+// [16 x 64] slice (4-way split-K over warps, 4x4 register tiles, operands read as 128-bit shared loads),
+// reduces the partials, adds xproj (prefetched one step ahead), applies tanh, stores h_t to HBM and broadcasts
+// its slice into every CTA's shared memory through DSMEM; one cluster barrier per step.  Per step a CTA touches
+// HBM only for its xproj slice and its output slice.
+//
+// Shapes outside the cluster kernel's envelope (H not 64 * 2^j <= 512, GRU) use one small kernel per timestep
+// with W_hh streamed from L2.
+#include <cooperative_groups.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace gasr {
+
+// ---- single cell step (RNN_Cell::forward) ------------------------------------------------------------------
+__global__ void rnn_cell_kernel(const float *__restrict__ x, const float *__restrict__ h, const float *__restrict__ w_ih,
+                                const float *__restrict__ w_hh, const float *__restrict__ b_ih,
+                                const float *__restrict__ b_hh, float *__restrict__ out, int batch, int in, int hidden) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = blockIdx.y;
+    if (j >= hidden || n >= batch) return;
+    float ih = 0.0f, hh = 0.0f;
+    for (int k = 0; k < in; k++) ih = fmaf(x[(size_t)n * in + k], w_ih[(size_t)k * hidden + j], ih);
+    for (int k = 0; k < hidden; k++) hh = fmaf(h[(size_t)n * hidden + k], w_hh[(size_t)k * hidden + j], hh);
+    // matrixAdd(ih, hh) then data += (bias1 + bias2), tanh  (RNN_Cell.cu:68, :10-12)
+    out[(size_t)n * hidden + j] = tanhf((ih + hh) + (b_hh[j] + b_ih[j]));
+}
+
+int launch_rnn_cell(gasr_ctx *ctx, const float *x, const float *h_prev, const float *w_ih, const float *w_hh,
+                    const float *b_ih, const float *b_hh, float *out, int batch, int in, int hidden, cudaStream_t st) {
+    GASR_CHECK(x && h_prev && w_ih && w_hh && b_ih && b_hh && out, "rnn_cell: null operand");
+    GASR_CHECK(batch >= 0 && in >= 1 && hidden >= 1 && batch <= 65535, "rnn_cell: bad shape");
+    if (batch == 0) return GASR_OK;
+    dim3 grid(ceil_div(hidden, 128), batch);
+    rnn_cell_kernel<<<grid, 128, 0, st>>>(x, h_prev, w_ih, w_hh, b_ih, b_hh, out, batch, in, hidden);
+    GASR_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return GASR_OK;
+}
+
+// ---- per-timestep fallback kernels ---------------------------------------------------------------------------
+// out[n, j] = tanh(xp[n, j] + sum_k hprev[n, k] * W[k, j])
+__global__ void rnn_tanh_step_kernel(const float *__restrict__ xp, int ldxp, const float *__restrict__ hprev, int ldh,
+                                     const float *__restrict__ W, float *__restrict__ out, int ldo, int N, int H) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = blockIdx.y;
+    if (j >= H) return;
+    float acc = 0.0f;
+    if (hprev != nullptr)
+        for (int k = 0; k < H; k++) acc = fmaf(hprev[(size_t)n * ldh + k], W[(size_t)k * H + j], acc);
+    out[(size_t)n * ldo + j] = tanhf(xp[(size_t)n * ldxp + j] + acc);
+}
+
+__device__ __forceinline__ float sigmoid_f(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+// torch.nn.GRU step, gate order r,z,n; xp already holds x*W_ih + b_ih; b_hh stays on the hidden side.
+__global__ void gru_step_kernel(const float *__restrict__ xp, int ldxp, const float *__restrict__ hprev, int ldh,
+                                const float *__restrict__ W, const float *__restrict__ b_hh, float *__restrict__ out,
+                                int ldo, int N, int H) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = blockIdx.y;
+    if (j >= H) return;
+    float gr = 0.0f, gz = 0.0f, gn = 0.0f, hj = 0.0f;
+    if (hprev != nullptr) {
+        const float *hp = hprev + (size_t)n * ldh;
+        for (int k = 0; k < H; k++) {
+            const float hv = hp[k];
+            const float *w = W + (size_t)k * 3 * H;
+            gr = fmaf(hv, w[j], gr);
+            gz = fmaf(hv, w[H + j], gz);
+            gn = fmaf(hv, w[2 * H + j], gn);
+        }
+        hj = hp[j];
+    }
+    const float *xr = xp + (size_t)n * ldxp;
+    const float r = sigmoid_f(xr[j] + (gr + b_hh[j]));
+    const float z = sigmoid_f(xr[H + j] + (gz + b_hh[H + j]));
+    const float nn = tanhf(xr[2 * H + j] + r * (gn + b_hh[2 * H + j]));
+    out[(size_t)n * ldo + j] = (1.0f - z) * nn + z * hj;
+}
+
+// ---- persistent cluster kernel (tanh) ------------------------------------------------------------------------
+constexpr int RC_NB = 16;     // utterances per cluster
+constexpr int RC_HC = 64;     // hidden columns per CTA
+constexpr int RC_THREADS = 256;
+
+struct RnnClusterParams {
+    const float *xproj; int ldxp;
+    const float *w_hh;
+    float *out; int ldo, col0;
+    int T, N, H, CS, reverse;
+};
+
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
+
+__global__ void __launch_bounds__(RC_THREADS, 1) rnn_tanh_cluster_kernel(const RnnClusterParams p) {
+    extern __shared__ __align__(16) float smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int H = p.H, CS = p.CS;
+    const int HS = H + 4;                          // padded h row (keeps 128-bit loads of 4 rows conflict-free)
+    float *Ws = smem;                              // [H][64]
+    float *hbuf = Ws + (size_t)H * RC_HC;          // [2][16][HS]
+    float *red = hbuf + 2 * RC_NB * HS;            // [4][16][64]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rank = (int)cluster.block_rank();
+    const int group = blockIdx.x / CS;
+    const int n0 = group * RC_NB;
+    const int colbase = rank * RC_HC;
+
+    // resident weights: Ws[k][c] = W_hh[k][colbase + c]
+    for (int i = tid; i < H * (RC_HC / 4); i += RC_THREADS) {
+        const int k = i / (RC_HC / 4), c4 = i % (RC_HC / 4);
+        reinterpret_cast<float4 *>(Ws)[i] = __ldg(reinterpret_cast<const float4 *>(p.w_hh + (size_t)k * H + colbase) + c4);
+    }
+    for (int i = tid; i < 2 * RC_NB * HS; i += RC_THREADS) hbuf[i] = 0.0f;   // h_0 = 0 (RNN.h:16-17)
+
+    // compute-phase mapping: warp -> (K quarter, column half); lane -> (utterance set, 4-column group)
+    const int kq = warp & 3, ch = warp >> 2;
+    const int cgp = lane & 7, ug = lane >> 3;      // utterances ug, ug+4, ug+8, ug+12
+    const int kbeg = kq * (H / 4), kend = kbeg + H / 4;
+    const float *wcol = Ws + ch * 32 + cgp * 4;
+    // epilogue mapping: thread -> (utterance, 4 columns)
+    const int eu = tid >> 4, ec = (tid & 15) * 4;
+    const int en = n0 + eu;
+    const bool evalid = en < p.N;
+
+    float4 xnext = make_float4(0.f, 0.f, 0.f, 0.f);
+    {
+        const int t0 = p.reverse ? p.T - 1 : 0;
+        if (evalid) xnext = __ldg(reinterpret_cast<const float4 *>(p.xproj + ((size_t)t0 * p.N + en) * p.ldxp + colbase + ec));
+    }
+    cluster.sync();   // weights + zeroed h visible, all CTAs of the cluster are running
+
+    for (int s = 0; s < p.T; s++) {
+        const int t = p.reverse ? p.T - 1 - s : s;
+        const float *hc = hbuf + (size_t)(s & 1) * RC_NB * HS;
+        float *hn = hbuf + (size_t)((s & 1) ^ 1) * RC_NB * HS;
+        const float4 xcur = xnext;
+        if (s + 1 < p.T && evalid) {
+            const int tn = p.reverse ? t - 1 : t + 1;
+            xnext = __ldg(reinterpret_cast<const float4 *>(p.xproj + ((size_t)tn * p.N + en) * p.ldxp + colbase + ec));
+        }
+        // ---- partial products over this warp's K quarter ------------------------------------------------
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+        const float *h0 = hc + (size_t)ug * HS;
+#pragma unroll 2
+        for (int k = kbeg; k < kend; k += 4) {
+            float4 hv[4], wv[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) hv[i] = *reinterpret_cast<const float4 *>(h0 + (size_t)(4 * i) * HS + k);
+#pragma unroll
+            for (int q = 0; q < 4; q++) wv[q] = *reinterpret_cast<const float4 *>(wcol + (size_t)(k + q) * RC_HC);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                acc[i][0] = fmaf(hv[i].x, wv[0].x, acc[i][0]); acc[i][1] = fmaf(hv[i].x, wv[0].y, acc[i][1]);
+                acc[i][2] = fmaf(hv[i].x, wv[0].z, acc[i][2]); acc[i][3] = fmaf(hv[i].x, wv[0].w, acc[i][3]);
+                acc[i][0] = fmaf(hv[i].y, wv[1].x, acc[i][0]); acc[i][1] = fmaf(hv[i].y, wv[1].y, acc[i][1]);
+                acc[i][2] = fmaf(hv[i].y, wv[1].z, acc[i][2]); acc[i][3] = fmaf(hv[i].y, wv[1].w, acc[i][3]);
+                acc[i][0] = fmaf(hv[i].z, wv[2].x, acc[i][0]); acc[i][1] = fmaf(hv[i].z, wv[2].y, acc[i][1]);
+                acc[i][2] = fmaf(hv[i].z, wv[2].z, acc[i][2]); acc[i][3] = fmaf(hv[i].z, wv[2].w, acc[i][3]);
+                acc[i][0] = fmaf(hv[i].w, wv[3].x, acc[i][0]); acc[i][1] = fmaf(hv[i].w, wv[3].y, acc[i][1]);
+                acc[i][2] = fmaf(hv[i].w, wv[3].z, acc[i][2]); acc[i][3] = fmaf(hv[i].w, wv[3].w, acc[i][3]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            *reinterpret_cast<float4 *>(red + ((size_t)kq * RC_NB + ug + 4 * i) * RC_HC + ch * 32 + cgp * 4) =
+                make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        __syncthreads();
+        // ---- reduce the 4 K quarters, add xproj, tanh, publish --------------------------------------------
+        float4 v = xcur;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float4 r = *reinterpret_cast<const float4 *>(red + ((size_t)q * RC_NB + eu) * RC_HC + ec);
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+        v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w);
+        if (s + 1 < p.T) {
+            // broadcast this CTA's slice of h_t into every CTA's next-step buffer (DSMEM)
+            float *dst_local = hn + (size_t)eu * HS + colbase + ec;
+            for (int r = 0; r < CS; r++) {
+                float *dst = cluster.map_shared_rank(dst_local, r);
+                *reinterpret_cast<float4 *>(dst) = v;
+            }
+        }
+        cluster_arrive();
+        if (evalid) *reinterpret_cast<float4 *>(p.out + ((size_t)t * p.N + en) * p.ldo + p.col0 + colbase + ec) = v;
+        cluster_wait();
+    }
+}
+
+static bool cluster_kernel_supported(const gasr_ctx *ctx, const RnnLayerArgs &a) {
+    if (a.cell != GASR_CELL_TANH || !ctx->cluster_ok) return false;
+    const int H = a.H;
+    if (H != 64 && H != 128 && H != 256 && H != 512) return false;
+    if (a.ldxp % 4 != 0 || a.ldo % 4 != 0 || a.col0 % 4 != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(a.xproj) & 15) || (reinterpret_cast<uintptr_t>(a.out) & 15) ||
+        (reinterpret_cast<uintptr_t>(a.w_hh) & 15))
+        return false;
+    return true;
+}
+
+static size_t cluster_smem_bytes(int H) {
+    return sizeof(float) * ((size_t)H * RC_HC + 2 * RC_NB * (H + 4) + 4 * RC_NB * RC_HC);
+}
+
+int launch_rnn_recurrence(gasr_ctx *ctx, const RnnLayerArgs &a, cudaStream_t st) {
+    GASR_CHECK(a.xproj && a.w_hh && a.out, "rnn_recurrence: null operand");
+    GASR_CHECK(a.T >= 0 && a.N >= 0 && a.H >= 1, "rnn_recurrence: bad shape");
+    GASR_CHECK(a.cell == GASR_CELL_TANH || (a.cell == GASR_CELL_GRU && a.b_hh), "rnn_recurrence: bad cell");
+    if (a.T == 0 || a.N == 0) return GASR_OK;
+    if (cluster_kernel_supported(ctx, a)) {
+        RnnClusterParams p;
+        p.xproj = a.xproj; p.ldxp = a.ldxp; p.w_hh = a.w_hh; p.out = a.out; p.ldo = a.ldo; p.col0 = a.col0;
+        p.T = a.T; p.N = a.N; p.H = a.H; p.CS = a.H / RC_HC; p.reverse = a.reverse;
+        const int groups = ceil_div(a.N, RC_NB);
+        const size_t smem = cluster_smem_bytes(a.H);
+        GASR_CUDA(cudaFuncSetAttribute(rnn_tanh_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(groups * p.CS);
+        cfg.blockDim = dim3(RC_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = p.CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        GASR_CUDA(cudaLaunchKernelEx(&cfg, rnn_tanh_cluster_kernel, p));
+        ctx->launches += 1;
+        return GASR_OK;
+    }
+    // fallback: one kernel per timestep
+    GASR_CHECK(a.N <= 65535, "rnn_recurrence: batch too large for the per-step path");
+    dim3 grid(ceil_div(a.H, 128), a.N);
+    for (int s = 0; s < a.T; s++) {
+        const int t = a.reverse ? a.T - 1 - s : s;
+        const int tp = a.reverse ? t + 1 : t - 1;
+        const float *xp = a.xproj + (size_t)t * a.N * a.ldxp;
+        float *o = a.out + (size_t)t * a.N * a.ldo + a.col0;
+        const float *hp = s == 0 ? nullptr : a.out + (size_t)tp * a.N * a.ldo + a.col0;
+        if (a.cell == GASR_CELL_TANH)
+            rnn_tanh_step_kernel<<<grid, 128, 0, st>>>(xp, a.ldxp, hp, a.ldo, a.w_hh, o, a.ldo, a.N, a.H);
+        else
+            gru_step_kernel<<<grid, 128, 0, st>>>(xp, a.ldxp, hp, a.ldo, a.w_hh, a.b_hh, o, a.ldo, a.N, a.H);
+        ctx->launches += 1;
+    }
+    GASR_CUDA(cudaGetLastError());
+    return GASR_OK;
+}
+
+}  // namespace gasr

@@ -1,0 +1,375 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI (ctypes ->
+libgasr.so), against the CPU oracle on the same seeded inputs and against the committed golden fixtures.
+Integer / string results must be bit-exact; fp32 beam scores must be bit-exact too (same arithmetic on both
+sides); acoustic-model outputs must agree within 1e-4 absolute (BASELINE.json north_star)."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "gpu-accelerated-speech-recognition_b200"))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+pytestmark = pytest.mark.gpu
+
+AM_TOL = 1e-4   # fp32 acoustic-model tolerance (absolute), north_star
+
+
+@pytest.fixture(scope="module")
+def gasr():
+    import gasr as g
+    return g
+
+
+@pytest.fixture(scope="module")
+def ctx(gasr):
+    c = gasr.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+def _softmax_probs(rng, T, N, V, scale=2.0):
+    logits = rng.normal(size=(T, N, V)).astype(np.float32) * scale
+    p = np.exp(logits - logits.max(-1, keepdims=True))
+    return (p / p.sum(-1, keepdims=True)).astype(np.float32)
+
+
+def _assert_same(gp, gs, op, os_):
+    assert gp == op
+    a, b = np.array(gs, dtype=np.float32), np.array(os_, dtype=np.float32)
+    assert (a.view(np.uint32) == b.view(np.uint32)).all(), (a, b)
+
+
+# ---------------------------------------------------------------- CTC beam search ----------------------------
+def test_ctc_main_cpp_vector(gasr, ctx):
+    g = json.load(open(os.path.join(GOLDEN, "ctc_main.json")))
+    P = np.array(g["probs"], dtype=np.float32).reshape(g["T"], 1, 4)
+    for beam, (path, prob) in g["expected"].items():
+        p, s = ctx.ctc_decode_host(P, gasr.DOMAIN_PROB, int(beam), g["blank"], g["vocab"].encode())
+        assert p[0].decode() == path
+        assert np.float32(s[0]) == np.float32(prob)
+
+
+def test_ctc_reference_class_api(gasr, ctx):
+    """main.cpp:48-72 through the mirrored classes: CTCBeamSearch(vocab, 4, 2, 0)->decode(seqProb, 10, 1)."""
+    g = json.load(open(os.path.join(GOLDEN, "ctc_main.json")))
+    seq = gasr.cuMatrix(np.array(g["probs"], dtype=np.float32).reshape(10, 4), ctx=ctx)
+    seq.toGpu()
+    dec = gasr.CTCBeamSearch(b"$abc", 4, 2, 0, ctx=ctx)
+    res = dec.decode(seq, 10, 1)
+    assert res[0][0] == b"cbacbc" and np.float32(res[0][1]) == np.float32(1.9566051e-3)
+    with pytest.raises(gasr.GasrError):
+        gasr.CTCBeamSearch(b"$ab", 3, 2, 0, ctx=ctx).decode(seq, 10, 1)   # inconsistent vocabulary size
+
+
+@pytest.mark.parametrize("V,beam", [(4, 1), (4, 2), (4, 3), (4, 9), (8, 5), (29, 16), (29, 40), (47, 100), (29, 128)])
+def test_ctc_prob_domain_random(gasr, ctx, O, V, beam):
+    rng = np.random.default_rng(V * 1000 + beam)
+    vocab = bytes(range(1, V + 1)) if V != 29 else __import__("synth").VOCAB29
+    for T, N in ((1, 3), (2, 4), (7, 5), (20, 6)):
+        P = _softmax_probs(rng, T, N, V)
+        gp, gs = ctx.ctc_decode_host(P, gasr.DOMAIN_PROB, beam, 0, vocab)
+        op, os_ = O.ctc_decode(P, vocab, 0, beam, domain="prob")
+        _assert_same(gp, gs, op, os_)
+
+
+@pytest.mark.parametrize("V,beam,T", [(29, 16, 200), (29, 32, 120), (29, 8, 300), (5, 3, 150), (47, 100, 40), (29, 128, 60)])
+def test_ctc_log_domain_random(gasr, ctx, O, V, beam, T):
+    import synth
+    vocab = synth.VOCAB29 if V == 29 else bytes(range(1, V + 1))
+    N = 6
+    lp = synth.random_logprobs(V * 7 + beam, T, N, V, scale=1.5)
+    gp, gs = ctx.ctc_decode_host(lp, gasr.DOMAIN_LOG, beam, 0, vocab)
+    op, os_ = O.ctc_decode(lp, vocab, 0, beam, domain="log", nthreads=4)
+    _assert_same(gp, gs, op, os_)
+
+
+def test_ctc_blank_not_first_and_peaky(gasr, ctx, O):
+    import synth
+    rng = np.random.default_rng(5)
+    vocab = b"abc\x01de"   # blank id 3, still the smallest char
+    P = _softmax_probs(rng, 30, 4, 6)
+    _assert_same(*ctx.ctc_decode_host(P, gasr.DOMAIN_PROB, 4, 3, vocab), *O.ctc_decode(P, vocab, 3, 4, domain="prob"))
+    lp = synth.peaky_logprobs(3, 160, 5, 29)
+    _assert_same(*ctx.ctc_decode_host(lp, gasr.DOMAIN_LOG, 16, 0, synth.VOCAB29),
+                 *O.ctc_decode(lp, synth.VOCAB29, 0, 16, domain="log"))
+
+
+def test_ctc_exact_ties_break_by_raw_string(gasr, ctx, O):
+    """Quantised probabilities produce many exactly equal scores; order must follow the raw-string order."""
+    rng = np.random.default_rng(11)
+    for V, vocab in ((3, b"$ab"), (4, b"$abc"), (5, b"\x01zyxw"), (6, b"\x01badce")):
+        for trial in range(12):
+            T = int(rng.integers(2, 9))
+            q = rng.integers(1, 4, size=(T, 3, V)).astype(np.float32)
+            P = (q / 8.0).astype(np.float32)          # exact in fp32, products stay exact for short T
+            for beam in (1, 2, 3, 5, 12):
+                gp, gs = ctx.ctc_decode_host(P, gasr.DOMAIN_PROB, beam, 0, vocab, nbest=beam)
+                op, os_ = O.ctc_decode(P, vocab, 0, beam, domain="prob", nbest=beam)
+                assert gp == op, (vocab, T, beam, trial)
+                assert gs == os_
+    # uniform input: every candidate ties
+    P = np.full((5, 2, 4), 0.25, dtype=np.float32)
+    gp, gs = ctx.ctc_decode_host(P, gasr.DOMAIN_PROB, 3, 0, b"$abc", nbest=3)
+    op, os_ = O.ctc_decode(P, b"$abc", 0, 3, domain="prob", nbest=3)
+    assert gp == op and gs == os_
+    lp = np.log(P)
+    gp, gs = ctx.ctc_decode_host(lp, gasr.DOMAIN_LOG, 3, 0, b"$abc", nbest=3)
+    op, os_ = O.ctc_decode(lp, b"$abc", 0, 3, domain="log", nbest=3)
+    assert gp == op and gs == os_
+
+
+def test_ctc_zero_probabilities_and_minus_inf(gasr, ctx, O):
+    rng = np.random.default_rng(2)
+    P = _softmax_probs(rng, 12, 3, 5)
+    P[rng.random(P.shape) < 0.3] = 0.0
+    vocab = b"\x01abcd"
+    _assert_same(*ctx.ctc_decode_host(P, gasr.DOMAIN_PROB, 4, 0, vocab), *O.ctc_decode(P, vocab, 0, 4, domain="prob"))
+    with np.errstate(divide="ignore"):
+        lp = np.log(P)
+    _assert_same(*ctx.ctc_decode_host(lp, gasr.DOMAIN_LOG, 4, 0, vocab), *O.ctc_decode(lp, vocab, 0, 4, domain="log"))
+
+
+def test_ctc_nbest_and_edge_cases(gasr, ctx, O):
+    import synth
+    lp = synth.random_logprobs(9, 50, 4, 29)
+    gp, gs = ctx.ctc_decode_host(lp, gasr.DOMAIN_LOG, 16, 0, synth.VOCAB29, nbest=16)
+    op, os_ = O.ctc_decode(lp, synth.VOCAB29, 0, 16, domain="log", nbest=16)
+    assert gp == op and gs == os_
+    # T == 1 returns the initial path unstripped (blank included)
+    p, s = ctx.ctc_decode_host(np.array([[[0.7, 0.2, 0.1]]], dtype=np.float32), gasr.DOMAIN_PROB, 2, 0, b"$ab")
+    assert p == [b"$"] and np.float32(s[0]) == np.float32(0.7)
+    # all blank -> empty transcript
+    P = np.tile(np.array([0.98, 0.01, 0.01], dtype=np.float32), (6, 2, 1))
+    p, _ = ctx.ctc_decode_host(P, gasr.DOMAIN_PROB, 3, 0, b"$ab")
+    assert p == [b"", b""]
+    # empty batch, and invalid arguments are reported, not fatal
+    p, s = ctx.ctc_decode_host(np.zeros((4, 0, 3), dtype=np.float32), gasr.DOMAIN_PROB, 3, 0, b"$ab")
+    assert p == [] and s == []
+    for bad in (dict(beam=0), dict(blank=5), dict(vocab=b"$aa")):
+        kw = dict(beam=2, blank=0, vocab=b"$ab")
+        kw.update(bad)
+        with pytest.raises(gasr.GasrError) as e:
+            ctx.ctc_decode_host(P, gasr.DOMAIN_PROB, kw["beam"], kw["blank"], kw["vocab"])
+        assert e.value.status == gasr.ERR_INVALID
+    # truncated output: the length is still reported
+    with pytest.raises(gasr.GasrError) as e:
+        ctx.ctc_decode_host(lp, gasr.DOMAIN_LOG, 4, 0, synth.VOCAB29, max_len=3)
+    assert e.value.status == gasr.ERR_TRUNCATED
+
+
+def test_ctc_full_size_properties(gasr, ctx, O):
+    """cfg2 / cfg4 sizes: determinism, batch-order invariance, and an oracle spot check on two utterances."""
+    import synth
+    T, N, V = 1000, 64, 29
+    lp = synth.random_logprobs(1234, T, N, V)
+    a = ctx.ctc_decode_host(lp, gasr.DOMAIN_LOG, 16, 0, synth.VOCAB29)
+    b = ctx.ctc_decode_host(lp, gasr.DOMAIN_LOG, 16, 0, synth.VOCAB29)
+    assert a == b
+    perm = np.random.default_rng(0).permutation(N)
+    c = ctx.ctc_decode_host(np.ascontiguousarray(lp[:, perm, :]), gasr.DOMAIN_LOG, 16, 0, synth.VOCAB29)
+    assert [a[0][i] for i in perm] == c[0] and [a[1][i] for i in perm] == c[1]
+    op, os_ = O.ctc_decode(np.ascontiguousarray(lp[:, :2, :]), synth.VOCAB29, 0, 16, domain="log", nthreads=2)
+    _assert_same(a[0][:2], a[1][:2], op, os_)
+    # cfg4: T = 4000, beam 8 / 32 / 128 (a few utterances; the oracle checks one at beam 8)
+    lp4 = synth.random_logprobs(77, 4000, 4, V)
+    for beam in (8, 32, 128):
+        r1 = ctx.ctc_decode_host(lp4, gasr.DOMAIN_LOG, beam, 0, synth.VOCAB29)
+        r2 = ctx.ctc_decode_host(lp4, gasr.DOMAIN_LOG, beam, 0, synth.VOCAB29)
+        assert r1 == r2 and all(len(p) > 0 for p in r1[0])
+        if beam == 8:
+            op, os_ = O.ctc_decode(np.ascontiguousarray(lp4[:, :1, :]), synth.VOCAB29, 0, 8, domain="log")
+            _assert_same(r1[0][:1], r1[1][:1], op, os_)
+
+
+def test_oracle_matches_reference_build(O):
+    """oracle/_ref = the reference's own sources compiled for sm_100a: inside its envelope (beam <= V, short T,
+    zeroed allocations) its top-1 strings must equal the oracle's (scores up to atomicAdd order: 1e-6 rel)."""
+    if O.ref_lib() is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    rng = np.random.default_rng(21)
+    for V, beam, T, N in ((4, 2, 10, 1), (4, 4, 8, 3), (6, 3, 12, 2), (8, 8, 10, 2)):
+        vocab = b"$abcdefg"[:V]
+        P = _softmax_probs(rng, T, N, V, scale=1.0)
+        rp, rs, rc = O.ref_ctc_decode(P, vocab, 0, beam)
+        op, os_ = O.ctc_decode(P, vocab, 0, beam, domain="prob", merge="hash31")
+        assert rp == op, (V, beam, T)
+        assert np.allclose(rs, os_, rtol=1e-5, atol=0)
+    g = json.load(open(os.path.join(GOLDEN, "nn_test.json")))
+    y, _ = O.ref_linear(np.array(g["linear"]["x"]), np.array(g["linear"]["w_in_out"]), np.array(g["linear"]["b"]))
+    assert np.abs(y - O.linear(np.array(g["linear"]["x"]), np.array(g["linear"]["w_in_out"]),
+                               np.array(g["linear"]["b"]))).max() < 1e-6
+    r = g["rnn"]
+    y, _ = O.ref_rnn(np.array(r["x_time_major"]), r["T"], r["N"], [np.array(r["w_ih"])], [np.array(r["w_hh"])],
+                     [np.array(r["b_ih"])], [np.array(r["b_hh"])])
+    ref = O.rnn_forward(np.array(r["x_time_major"]), r["T"], r["N"], [np.array(r["w_ih"])], [np.array(r["w_hh"])],
+                        [np.array(r["b_ih"])], [np.array(r["b_hh"])])[-1]
+    assert np.abs(y - ref).max() < 1e-6
+
+
+# ---------------------------------------------------------------- acoustic model ---------------------------
+def test_linear_and_rnn_nn_test_fixtures(gasr, ctx):
+    g = json.load(open(os.path.join(GOLDEN, "nn_test.json")))
+    lin = g["linear"]
+    inp = gasr.cuMatrix(np.array(lin["x"], dtype=np.float32), ctx=ctx).toGpu()
+    mlp = gasr.Linear(2, 3, 4, ctx=ctx).initParams(lin["w_in_out"], lin["b"])
+    out = mlp.forward(inp).toCpu().getHost()
+    assert np.abs(out - np.array(lin["expected_4dp"])).max() < 1e-4
+    r = g["rnn"]
+    x = gasr.cuMatrix(np.array(r["x_time_major"], dtype=np.float32), ctx=ctx).toGpu()
+    rnn = gasr.RNN(r["N"], r["in"], r["H"], r["T"], 1, ctx=ctx)
+    rnn.rnn_cell[0].initParams(r["w_ih"], r["w_hh"], r["b_ih"], r["b_hh"])
+    out = rnn.forward(x).toCpu().getHost()
+    assert np.abs(out - np.array(r["expected_4dp"])).max() < 1e-4
+    # one RNN_Cell step == first timestep
+    cell = rnn.rnn_cell[0]
+    x0 = gasr.cuMatrix(np.array(r["x_time_major"][:2], dtype=np.float32), ctx=ctx).toGpu()
+    h0 = gasr.cuMatrix(2, 5, ctx=ctx).toGpu()
+    o = gasr.cuMatrix(2, 5, ctx=ctx)
+    cell.forward(x0, h0, o)
+    assert np.abs(o.toCpu().getHost() - np.array(r["expected_4dp"][:2])).max() < 1e-4
+
+
+def test_matmul_variants_and_matadd(gasr, ctx, O):
+    rng = np.random.default_rng(4)
+    for m, k, n in ((1, 1, 1), (5, 7, 3), (130, 70, 129), (64, 161, 512), (300, 512, 29)):
+        x = rng.normal(size=(m, k)).astype(np.float32)
+        y = rng.normal(size=(k, n)).astype(np.float32)
+        ref = O.matmul(x, y)
+        X, Y, Z = gasr.cuMatrix(x, ctx=ctx).toGpu(), gasr.cuMatrix(y, ctx=ctx).toGpu(), gasr.cuMatrix(m, n, ctx=ctx)
+        gasr.matrixMul(X, Y, Z)
+        assert np.abs(Z.toCpu().getHost() - ref).max() < 1e-4 * max(1, np.abs(ref).max())
+        XT = gasr.cuMatrix(np.ascontiguousarray(x.T), ctx=ctx).toGpu()
+        gasr.matrixMulTA(XT, Y, Z)
+        assert np.abs(Z.toCpu().getHost() - ref).max() < 1e-4 * max(1, np.abs(ref).max())
+        YT = gasr.cuMatrix(np.ascontiguousarray(y.T), ctx=ctx).toGpu()
+        gasr.matrixMulTB(X, YT, Z)
+        assert np.abs(Z.toCpu().getHost() - ref).max() < 1e-4 * max(1, np.abs(ref).max())
+    a = rng.normal(size=(33, 17)).astype(np.float32)
+    b = rng.normal(size=(33, 17)).astype(np.float32)
+    A, B, C = gasr.cuMatrix(a, ctx=ctx).toGpu(), gasr.cuMatrix(b, ctx=ctx).toGpu(), gasr.cuMatrix(33, 17, ctx=ctx)
+    gasr.matrixAdd(A, B, C, 1.0)
+    assert (C.toCpu().getHost() == a + b).all()
+    gasr.matrixAdd(A, B, C, -0.5)
+    assert np.abs(C.toCpu().getHost() - (a - 0.5 * b)).max() < 1e-6
+    with pytest.raises(gasr.GasrError):
+        gasr.matrixMul(A, B, C)   # dimension mismatch is an error code, not exit(0)
+
+
+@pytest.mark.parametrize("rows,in_,out,act", [(1, 5, 3, "relu"), (77, 64, 29, "logsoftmax"), (1000, 512, 29, "logsoftmax"),
+                                              (130, 512, 32, "none"), (50, 300, 47, "logsoftmax"), (40, 2048, 47, "relu"),
+                                              (64, 1600, 29, "logsoftmax")])
+def test_linear_fused_activations(gasr, ctx, O, rows, in_, out, act):
+    rng = np.random.default_rng(rows + in_ + out)
+    x = rng.normal(size=(rows, in_)).astype(np.float32)
+    W = (rng.normal(size=(in_, out)) / np.sqrt(in_)).astype(np.float32)
+    b = rng.normal(size=(out,)).astype(np.float32)
+    ref = O.linear(x, W, b, act=act)
+    lin = gasr.Linear(rows, in_, out, act={"none": gasr.ACT_NONE, "relu": gasr.ACT_RELU,
+                                          "logsoftmax": gasr.ACT_LOGSOFTMAX}[act], ctx=ctx).initParams(W, b)
+    got = lin.forward(gasr.cuMatrix(x, ctx=ctx).toGpu()).toCpu().getHost()
+    assert np.abs(got - ref).max() < AM_TOL
+
+
+def _run_rnn(gasr, ctx, cell, bidir, T, N, D, H, L, x, w_ih, w_hh, b_ih, b_hh):
+    Dn = 2 if bidir else 1
+    dx = ctx.to_device(x)
+    dw = [[ctx.to_device(a) for a in lst] for lst in (w_ih, w_hh, b_ih, b_hh)]
+    hid = [ctx.malloc(T * N * Dn * H * 4) for _ in range(L)]
+    ctx.rnn_forward(cell, bidir, T, N, D, H, L, dw[0], dw[1], dw[2], dw[3], dx, hid)
+    out = [ctx.to_host(h, (T * N, Dn * H)) for h in hid]
+    for p in [dx] + sum(dw, []) + hid:
+        ctx.free(p)
+    return out
+
+
+def test_rnn_torch_goldens(gasr, ctx):
+    g = np.load(os.path.join(GOLDEN, "rnn3_torch.npz"))
+    T, N = int(g["T"]), int(g["N"])
+    out = _run_rnn(gasr, ctx, gasr.CELL_TANH, False, T, N, g["x"].shape[1], 32, 3, g["x"],
+                   [g[f"w_ih{l}"] for l in range(3)], [g[f"w_hh{l}"] for l in range(3)],
+                   [g[f"b_ih{l}"] for l in range(3)], [g[f"b_hh{l}"] for l in range(3)])
+    assert np.abs(out[-1] - g["y"]).max() < AM_TOL
+    g = np.load(os.path.join(GOLDEN, "bigru_torch.npz"))
+    T, N, H, L = int(g["T"]), int(g["N"]), int(g["H"]), int(g["L"])
+    keys = [(l, d) for l in range(L) for d in range(2)]
+    out = _run_rnn(gasr, ctx, gasr.CELL_GRU, True, T, N, g["x"].shape[1], H, L, g["x"],
+                   [g[f"w_ih{l}_{d}"] for l, d in keys], [g[f"w_hh{l}_{d}"] for l, d in keys],
+                   [g[f"b_ih{l}_{d}"] for l, d in keys], [g[f"b_hh{l}_{d}"] for l, d in keys])
+    assert np.abs(out[-1] - g["y"]).max() < AM_TOL
+
+
+def test_deepspeech_baseline_model_golden(gasr, ctx):
+    """baseline/model.py:37-49 on the GPU modules: 3x(Linear+ReLU) -> RNN -> Linear+ReLU -> Linear+log_softmax."""
+    g = np.load(os.path.join(GOLDEN, "deepspeech_small.npz"))
+    B, T, D = g["x_bt"].shape
+    x = gasr.cuMatrix(np.ascontiguousarray(g["x_bt"].transpose(1, 0, 2)).reshape(T * B, D), ctx=ctx).toGpu()
+    for i in range(3):
+        w = g[f"fc{i}_w"]
+        x = gasr.Linear(T * B, w.shape[0], w.shape[1], ctx=ctx).initParams(w, g[f"fc{i}_b"]).forward(x)
+    H = g["rnn_w_hh"].shape[0]
+    rnn = gasr.RNN(B, H, H, T, 1, ctx=ctx)
+    rnn.rnn_cell[0].initParams(g["rnn_w_ih"], g["rnn_w_hh"], g["rnn_b_ih"], g["rnn_b_hh"])
+    h = rnn.forward(x)
+    w = g["fc3_w"]
+    h = gasr.Linear(T * B, w.shape[0], w.shape[1], ctx=ctx).initParams(w, g["fc3_b"]).forward(h)
+    w = g["fc4_w"]
+    logp = gasr.Linear(T * B, w.shape[0], w.shape[1], act=gasr.ACT_LOGSOFTMAX, ctx=ctx).initParams(w, g["fc4_b"]).forward(h)
+    got = logp.toCpu().getHost().reshape(T, B, -1)
+    assert np.abs(got - g["logp_tnv"]).max() < AM_TOL
+
+
+@pytest.mark.parametrize("H,N,T,L", [(64, 5, 30, 2), (128, 16, 20, 1), (256, 33, 25, 2), (512, 64, 40, 3), (512, 7, 200, 1),
+                                     (96, 9, 12, 2)])
+def test_rnn_recurrence_vs_oracle(gasr, ctx, O, H, N, T, L):
+    import synth
+    D = 37
+    x = synth.spectrogram_batch(H + N, T, N, D)
+    w_ih, w_hh, b_ih, b_hh = synth.rnn_weights(H * 3 + 1, D, H, L)
+    out = _run_rnn(gasr, ctx, gasr.CELL_TANH, False, T, N, D, H, L, x, w_ih, w_hh, b_ih, b_hh)
+    ref = O.rnn_forward(x, T, N, w_ih, w_hh, b_ih, b_hh, nthreads=4)
+    for l in range(L):
+        assert np.abs(out[l] - ref[l]).max() < AM_TOL, f"layer {l}"
+
+
+def test_gru_bidirectional_vs_oracle(gasr, ctx, O):
+    import synth
+    T, N, D, H, L = 15, 6, 21, 40, 2
+    x = synth.spectrogram_batch(3, T, N, D)
+    w_ih, w_hh, b_ih, b_hh = synth.rnn_weights(4, D, H, L, cell_gates=3, bidir=True)
+    out = _run_rnn(gasr, ctx, gasr.CELL_GRU, True, T, N, D, H, L, x, w_ih, w_hh, b_ih, b_hh)
+    ref = O.gru_forward(x, T, N, H, L, True, w_ih, w_hh, b_ih, b_hh)
+    assert np.abs(out[-1] - ref[-1]).max() < AM_TOL
+
+
+# ---------------------------------------------------------------- end-to-end pipeline ----------------------
+@pytest.mark.parametrize("T,N,D,H,L,beam", [(60, 10, 161, 512, 3, 16), (33, 3, 20, 64, 1, 4)])
+def test_pipeline_end_to_end(gasr, ctx, O, T, N, D, H, L, beam):
+    import synth
+    V = 29
+    x = synth.spectrogram_batch(1234, T, N, D)
+    w_ih, w_hh, b_ih, b_hh = synth.rnn_weights(4321, D, H, L)
+    fc_w, fc_b = synth.fc_weights(99, H, V)
+    pipe = gasr.AsrPipeline(ctx, gasr.CELL_TANH, False, T, N, D, H, L, V, beam, 0, synth.VOCAB29)
+    pipe.set_weights(w_ih, w_hh, b_ih, b_hh, fc_w, fc_b)
+    paths, scores = pipe.run_host(x)
+    logp = pipe.logprobs()
+    ref_logp = O.linear(O.rnn_forward(x, T, N, w_ih, w_hh, b_ih, b_hh, nthreads=4)[-1], fc_w, fc_b, act="logsoftmax")
+    assert np.abs(logp - ref_logp).max() < AM_TOL
+    # decode parity on identical log-probs (the GPU's own), bit-exact
+    op, os_ = O.ctc_decode(logp.reshape(T, N, V), synth.VOCAB29, 0, beam, domain="log", nthreads=4)
+    _assert_same(paths, scores, op, os_)
+    # resident-input entry point gives the same answer
+    dx = ctx.to_device(x)
+    assert pipe.run_device(dx) == (paths, scores)
+    ctx.free(dx)
+    pipe.close()
