@@ -317,11 +317,27 @@ int gasr_rnn_cell_forward(gasr_ctx *ctx, const float *x, const float *h_prev, co
 
 namespace gasr {
 
+// Optional per-kernel timing: events recorded between launches on the same stream (no host sync).
+struct StageEvents {
+    std::vector<cudaEvent_t> pool;
+    std::vector<int> tag;        // tag[i] = stage that ends at event i (0 proj, 1 recurrence, 2 linear, 3 decode, -1 start)
+    size_t used = 0;
+    int mark(int stage, cudaStream_t st) {
+        if (used == pool.size()) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return GASR_ERR_CUDA;
+            pool.push_back(e); tag.push_back(-1);
+        }
+        tag[used] = stage;
+        return cudaEventRecord(pool[used++], st) == cudaSuccess ? GASR_OK : GASR_ERR_CUDA;
+    }
+};
+
 // One layer, one direction: xproj = src*W_ih + bias (all timesteps), then the persistent recurrence.
 static int rnn_layer_direction(gasr_ctx *ctx, int cell, int T, int N, int in_l, int H, const float *src, int ld_src,
                                const float *w_ih, const float *w_hh, const float *b_ih, const float *b_hh, int reverse,
                                float *out, int ldo, int col0, int precision, float *xproj, float *bias,
-                               cudaStream_t st) {
+                               cudaStream_t st, StageEvents *prof) {
     (void)precision;
     const int G = cell == GASR_CELL_GRU ? 3 : 1;
     if (cell == GASR_CELL_TANH) {
@@ -330,15 +346,18 @@ static int rnn_layer_direction(gasr_ctx *ctx, int cell, int T, int N, int in_l, 
         GASR_CUDA(cudaMemcpyAsync(bias, b_ih, sizeof(float) * G * H, cudaMemcpyDeviceToDevice, st));
     }
     GASR_TRY(launch_matmul(ctx, src, ld_src, 0, w_ih, G * H, 0, xproj, G * H, T * N, in_l, G * H, bias, st));
+    if (prof) GASR_TRY(prof->mark(0, st));
     RnnLayerArgs a;
     a.cell = cell; a.T = T; a.N = N; a.H = H; a.reverse = reverse;
     a.xproj = xproj; a.ldxp = G * H; a.w_hh = w_hh; a.b_hh = b_hh; a.out = out; a.ldo = ldo; a.col0 = col0;
-    return launch_rnn_recurrence(ctx, a, st);
+    GASR_TRY(launch_rnn_recurrence(ctx, a, st));
+    if (prof) GASR_TRY(prof->mark(1, st));
+    return GASR_OK;
 }
 
 int rnn_forward_impl(gasr_ctx *ctx, int cell, int bidir, int T, int N, int in, int H, int L, const float *const *w_ih,
                      const float *const *w_hh, const float *const *b_ih, const float *const *b_hh, const float *x,
-                     float *const *hiddens, int precision, cudaStream_t st) {
+                     float *const *hiddens, int precision, cudaStream_t st, StageEvents *prof = nullptr) {
     GASR_CHECK(cell == GASR_CELL_TANH || cell == GASR_CELL_GRU, "rnn_forward: unknown cell type %d", cell);
     GASR_CHECK(T >= 0 && N >= 0 && in >= 1 && H >= 1 && L >= 1, "rnn_forward: bad shape");
     GASR_CHECK(w_ih && w_hh && b_ih && b_hh && x && hiddens, "rnn_forward: null argument");
@@ -356,7 +375,7 @@ int rnn_forward_impl(gasr_ctx *ctx, int cell, int bidir, int T, int N, int in, i
             const int i = l * D + d;
             GASR_CHECK(w_ih[i] && w_hh[i] && b_ih[i] && b_hh[i] && hiddens[l], "rnn_forward: null layer parameter");
             GASR_TRY(rnn_layer_direction(ctx, cell, T, N, in_l, H, src, in_l, w_ih[i], w_hh[i], b_ih[i], b_hh[i], d,
-                                         hiddens[l], D * H, d * H, precision, xproj, bias, st));
+                                         hiddens[l], D * H, d * H, precision, xproj, bias, st, prof));
         }
     }
     return GASR_OK;
@@ -408,7 +427,7 @@ struct gasr_asr {
     std::vector<float *> w_ih, w_hh, b_ih, b_hh, hiddens;
     float *fc_w = nullptr, *fc_b = nullptr, *x_dev = nullptr, *logp = nullptr;
     bool have_weights = false;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    gasr::StageEvents prof;
     float stage_ms[4] = {0, 0, 0, 0};
 };
 
@@ -448,8 +467,6 @@ int gasr_asr_create(gasr_ctx *ctx, const gasr_asr_config *cfg, const char *vocab
     alloc(&a->fc_b, (size_t)cfg->V);
     alloc(&a->x_dev, rows * cfg->in);
     alloc(&a->logp, rows * a->ldp);
-    for (int i = 0; i < 5 && st == GASR_OK; i++)
-        if (cudaEventCreate(&a->ev[i]) != cudaSuccess) { set_error("event creation failed"); st = GASR_ERR_CUDA; }
     if (st != GASR_OK) { gasr_asr_destroy(a); return st; }
     *out = a;
     return GASR_OK;
@@ -463,7 +480,7 @@ int gasr_asr_destroy(gasr_asr *a) {
     for (auto v : {&a->w_ih, &a->w_hh, &a->b_ih, &a->b_hh, &a->hiddens})
         for (float *p : *v) if (p) gasr_free_device(ctx, p);
     for (float *p : {a->fc_w, a->fc_b, a->x_dev, a->logp}) if (p) gasr_free_device(ctx, p);
-    for (int i = 0; i < 5; i++) if (a->ev[i]) cudaEventDestroy(a->ev[i]);
+    for (cudaEvent_t e : a->prof.pool) cudaEventDestroy(e);
     delete a;
     return GASR_OK;
 }
@@ -502,22 +519,24 @@ int gasr_asr_run_device(gasr_asr *a, const float *x_dev, char *out_paths, int *o
     const gasr_asr_config &c = a->cfg;
     cudaStream_t st = ctx->stream;
     const int rows = c.T * c.N;
-    GASR_CUDA(cudaEventRecord(a->ev[0], st));
+    a->prof.used = 0;
+    GASR_TRY(a->prof.mark(-1, st));
     GASR_TRY(rnn_forward_impl(ctx, c.cell, c.bidirectional, c.T, c.N, c.in, c.H, c.L, a->w_ih.data(), a->w_hh.data(),
-                              a->b_ih.data(), a->b_hh.data(), x_dev, a->hiddens.data(), c.precision, st));
-    GASR_CUDA(cudaEventRecord(a->ev[1], st));
+                              a->b_ih.data(), a->b_hh.data(), x_dev, a->hiddens.data(), c.precision, st, &a->prof));
     GASR_TRY(launch_linear(ctx, a->hiddens[c.L - 1], a->D * c.H, a->fc_w, a->fc_b, a->logp, a->ldp, rows, a->D * c.H,
                            c.V, GASR_ACT_LOGSOFTMAX, st));
-    GASR_CUDA(cudaEventRecord(a->ev[2], st));
+    GASR_TRY(a->prof.mark(2, st));
     CtcArgs ca = {a->logp, GASR_DOMAIN_LOG, c.T, c.N, c.V, a->ldp, c.beam, c.blank, a->vocab.data(), c.max_len,
                   c.nbest, out_paths, out_lens, out_scores, nullptr};
     GASR_TRY(ctc_decode_launch(ctx, ca, st));
-    GASR_CUDA(cudaEventRecord(a->ev[3], st));
+    GASR_TRY(a->prof.mark(3, st));
     GASR_CUDA(cudaStreamSynchronize(st));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, a->ev[0], a->ev[1]); a->stage_ms[0] = 0; a->stage_ms[1] = ms;
-    cudaEventElapsedTime(&ms, a->ev[1], a->ev[2]); a->stage_ms[2] = ms;
-    cudaEventElapsedTime(&ms, a->ev[2], a->ev[3]); a->stage_ms[3] = ms;
+    for (int i = 0; i < 4; i++) a->stage_ms[i] = 0.0f;
+    for (size_t i = 1; i < a->prof.used; i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a->prof.pool[i - 1], a->prof.pool[i]);
+        if (a->prof.tag[i] >= 0) a->stage_ms[a->prof.tag[i]] += ms;
+    }
     return ctc_decode_finish(ctx, ca);
 }
 
