@@ -106,7 +106,7 @@ __device__ __forceinline__ float mrg(float a, float b) {
 
 // raw-string order of two candidates = (trie node, optional suffix char): walk both up to the lowest common
 // ancestor and compare the first characters after it (reference operator<, CTCBeamSearch.cu:137-147).
-__device__ bool raw_less(const int *__restrict__ parent, const int *__restrict__ meta, const char *vocab, int na,
+__device__ __noinline__ bool raw_less(const int *__restrict__ parent, const int *__restrict__ meta, const char *vocab, int na,
                          int sufa, int nb, int sufb) {
     int da = meta[na] >> 8, db = meta[nb] >> 8;
     const int lena = da + (sufa ? 1 : 0), lenb = db + (sufb ? 1 : 0);
@@ -408,6 +408,286 @@ __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
     }
 }
 
+// =====================================================================================================
+// Fast path: ONE WARP PER UTTERANCE (beam <= 32, vocabulary <= 32).  lane = vocabulary id, so the V candidates of a
+// parent state are evaluated by one warp instruction stream with the parent's fields warp-uniform; the merged
+// candidate scores stay in registers (val[i] of lane v = candidate i*V+v), and the prune is beam rounds of
+// "warp max" (REDUX) extraction, which yields the kept states already in rank order.  There is no block-level
+// barrier at all: warps of a CTA decode different utterances and only use __syncwarp().
+// Same CTC-REF semantics, bit for bit, as ctc_beam_kernel below.
+// =====================================================================================================
+template <int BMAX>
+struct WarpBeam {
+    float sc[2][BMAX];
+    int node[2][BMAX];
+    int pnode[2][BMAX];
+    int depth[2][BMAX];
+    int pk[2][BMAX];          // last label (0xff = none) | eb << 8
+    int tw[BMAX], p0[BMAX], p1[BMAX];
+    unsigned abs0[BMAX], abs1[BMAX];
+    float stay[BMAX];
+    unsigned selkey[BMAX];
+    int seli[BMAX], selv[BMAX];
+    unsigned cand[BMAX][32];  // merged candidate keys, [parent rank][vocab id]; 0 = absorbed / absent
+};
+
+__device__ __forceinline__ int cand_suffix(int v, int blank, int ebi, int lasti, const char *vch) {
+    if (v == blank) return vch[blank];
+    if (ebi == 0 && v == lasti) return 0;
+    return vch[v];
+}
+
+template <int DOMAIN, int BMAX>
+__global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int utt = blockIdx.x * W + warp;
+    if (utt >= p.N) return;
+    WarpBeam<BMAX> &wb = reinterpret_cast<WarpBeam<BMAX> *>(smem_raw)[warp];
+    __shared__ char vch_s[32];
+    const int V = p.V, B = p.beam, blank = p.blank, Vp = p.Vp;
+    constexpr unsigned FULL = 0xffffffffu;
+    const bool active = lane < V;
+
+    int *parent = p.parent + (size_t)utt * p.cap;
+    int *meta = p.meta + (size_t)utt * p.cap;
+    int *child = p.child + (size_t)utt * p.cap * Vp;
+    const float *S = p.scores + (size_t)utt * p.ld;
+    const size_t frame_stride = (size_t)p.N * p.ld;
+
+    // every warp writes the same bytes; only __syncwarp ordering is needed for its own reads
+    if (active) vch_s[lane] = p.vocab[lane];
+    const char *vch = vch_s;
+    if (lane < Vp) child[lane] = 0;
+    if (lane == 0) {
+        parent[0] = -1; meta[0] = 0xff;
+        wb.sc[0][0] = DOMAIN ? 0.0f : 1.0f;
+        wb.node[0][0] = 0; wb.pnode[0][0] = kNone; wb.depth[0][0] = 0; wb.pk[0][0] = 0xff | (1 << 8);
+    }
+    int kept = 1, nodes = 1, cur = 0;
+    float lp_next = active ? S[lane] : 0.0f;
+    __syncwarp();
+
+    for (int t = 0; t < p.T; t++) {
+        const float lp = lp_next;
+        if (t + 1 < p.T && active) lp_next = S[(size_t)(t + 1) * frame_stride + lane];
+        const bool last_frame = (t == p.T - 1) && (t > 0);
+        const int k = kept;
+        const float *sc = wb.sc[cur];
+        const int *node = wb.node[cur], *pnode = wb.pnode[cur], *pk = wb.pk[cur], *depth = wb.depth[cur];
+        const float lpb = __shfl_sync(FULL, lp, blank);
+
+        // ---- relations among kept states (lane r owns state r) ------------------------------------------
+        int my_last = 0xff, my_eb = 1, my_tw = kNone, my_p0 = kNone, my_p1 = kNone;
+        if (lane < k) {
+            const int nd = node[lane], pn = pnode[lane];
+            my_last = pk[lane] & 0xff; my_eb = (pk[lane] >> 8) & 1;
+            unsigned a0 = 0, a1 = 0;
+            for (int j = 0; j < k; j++) {
+                const int nj = node[j], pnj = pnode[j], pkj = pk[j];
+                if (nj == nd && j != lane) my_tw = j;
+                if (nj == pn) { if ((pkj >> 8) & 1) my_p1 = j; else my_p0 = j; }
+                if (pnj == nd) { const unsigned bit = 1u << (pkj & 0xff); if ((pkj >> 8) & 1) a1 |= bit; else a0 |= bit; }
+            }
+            wb.tw[lane] = my_tw; wb.p0[lane] = my_p0; wb.p1[lane] = my_p1; wb.abs0[lane] = a0; wb.abs1[lane] = a1;
+        }
+        // ---- "stay" candidates, one per (X,0) state, all lanes in parallel ------------------------------
+        {
+            const bool do_stay = lane < k && my_eb == 0;
+            const float lpv = __shfl_sync(FULL, lp, do_stay ? my_last : 0);
+            if (do_stay) {
+                int m0 = my_p0, m1 = my_p1, m2 = lane, tmp;
+                if (m0 >= 0 && (pk[m0] & 0xff) == my_last) m0 = kNone;    // (P,0)+v with last(P)==v stays on P
+                if (m0 > m1) { tmp = m0; m0 = m1; m1 = tmp; }
+                if (m1 > m2) { tmp = m1; m1 = m2; m2 = tmp; }
+                if (m0 > m1) { tmp = m0; m0 = m1; m1 = tmp; }
+                // chain in ascending state index; absent members (-1) sorted to the front, m2 is always present
+                float acc = comb<DOMAIN>(sc[m0 >= 0 ? m0 : (m1 >= 0 ? m1 : m2)], lpv);
+                if (m0 >= 0) acc = mrg<DOMAIN>(acc, comb<DOMAIN>(sc[m1], lpv));
+                if (m1 >= 0) acc = mrg<DOMAIN>(acc, comb<DOMAIN>(sc[m2], lpv));
+                if (last_frame) {
+                    int b0 = lane, b1 = my_tw;
+                    if (b1 >= 0 && b1 < b0) { b0 = my_tw; b1 = lane; }
+                    acc = mrg<DOMAIN>(acc, comb<DOMAIN>(sc[b0], lpb));
+                    if (b1 >= 0) acc = mrg<DOMAIN>(acc, comb<DOMAIN>(sc[b1], lpb));
+                }
+                wb.stay[lane] = acc;
+            }
+        }
+        __syncwarp();
+
+        // ---- merged candidate scores: val[i] of lane v  <->  candidate i*V + v -----------------------------
+        for (int i = 0; i < k; i++) {
+            unsigned key = 0u;
+            {
+                const float sci = sc[i];
+                const int pki = pk[i], twi = wb.tw[i];
+                const int ebi = (pki >> 8) & 1, lasti = pki & 0xff;
+                const float s = comb<DOMAIN>(sci, lp);
+                float acc = s;
+                bool dead = false;
+                const bool is_stay = (ebi == 0 && lane == lasti);
+                const bool is_blank = (lane == blank);
+                const bool member = twi >= 0 && (is_blank || ebi == 0 || lane != lasti);
+                if (!last_frame || !is_blank) {
+                    if (twi >= 0) {
+                        if (twi < i) dead = member;
+                        else {
+                            const float m = mrg<DOMAIN>(s, comb<DOMAIN>(sc[twi], lp));
+                            acc = member ? m : s;
+                        }
+                    }
+                    if (!is_blank && ((wb.abs0[i] >> lane) & 1u)) dead = true;   // kept (X.v, 0) hosts this extend
+                    if (last_frame && !dead && !is_stay && ((wb.abs1[i] >> lane) & 1u)) {
+                        // kept (X.v, 1): on the last frame its blank candidate strips to X.v as well
+                        const int nd = node[i];
+                        for (int j = 0; j < k; j++)
+                            if (pnode[j] == nd && (pk[j] & 0xff) == lane && ((pk[j] >> 8) & 1))
+                                acc = mrg<DOMAIN>(acc, comb<DOMAIN>(sc[j], lpb));
+                    }
+                } else {
+                    // blank candidate on the last frame: it strips to X, so the (X,0) stay slot or an extend slot
+                    // that spells X hosts it; otherwise it stands alone
+                    if (ebi == 0 || twi >= 0) dead = true;
+                    else if (lasti != 0xff) {
+                        const int q0 = wb.p0[i], q1 = wb.p1[i];
+                        if (q1 >= 0 || (q0 >= 0 && (pk[q0] & 0xff) != lasti)) dead = true;
+                    }
+                }
+                if (is_stay) { acc = wb.stay[i]; dead = false; }
+                if (active && !dead) key = f2ord(acc);
+            }
+            wb.cand[i][lane] = key;
+        }
+        unsigned val[BMAX];
+#pragma unroll
+        for (int i = 0; i < BMAX; i++) val[i] = i < k ? wb.cand[i][lane] : 0u;
+
+        // ---- prune: beam rounds of warp-max extraction -> kept states in rank order -------------------------
+        int m = 0;
+        bool tie = false;
+        unsigned prev = 0u;
+        for (; m < B; m++) {
+            unsigned lmax = 0u;
+#pragma unroll
+            for (int i = 0; i < BMAX; i++) lmax = max(lmax, val[i]);
+            const unsigned gmax = __reduce_max_sync(FULL, lmax);
+            if (gmax == 0u) break;
+            int li = BMAX;
+#pragma unroll
+            for (int i = BMAX - 1; i >= 0; i--) if (val[i] == gmax) li = i;
+            const unsigned myidx = (li < BMAX) ? (unsigned)(li * V + lane) : 0xffffffffu;
+            const unsigned gidx = __reduce_min_sync(FULL, myidx);
+            const bool win = myidx == gidx;
+            const int wl = __ffs(__ballot_sync(FULL, win)) - 1;
+            const int wi = __shfl_sync(FULL, li, wl);
+#pragma unroll
+            for (int i = 0; i < BMAX; i++) if (win && i == li) val[i] = 0u;
+            if (lane == 0) { wb.selkey[m] = gmax; wb.seli[m] = wi; wb.selv[m] = wl; }
+            if (t > 0 && gmax == prev) tie = true;
+            prev = gmax;
+        }
+        if (t > 0 && m == B) {   // a tie across the cut?
+            unsigned lmax = 0u;
+#pragma unroll
+            for (int i = 0; i < BMAX; i++) lmax = max(lmax, val[i]);
+            if (__reduce_max_sync(FULL, lmax) == prev) tie = true;
+        }
+        __syncwarp();
+        if (tie) {
+            // ---- rare slow path: redo the selection on the staged keys; equal scores are ordered by raw string ---
+            for (m = 0; m < B; m++) {
+                unsigned lmax = 0u;
+                for (int i = 0; i < k; i++) lmax = max(lmax, wb.cand[i][lane]);
+                const unsigned gmax = __reduce_max_sync(FULL, lmax);
+                if (gmax == 0u) break;
+                // local best (smallest raw string) among this lane's candidates with the top score
+                int bi = -1, bnode = 0, bsuf = 0;
+                for (int i = 0; i < k; i++) {
+                    if (wb.cand[i][lane] == gmax) {
+                        const int pki = pk[i];
+                        const int suf = cand_suffix(lane, blank, (pki >> 8) & 1, pki & 0xff, vch);
+                        if (bi < 0 || raw_less(parent, meta, vch, node[i], suf, bnode, bsuf)) { bi = i; bnode = node[i]; bsuf = suf; }
+                    }
+                }
+                int bl = lane;
+                for (int off = 16; off > 0; off >>= 1) {
+                    const int oi = __shfl_xor_sync(FULL, bi, off), on = __shfl_xor_sync(FULL, bnode, off);
+                    const int os = __shfl_xor_sync(FULL, bsuf, off), ol = __shfl_xor_sync(FULL, bl, off);
+                    bool take = false;
+                    if (oi >= 0) {
+                        if (bi < 0) take = true;
+                        else if (raw_less(parent, meta, vch, on, os, bnode, bsuf)) take = true;
+                        else if (!raw_less(parent, meta, vch, bnode, bsuf, on, os)) take = (oi * V + ol) < (bi * V + bl);
+                    }
+                    if (take) { bi = oi; bnode = on; bsuf = os; bl = ol; }
+                }
+                if (lane == bl) wb.cand[bi][lane] = 0u;
+                if (lane == 0) { wb.selkey[m] = gmax; wb.seli[m] = bi; wb.selv[m] = bl; }
+                __syncwarp();
+            }
+            __syncwarp();
+        }
+
+        // ---- the selected candidates become the next kept states (lane r builds state r) ---------------------
+        {
+            const int nxt = cur ^ 1;
+            bool need_new = false;
+            int i = 0, v = 0, nd = 0, pn = 0, dp = 0, npk = 0;
+            if (lane < m) {
+                i = wb.seli[lane]; v = wb.selv[lane];
+                const int pki = pk[i];
+                const int ebi = (pki >> 8) & 1, lasti = pki & 0xff;
+                if (v == blank) { nd = node[i]; pn = pnode[i]; dp = depth[i]; npk = lasti | (1 << 8); }
+                else if (ebi == 0 && v == lasti) { nd = node[i]; pn = pnode[i]; dp = depth[i]; npk = lasti; }
+                else {
+                    pn = node[i]; dp = depth[i] + 1; npk = v;
+                    nd = child[(size_t)pn * Vp + v];
+                    need_new = nd == 0;
+                }
+            }
+            const unsigned nb = __ballot_sync(FULL, need_new);
+            if (need_new) {
+                nd = nodes + __popc(nb & ((1u << lane) - 1u));
+                parent[nd] = pn;
+                meta[nd] = (dp << 8) | v;
+                child[(size_t)pn * Vp + v] = nd;
+                int4 *row = reinterpret_cast<int4 *>(child + (size_t)nd * Vp);
+                for (int q = 0; q < Vp / 4; q++) row[q] = make_int4(0, 0, 0, 0);
+            }
+            nodes += __popc(nb);
+            if (lane < m) {
+                wb.sc[nxt][lane] = ord2f(wb.selkey[lane]);
+                wb.node[nxt][lane] = nd; wb.pnode[nxt][lane] = pn; wb.depth[nxt][lane] = dp; wb.pk[nxt][lane] = npk;
+            }
+            kept = m;
+            cur = nxt;
+        }
+        __syncwarp();
+    }
+
+    // ---- result (CTCBeamSearch.cu:290-298): kept states best first, path = labels of X -------------------------
+    if (lane == 0 && p.out_counts) p.out_counts[utt] = kept;
+    for (int r = lane; r < p.nbest; r += 32) {
+        char *out = p.out_paths + ((size_t)utt * p.nbest + r) * p.max_len;
+        int len = 0;
+        float scv = 0.0f;
+        if (r < kept) {
+            int nd = wb.node[cur][r];
+            const int dpt = wb.depth[cur][r];
+            len = dpt;
+            if (p.T == 1 && ((wb.pk[cur][r] >> 8) & 1)) { if (len < p.max_len) out[len] = vch[blank]; len += 1; }
+            for (int pos = dpt - 1; pos >= 0; pos--) {
+                if (pos < p.max_len) out[pos] = vch[meta[nd] & 0xff];
+                nd = parent[nd];
+            }
+            scv = wb.sc[cur][r];
+        }
+        p.out_lens[(size_t)utt * p.nbest + r] = len;
+        p.out_scores[(size_t)utt * p.nbest + r] = scv;
+    }
+}
+
 static size_t ctc_smem_bytes(int B, int V, int Vp, int n_pad) {
     size_t s = sizeof(unsigned long long) * n_pad + sizeof(float) * Vp;
     s += (sizeof(float) + 2 * sizeof(int)) * 2 * B;   // score, node, pnode (x2 buffers)
@@ -466,7 +746,7 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
     if (a.N == 0) return GASR_OK;
     CtcLayout L;
     ctc_layout(a, L);
-    if (L.smem > (size_t)ctx->max_smem_optin) {
+    if (!(a.beam <= 32 && a.V <= 32) && L.smem > (size_t)ctx->max_smem_optin) {
         set_error("ctc_decode: beam %d x vocab %d needs %zu B of shared memory (> %d)", a.beam, a.V, L.smem,
                   ctx->max_smem_optin);
         return GASR_ERR_UNSUPPORTED;
@@ -491,18 +771,37 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
     p.out_counts = reinterpret_cast<int *>(wo + L.off_counts);
 
     GASR_CUDA(cudaMemsetAsync(wo + L.off_paths, 0, (size_t)a.N * a.nbest * a.max_len, st));
+    if (a.beam <= 32 && a.V <= 32) {
+        // warp-per-utterance fast path; few warps per CTA when utterances are scarce (latency), 8 when plentiful
+        int W = ceil_div(a.N, ctx->sm_count);
+        if (W > 8) W = 8;
+        const int blocks = ceil_div(a.N, W);
+#define GASR_CTCW_LAUNCH(DOM, BM)                                                                                \
+    do {                                                                                                          \
+        GASR_CUDA(cudaFuncSetAttribute(ctc_beam_warp_kernel<DOM, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)(sizeof(WarpBeam<BM>) * 8)));                                         \
+        ctc_beam_warp_kernel<DOM, BM><<<blocks, W * 32, sizeof(WarpBeam<BM>) * W, st>>>(p);                       \
+    } while (0)
+        if (a.domain == GASR_DOMAIN_LOG) {
+            if (a.beam <= 16) GASR_CTCW_LAUNCH(1, 16); else GASR_CTCW_LAUNCH(1, 32);
+        } else {
+            if (a.beam <= 16) GASR_CTCW_LAUNCH(0, 16); else GASR_CTCW_LAUNCH(0, 32);
+        }
+#undef GASR_CTCW_LAUNCH
+    } else {
 #define GASR_CTC_LAUNCH(DOM, MT)                                                                                  \
     do {                                                                                                          \
         GASR_CUDA(cudaFuncSetAttribute(ctc_beam_kernel<DOM, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                        (int)L.smem));                                                             \
         ctc_beam_kernel<DOM, MT><<<a.N, L.threads, L.smem, st>>>(p);                                              \
     } while (0)
-    if (a.domain == GASR_DOMAIN_LOG) {
-        if (L.threads <= 256) GASR_CTC_LAUNCH(1, 256); else GASR_CTC_LAUNCH(1, 1024);
-    } else {
-        if (L.threads <= 256) GASR_CTC_LAUNCH(0, 256); else GASR_CTC_LAUNCH(0, 1024);
-    }
+        if (a.domain == GASR_DOMAIN_LOG) {
+            if (L.threads <= 256) GASR_CTC_LAUNCH(1, 256); else GASR_CTC_LAUNCH(1, 1024);
+        } else {
+            if (L.threads <= 256) GASR_CTC_LAUNCH(0, 256); else GASR_CTC_LAUNCH(0, 1024);
+        }
 #undef GASR_CTC_LAUNCH
+    }
     GASR_CUDA(cudaGetLastError());
     ctx->launches += 1;
     GASR_CUDA(cudaMemcpyAsync(ctx->pinned_out, wo, L.out_bytes, cudaMemcpyDeviceToHost, st));
