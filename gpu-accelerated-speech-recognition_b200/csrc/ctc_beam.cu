@@ -414,27 +414,71 @@ __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
 // candidate scores stay in registers (val[i] of lane v = candidate i*V+v), and the prune is beam rounds of
 // "warp max" (REDUX) extraction, which yields the kept states already in rank order.  There is no block-level
 // barrier at all: warps of a CTA decode different utterances and only use __syncwarp().
+//
+// Exact score ties are common (fp32 spacing is ~2.4e-4 at |score| ~ 3000), so the raw-string tie-break must be
+// O(1): the warp keeps rel[i][j], the lexicographic relation between the label prefixes of kept states i and j
+// (equal / first difference inside both / one is a proper prefix of the other + the next character), and updates
+// it incrementally when the beam moves -- children only append one character, so the new relation is a function
+// of the old one and the two appended characters.  No trie walk on the hot path.
 // Same CTC-REF semantics, bit for bit, as ctc_beam_kernel below.
 // =====================================================================================================
+constexpr int REL_EQ = 0, REL_LT = 1, REL_GT = 2, REL_PFX = 3, REL_RPFX = 3 + 32;   // PFX + y / RPFX + y (y < 32)
+
 template <int BMAX>
 struct WarpBeam {
     float sc[2][BMAX];
     int node[2][BMAX];
-    int pnode[2][BMAX];
     int depth[2][BMAX];
     int pk[2][BMAX];          // last label (0xff = none) | eb << 8
+    int4 pinfo[BMAX];         // per kept state: {score, twin's score, pk | (twin + 1) << 9, abs0} for the candidate loop
     int tw[BMAX], p0[BMAX], p1[BMAX];
     unsigned abs0[BMAX], abs1[BMAX];
     float stay[BMAX];
     unsigned selkey[BMAX];
     int seli[BMAX], selv[BMAX];
-    unsigned cand[BMAX][32];  // merged candidate keys, [parent rank][vocab id]; 0 = absorbed / absent
+    unsigned char rel[2][BMAX][BMAX];
+    unsigned cand[BMAX][32];  // merged candidate keys staged [parent rank][vocab id]; 0 = absorbed / absent
 };
 
-__device__ __forceinline__ int cand_suffix(int v, int blank, int ebi, int lasti, const char *vch) {
-    if (v == blank) return vch[blank];
-    if (ebi == 0 && v == lasti) return 0;
-    return vch[v];
+// the character at 0-based position pos of the label string of trie node nd (depth(nd) > pos); rare path
+__device__ __noinline__ int trie_char_at(const int *__restrict__ parent, const int *__restrict__ meta, int nd, int pos) {
+    while ((meta[nd] >> 8) > pos + 1) nd = parent[nd];
+    return meta[nd] & 0xff;
+}
+
+__device__ __forceinline__ bool ch_less(const char *vch, int a, int b) { return (signed char)vch[a] < (signed char)vch[b]; }
+
+// label appended to the prefix when candidate (state pk, vocab id v) is kept: -1 = none (stay / blank)
+__device__ __forceinline__ int cand_ext_id(int v, int blank, int pki) {
+    if (v == blank) return -1;
+    if (((pki >> 8) & 1) == 0 && v == (pki & 0xff)) return -1;
+    return v;
+}
+
+// suffix of candidate (state with pk, vocab id v): -1 = none ("stay"), otherwise the appended vocab id
+__device__ __forceinline__ int cand_suffix_id(int v, int blank, int pki) {
+    if (v == blank) return blank;
+    if (((pki >> 8) & 1) == 0 && v == (pki & 0xff)) return -1;
+    return v;
+}
+
+// raw-string order of candidates (i, sa) and (j, sb) from the relation R = rel[i][j] of their label prefixes
+__device__ __forceinline__ bool cand_less_rel(int R, int sa, int sb, const char *vch) {
+    if (R == REL_EQ) {
+        if (sa < 0) return sb >= 0;
+        if (sb < 0 || sa == sb) return false;
+        return ch_less(vch, sa, sb);
+    }
+    if (R == REL_LT) return true;
+    if (R == REL_GT) return false;
+    if (R < REL_RPFX) {                 // X_i is a proper prefix of X_j, next char y
+        const int y = R - REL_PFX;
+        if (sa < 0 || sa == y) return true;
+        return ch_less(vch, sa, y);
+    }
+    const int y = R - REL_RPFX;         // X_j is a proper prefix of X_i
+    if (sb < 0 || sb == y) return false;
+    return ch_less(vch, y, sb);
 }
 
 template <int DOMAIN, int BMAX>
@@ -462,7 +506,8 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
     if (lane == 0) {
         parent[0] = -1; meta[0] = 0xff;
         wb.sc[0][0] = DOMAIN ? 0.0f : 1.0f;
-        wb.node[0][0] = 0; wb.pnode[0][0] = kNone; wb.depth[0][0] = 0; wb.pk[0][0] = 0xff | (1 << 8);
+        wb.node[0][0] = 0; wb.depth[0][0] = 0; wb.pk[0][0] = 0xff | (1 << 8);
+        wb.rel[0][0][0] = REL_EQ;
     }
     int kept = 1, nodes = 1, cur = 0;
     float lp_next = active ? S[lane] : 0.0f;
@@ -474,22 +519,28 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
         const bool last_frame = (t == p.T - 1) && (t > 0);
         const int k = kept;
         const float *sc = wb.sc[cur];
-        const int *node = wb.node[cur], *pnode = wb.pnode[cur], *pk = wb.pk[cur], *depth = wb.depth[cur];
+        const int *node = wb.node[cur], *pk = wb.pk[cur], *depth = wb.depth[cur];
+        const unsigned char (*rel)[BMAX] = wb.rel[cur];
         const float lpb = __shfl_sync(FULL, lp, blank);
 
-        // ---- relations among kept states (lane r owns state r) ------------------------------------------
+        // ---- relations among kept states, read off the prefix-relation matrix (lane r owns state r) ---------
         int my_last = 0xff, my_eb = 1, my_tw = kNone, my_p0 = kNone, my_p1 = kNone;
         if (lane < k) {
-            const int nd = node[lane], pn = pnode[lane];
+            const int dr = depth[lane];
             my_last = pk[lane] & 0xff; my_eb = (pk[lane] >> 8) & 1;
             unsigned a0 = 0, a1 = 0;
             for (int j = 0; j < k; j++) {
-                const int nj = node[j], pnj = pnode[j], pkj = pk[j];
-                if (nj == nd && j != lane) my_tw = j;
-                if (nj == pn) { if ((pkj >> 8) & 1) my_p1 = j; else my_p0 = j; }
-                if (pnj == nd) { const unsigned bit = 1u << (pkj & 0xff); if ((pkj >> 8) & 1) a1 |= bit; else a0 |= bit; }
+                const int R = rel[lane][j], pkj = pk[j], dj = depth[j];
+                if (R == REL_EQ && j != lane) my_tw = j;
+                if (R >= REL_RPFX && dr == dj + 1) { if ((pkj >> 8) & 1) my_p1 = j; else my_p0 = j; }   // X_j = parent(X_r)
+                if (R >= REL_PFX && R < REL_RPFX && dj == dr + 1) {                                        // X_j = X_r . y
+                    const unsigned bit = 1u << (R - REL_PFX);
+                    if ((pkj >> 8) & 1) a1 |= bit; else a0 |= bit;
+                }
             }
             wb.tw[lane] = my_tw; wb.p0[lane] = my_p0; wb.p1[lane] = my_p1; wb.abs0[lane] = a0; wb.abs1[lane] = a1;
+            wb.pinfo[lane] = make_int4(__float_as_int(sc[lane]), __float_as_int(my_tw >= 0 ? sc[my_tw] : 0.0f),
+                                       pk[lane] | ((my_tw + 1) << 9), (int)a0);
         }
         // ---- "stay" candidates, one per (X,0) state, all lanes in parallel ------------------------------
         {
@@ -517,129 +568,104 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
         __syncwarp();
 
         // ---- merged candidate scores: val[i] of lane v  <->  candidate i*V + v -----------------------------
+        unsigned lmax = 0u;   // this lane's column maximum over the merged candidate keys
+#pragma unroll 4
         for (int i = 0; i < k; i++) {
-            unsigned key = 0u;
-            {
-                const float sci = sc[i];
-                const int pki = pk[i], twi = wb.tw[i];
-                const int ebi = (pki >> 8) & 1, lasti = pki & 0xff;
-                const float s = comb<DOMAIN>(sci, lp);
-                float acc = s;
-                bool dead = false;
-                const bool is_stay = (ebi == 0 && lane == lasti);
-                const bool is_blank = (lane == blank);
-                const bool member = twi >= 0 && (is_blank || ebi == 0 || lane != lasti);
-                if (!last_frame || !is_blank) {
-                    if (twi >= 0) {
-                        if (twi < i) dead = member;
-                        else {
-                            const float m = mrg<DOMAIN>(s, comb<DOMAIN>(sc[twi], lp));
-                            acc = member ? m : s;
-                        }
-                    }
-                    if (!is_blank && ((wb.abs0[i] >> lane) & 1u)) dead = true;   // kept (X.v, 0) hosts this extend
-                    if (last_frame && !dead && !is_stay && ((wb.abs1[i] >> lane) & 1u)) {
-                        // kept (X.v, 1): on the last frame its blank candidate strips to X.v as well
-                        const int nd = node[i];
-                        for (int j = 0; j < k; j++)
-                            if (pnode[j] == nd && (pk[j] & 0xff) == lane && ((pk[j] >> 8) & 1))
-                                acc = mrg<DOMAIN>(acc, comb<DOMAIN>(sc[j], lpb));
-                    }
-                } else {
-                    // blank candidate on the last frame: it strips to X, so the (X,0) stay slot or an extend slot
-                    // that spells X hosts it; otherwise it stands alone
-                    if (ebi == 0 || twi >= 0) dead = true;
-                    else if (lasti != 0xff) {
-                        const int q0 = wb.p0[i], q1 = wb.p1[i];
-                        if (q1 >= 0 || (q0 >= 0 && (pk[q0] & 0xff) != lasti)) dead = true;
+            const int4 pi = wb.pinfo[i];
+            const float sci = __int_as_float(pi.x);
+            const int pki = pi.z & 0x1ff, twi = ((pi.z >> 9) & 0x3f) - 1;
+            const int ebi = (pki >> 8) & 1, lasti = pki & 0xff;
+            const float s = comb<DOMAIN>(sci, lp);
+            float acc = s;
+            bool dead = false;
+            const bool is_stay = (ebi == 0 && lane == lasti);
+            const bool is_blank = (lane == blank);
+            const bool member = twi >= 0 && (is_blank || ebi == 0 || lane != lasti);
+            if (!last_frame || !is_blank) {
+                if (twi >= 0) {
+                    if (twi < i) dead = member;
+                    else {
+                        const float mm = mrg<DOMAIN>(s, comb<DOMAIN>(__int_as_float(pi.y), lp));
+                        acc = member ? mm : s;
                     }
                 }
-                if (is_stay) { acc = wb.stay[i]; dead = false; }
-                if (active && !dead) key = f2ord(acc);
+                if (!is_blank && (((unsigned)pi.w >> lane) & 1u)) dead = true;   // kept (X.v, 0) hosts this extend
+                if (last_frame && !dead && !is_stay && ((wb.abs1[i] >> lane) & 1u)) {
+                    // kept (X.v, 1): on the last frame its blank candidate strips to X.v as well
+                    for (int j = 0; j < k; j++) {
+                        const int R = rel[i][j];
+                        if (R == REL_PFX + lane && depth[j] == depth[i] + 1 && ((pk[j] >> 8) & 1))
+                            acc = mrg<DOMAIN>(acc, comb<DOMAIN>(sc[j], lpb));
+                    }
+                }
+            } else {
+                // blank candidate on the last frame: it strips to X, so the (X,0) stay slot or an extend slot
+                // that spells X hosts it; otherwise it stands alone
+                if (ebi == 0 || twi >= 0) dead = true;
+                else if (lasti != 0xff) {
+                    const int q0 = wb.p0[i], q1 = wb.p1[i];
+                    if (q1 >= 0 || (q0 >= 0 && (pk[q0] & 0xff) != lasti)) dead = true;
+                }
             }
+            if (is_stay) { acc = wb.stay[i]; dead = false; }
+            const unsigned key = (active && !dead) ? f2ord(acc) : 0u;
             wb.cand[i][lane] = key;
-        }
-        unsigned val[BMAX];
-#pragma unroll
-        for (int i = 0; i < BMAX; i++) val[i] = i < k ? wb.cand[i][lane] : 0u;
-
-        // ---- prune: beam rounds of warp-max extraction -> kept states in rank order -------------------------
-        int m = 0;
-        bool tie = false;
-        unsigned prev = 0u;
-        for (; m < B; m++) {
-            unsigned lmax = 0u;
-#pragma unroll
-            for (int i = 0; i < BMAX; i++) lmax = max(lmax, val[i]);
-            const unsigned gmax = __reduce_max_sync(FULL, lmax);
-            if (gmax == 0u) break;
-            int li = BMAX;
-#pragma unroll
-            for (int i = BMAX - 1; i >= 0; i--) if (val[i] == gmax) li = i;
-            const unsigned myidx = (li < BMAX) ? (unsigned)(li * V + lane) : 0xffffffffu;
-            const unsigned gidx = __reduce_min_sync(FULL, myidx);
-            const bool win = myidx == gidx;
-            const int wl = __ffs(__ballot_sync(FULL, win)) - 1;
-            const int wi = __shfl_sync(FULL, li, wl);
-#pragma unroll
-            for (int i = 0; i < BMAX; i++) if (win && i == li) val[i] = 0u;
-            if (lane == 0) { wb.selkey[m] = gmax; wb.seli[m] = wi; wb.selv[m] = wl; }
-            if (t > 0 && gmax == prev) tie = true;
-            prev = gmax;
-        }
-        if (t > 0 && m == B) {   // a tie across the cut?
-            unsigned lmax = 0u;
-#pragma unroll
-            for (int i = 0; i < BMAX; i++) lmax = max(lmax, val[i]);
-            if (__reduce_max_sync(FULL, lmax) == prev) tie = true;
+            lmax = max(lmax, key);
         }
         __syncwarp();
-        if (tie) {
-            // ---- rare slow path: redo the selection on the staged keys; equal scores are ordered by raw string ---
-            for (m = 0; m < B; m++) {
-                unsigned lmax = 0u;
-                for (int i = 0; i < k; i++) lmax = max(lmax, wb.cand[i][lane]);
-                const unsigned gmax = __reduce_max_sync(FULL, lmax);
-                if (gmax == 0u) break;
-                // local best (smallest raw string) among this lane's candidates with the top score
-                int bi = -1, bnode = 0, bsuf = 0;
-                for (int i = 0; i < k; i++) {
-                    if (wb.cand[i][lane] == gmax) {
-                        const int pki = pk[i];
-                        const int suf = cand_suffix(lane, blank, (pki >> 8) & 1, pki & 0xff, vch);
-                        if (bi < 0 || raw_less(parent, meta, vch, node[i], suf, bnode, bsuf)) { bi = i; bnode = node[i]; bsuf = suf; }
+
+        // ---- prune: beam rounds of warp-max extraction -> kept states in rank order.  Column maxima live in
+        //      registers (lmax); the winning column is re-read with one row per lane, so a round is O(1) instructions.
+        //      Equal scores are ordered by raw string through rel[][] (reference: stable prob sort on top of the
+        //      string sort); at t = 0 ties keep vocabulary order (CTCBeamSearch.cu:390). -------------------------
+        int m = 0;
+        for (; m < B; m++) {
+            const unsigned gmax = __reduce_max_sync(FULL, lmax);
+            if (gmax == 0u) break;
+            const unsigned any = __ballot_sync(FULL, lmax == gmax);
+            int wl = __ffs(any) - 1;
+            unsigned x = lane < k ? wb.cand[lane][wl] : 0u;          // column wl: row `lane`
+            const unsigned colmask = __ballot_sync(FULL, x == gmax);
+            int wi = __ffs(colmask) - 1;
+            if (t > 0 && (__popc(any) > 1 || __popc(colmask) > 1)) {
+                // exact tie: smallest raw string wins
+                int bi = -1, bs = 0;
+                if (lmax == gmax) {
+                    for (int i = 0; i < k; i++) {
+                        if (wb.cand[i][lane] != gmax) continue;
+                        const int si = cand_suffix_id(lane, blank, pk[i]);
+                        if (bi < 0 || cand_less_rel(rel[i][bi], si, bs, vch)) { bi = i; bs = si; }
                     }
                 }
                 int bl = lane;
+#pragma unroll
                 for (int off = 16; off > 0; off >>= 1) {
-                    const int oi = __shfl_xor_sync(FULL, bi, off), on = __shfl_xor_sync(FULL, bnode, off);
-                    const int os = __shfl_xor_sync(FULL, bsuf, off), ol = __shfl_xor_sync(FULL, bl, off);
-                    bool take = false;
-                    if (oi >= 0) {
-                        if (bi < 0) take = true;
-                        else if (raw_less(parent, meta, vch, on, os, bnode, bsuf)) take = true;
-                        else if (!raw_less(parent, meta, vch, bnode, bsuf, on, os)) take = (oi * V + ol) < (bi * V + bl);
-                    }
-                    if (take) { bi = oi; bnode = on; bsuf = os; bl = ol; }
+                    const int oi = __shfl_xor_sync(FULL, bi, off), os = __shfl_xor_sync(FULL, bs, off);
+                    const int ol = __shfl_xor_sync(FULL, bl, off);
+                    if (oi >= 0 && (bi < 0 || cand_less_rel(rel[oi][bi], os, bs, vch))) { bi = oi; bs = os; bl = ol; }
                 }
-                if (lane == bl) wb.cand[bi][lane] = 0u;
-                if (lane == 0) { wb.selkey[m] = gmax; wb.seli[m] = bi; wb.selv[m] = bl; }
-                __syncwarp();
+                wi = bi; wl = bl;
+                x = lane < k ? wb.cand[lane][wl] : 0u;
             }
+            if (lane == wi) { wb.cand[wi][wl] = 0u; x = 0u; }
+            const unsigned cmax = __reduce_max_sync(FULL, x);         // new maximum of the winning column
+            if (lane == wl) lmax = cmax;
+            if (lane == 0) { wb.selkey[m] = gmax; wb.seli[m] = wi; wb.selv[m] = wl; }
             __syncwarp();
         }
+        __syncwarp();
 
         // ---- the selected candidates become the next kept states (lane r builds state r) ---------------------
+        const int nxt = cur ^ 1;
         {
-            const int nxt = cur ^ 1;
             bool need_new = false;
             int i = 0, v = 0, nd = 0, pn = 0, dp = 0, npk = 0;
             if (lane < m) {
                 i = wb.seli[lane]; v = wb.selv[lane];
                 const int pki = pk[i];
                 const int ebi = (pki >> 8) & 1, lasti = pki & 0xff;
-                if (v == blank) { nd = node[i]; pn = pnode[i]; dp = depth[i]; npk = lasti | (1 << 8); }
-                else if (ebi == 0 && v == lasti) { nd = node[i]; pn = pnode[i]; dp = depth[i]; npk = lasti; }
+                if (v == blank) { nd = node[i]; dp = depth[i]; npk = lasti | (1 << 8); }
+                else if (ebi == 0 && v == lasti) { nd = node[i]; dp = depth[i]; npk = lasti; }
                 else {
                     pn = node[i]; dp = depth[i] + 1; npk = v;
                     nd = child[(size_t)pn * Vp + v];
@@ -658,11 +684,44 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
             nodes += __popc(nb);
             if (lane < m) {
                 wb.sc[nxt][lane] = ord2f(wb.selkey[lane]);
-                wb.node[nxt][lane] = nd; wb.pnode[nxt][lane] = pn; wb.depth[nxt][lane] = dp; wb.pk[nxt][lane] = npk;
+                wb.node[nxt][lane] = nd; wb.depth[nxt][lane] = dp; wb.pk[nxt][lane] = npk;
             }
-            kept = m;
-            cur = nxt;
         }
+        // ---- prefix relations of the new kept states from the old ones ----------------------------------------
+        for (int e = lane; e < BMAX * BMAX; e += 32) {
+            const int r = e / BMAX, q = e % BMAX;
+            if (r >= m || q >= m) continue;
+            const int ar = wb.seli[r], aq = wb.seli[q];
+            const int er = cand_ext_id(wb.selv[r], blank, pk[ar]);
+            const int eq2 = cand_ext_id(wb.selv[q], blank, pk[aq]);
+            const int R = rel[ar][aq];
+            const int dA = depth[ar], dB = depth[aq];
+            int out;
+            if (R == REL_EQ) {
+                if (er < 0 && eq2 < 0) out = REL_EQ;
+                else if (er < 0) out = REL_PFX + eq2;
+                else if (eq2 < 0) out = REL_RPFX + er;
+                else if (er == eq2) out = REL_EQ;
+                else out = ch_less(vch, er, eq2) ? REL_LT : REL_GT;
+            } else if (R == REL_LT || R == REL_GT) {
+                out = R;
+            } else if (R < REL_RPFX) {                         // A proper prefix of B, B = A.y...
+                const int y = R - REL_PFX;
+                if (er < 0) out = R;
+                else if (er != y) out = ch_less(vch, er, y) ? REL_LT : REL_GT;
+                else if (dB == dA + 1) out = eq2 < 0 ? REL_EQ : REL_PFX + eq2;
+                else out = REL_PFX + trie_char_at(parent, meta, node[aq], dA + 1);
+            } else {                                           // B proper prefix of A, A = B.y...
+                const int y = R - REL_RPFX;
+                if (eq2 < 0) out = R;
+                else if (eq2 != y) out = ch_less(vch, y, eq2) ? REL_LT : REL_GT;
+                else if (dA == dB + 1) out = er < 0 ? REL_EQ : REL_RPFX + er;
+                else out = REL_RPFX + trie_char_at(parent, meta, node[ar], dB + 1);
+            }
+            wb.rel[nxt][r][q] = (unsigned char)out;
+        }
+        kept = m;
+        cur = nxt;
         __syncwarp();
     }
 
