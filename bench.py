@@ -235,7 +235,10 @@ def main():
         stage_ms = stage_acc / args.steps                      # proj, recurrence, linear, decode (per step)
         rows = c["T"] * c["N"]
         rec_bytes = rows * c["H"] * 4 * 2                      # per launch: read xproj + write h
-        rec_ms_per_launch = stage_ms[1] / c["L"]
+        launches_per_stage, chunk_frames = pipe.stage_launches()
+        n_rec = max(launches_per_stage[1], 1)
+        rec_bytes = rec_bytes * c["L"] // n_rec                # algorithmic bytes of ONE launch (a time chunk of a layer)
+        rec_ms_per_launch = stage_ms[1] / n_rec
         achieved = rec_bytes / (rec_ms_per_launch * 1e-3) / 1e9
         proj_flop = 2.0 * rows * (c["D"] * c["H"] + (c["L"] - 1) * c["H"] * c["H"])
         lin_bytes = rows * (c["H"] * 4 + c["V"] * 4)
@@ -254,10 +257,14 @@ def main():
                     "h2d_bytes_per_step": int(x.nbytes), "d2h_bytes_per_step": int(c["N"] * (c["T"] + 1 + 8))},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "rnn_tanh_cluster_kernel (recurrence, one launch per layer)", "bound": "hbm",
+            "roofline": {"kernel": "rnn_tanh_cluster_kernel (recurrence, one launch per layer and time chunk)", "bound": "hbm",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": None, "peak_source": peak_kind,
-                         "algorithmic_bytes_per_launch": rec_bytes, "ms_per_launch": rec_ms_per_launch},
+                         "algorithmic_bytes_per_launch": rec_bytes, "ms_per_launch": rec_ms_per_launch,
+                         "launches_per_step": n_rec},
+            "pipeline": {"chunk_frames": chunk_frames, "launches_per_stage": launches_per_stage,
+                         "note": "chunk_frames > 0: stages overlap on separate streams; stage times are sums of "
+                                 "per-launch durations and may exceed ms_per_step"},
             "stages_ms_per_step": {"projection_gemm": stage_ms[0], "recurrence": stage_ms[1],
                                    "linear_logsoftmax": stage_ms[2], "ctc_decode": stage_ms[3]},
             "stage_rooflines": {

@@ -1,5 +1,6 @@
 // capi.cu -- the extern "C" boundary declared in include/gasr.h: context, memory, and the module entry points.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -429,6 +430,14 @@ struct gasr_asr {
     bool have_weights = false;
     gasr::StageEvents prof;
     float stage_ms[4] = {0, 0, 0, 0};
+    int stage_launches[4] = {0, 0, 0, 0};
+    // pipelined execution: time chunks flow through (layer 0 .. L-1, linear + decode) on separate streams
+    int chunk = 0;                              // frames per chunk (0 = sequential path)
+    float *xproj_all = nullptr, *bias_all = nullptr;   // [L][T*N*H], [L][H]
+    std::vector<cudaEvent_t> sync_ev;           // cross-stream dependencies (no timing)
+    std::vector<cudaEvent_t> t0_ev, t1_ev;      // per-launch timing pairs
+    std::vector<int> t_tag;
+    size_t n_timed = 0;
 };
 
 extern "C" {
@@ -467,6 +476,18 @@ int gasr_asr_create(gasr_ctx *ctx, const gasr_asr_config *cfg, const char *vocab
     alloc(&a->fc_b, (size_t)cfg->V);
     alloc(&a->x_dev, rows * cfg->in);
     alloc(&a->logp, rows * a->ldp);
+    {
+        // time-chunked pipelining needs the chunk-resumable kernels: cluster recurrence + warp decoder
+        int want = 50;
+        if (const char *e = getenv("GASR_CHUNK")) want = atoi(e);
+        const bool h_ok = (H == 64 || H == 128 || H == 256 || H == 512) && ctx->cluster_ok;
+        if (want > 0 && cfg->cell == GASR_CELL_TANH && !cfg->bidirectional && h_ok && cfg->beam <= 32 && cfg->V <= 32 &&
+            cfg->T >= 2 * want) {
+            a->chunk = want;
+            alloc(&a->xproj_all, (size_t)cfg->L * rows * H);
+            alloc(&a->bias_all, (size_t)cfg->L * H);
+        }
+    }
     if (st != GASR_OK) { gasr_asr_destroy(a); return st; }
     *out = a;
     return GASR_OK;
@@ -479,7 +500,10 @@ int gasr_asr_destroy(gasr_asr *a) {
     cudaStreamSynchronize(ctx->stream);
     for (auto v : {&a->w_ih, &a->w_hh, &a->b_ih, &a->b_hh, &a->hiddens})
         for (float *p : *v) if (p) gasr_free_device(ctx, p);
-    for (float *p : {a->fc_w, a->fc_b, a->x_dev, a->logp}) if (p) gasr_free_device(ctx, p);
+    for (float *p : {a->fc_w, a->fc_b, a->x_dev, a->logp, a->xproj_all, a->bias_all}) if (p) gasr_free_device(ctx, p);
+    for (cudaEvent_t e : a->sync_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : a->t0_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : a->t1_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : a->prof.pool) cudaEventDestroy(e);
     delete a;
     return GASR_OK;
@@ -510,12 +534,8 @@ int gasr_asr_set_weights(gasr_asr *a, const float *const *w_ih, const float *con
     return GASR_OK;
 }
 
-int gasr_asr_run_device(gasr_asr *a, const float *x_dev, char *out_paths, int *out_lens, float *out_scores) {
-    GASR_CHECK(a != nullptr, "null gasr_asr");
+static int asr_run_sequential(gasr_asr *a, const float *x_dev, char *out_paths, int *out_lens, float *out_scores) {
     gasr_ctx *ctx = a->ctx;
-    GASR_ENTER(ctx);
-    GASR_CHECK(a->have_weights, "gasr_asr_run: weights not set");
-    GASR_CHECK(x_dev && out_paths && out_lens && out_scores, "gasr_asr_run: null argument");
     const gasr_asr_config &c = a->cfg;
     cudaStream_t st = ctx->stream;
     const int rows = c.T * c.N;
@@ -531,13 +551,107 @@ int gasr_asr_run_device(gasr_asr *a, const float *x_dev, char *out_paths, int *o
     GASR_TRY(ctc_decode_launch(ctx, ca, st));
     GASR_TRY(a->prof.mark(3, st));
     GASR_CUDA(cudaStreamSynchronize(st));
-    for (int i = 0; i < 4; i++) a->stage_ms[i] = 0.0f;
+    for (int i = 0; i < 4; i++) { a->stage_ms[i] = 0.0f; a->stage_launches[i] = 0; }
     for (size_t i = 1; i < a->prof.used; i++) {
         float ms = 0;
         cudaEventElapsedTime(&ms, a->prof.pool[i - 1], a->prof.pool[i]);
-        if (a->prof.tag[i] >= 0) a->stage_ms[a->prof.tag[i]] += ms;
+        if (a->prof.tag[i] >= 0) { a->stage_ms[a->prof.tag[i]] += ms; a->stage_launches[a->prof.tag[i]] += 1; }
     }
     return ctc_decode_finish(ctx, ca);
+}
+
+// Pipelined path (unidirectional tanh stacks the cluster kernel supports, beam <= 32, vocab <= 32): the sequence is
+// cut into chunks of `chunk` frames; layer l works on chunk c while layer l+1 works on chunk c-1 and the decoder on
+// an even earlier one.  Every stage is sequential in time, so each owns a stream; cross-stage edges are events.
+static int asr_run_pipelined(gasr_asr *a, const float *x_dev, char *out_paths, int *out_lens, float *out_scores) {
+    gasr_ctx *ctx = a->ctx;
+    const gasr_asr_config &c = a->cfg;
+    const int T = c.T, N = c.N, H = c.H, L = c.L, Tc = a->chunk;
+    const int C = ceil_div(T, Tc);
+    cudaStream_t main_st = ctx->stream, dec_st = ctx->side[3];
+    auto layer_stream = [&](int l) { return ctx->side[l % 3]; };
+    const size_t need_ev = (size_t)L * C + 4;
+    while (a->sync_ev.size() < need_ev) {
+        cudaEvent_t e;
+        GASR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        a->sync_ev.push_back(e);
+    }
+    a->n_timed = 0;
+    auto timed_begin = [&](int tag, cudaStream_t st) -> int {
+        if (a->n_timed == a->t0_ev.size()) {
+            cudaEvent_t e0, e1;
+            if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return GASR_ERR_CUDA;
+            a->t0_ev.push_back(e0); a->t1_ev.push_back(e1); a->t_tag.push_back(tag);
+        }
+        a->t_tag[a->n_timed] = tag;
+        return cudaEventRecord(a->t0_ev[a->n_timed], st) == cudaSuccess ? GASR_OK : GASR_ERR_CUDA;
+    };
+    auto timed_end = [&](cudaStream_t st) -> int {
+        return cudaEventRecord(a->t1_ev[a->n_timed++], st) == cudaSuccess ? GASR_OK : GASR_ERR_CUDA;
+    };
+    cudaEvent_t ev_start = a->sync_ev[(size_t)L * C], ev_dec_done = a->sync_ev[(size_t)L * C + 1];
+    GASR_CUDA(cudaEventRecord(ev_start, main_st));
+    for (int l = 0; l < L && l < 3; l++) GASR_CUDA(cudaStreamWaitEvent(layer_stream(l), ev_start, 0));
+    GASR_CUDA(cudaStreamWaitEvent(dec_st, ev_start, 0));
+    for (int l = 0; l < L; l++)   // (b_hh + b_ih), RNN_Cell.cu:10
+        GASR_TRY(launch_matadd(ctx, a->b_ih[l], H, a->b_hh[l], H, a->bias_all + (size_t)l * H, H, 1, H, 1.0f, layer_stream(l)));
+    CtcArgs ca = {a->logp, GASR_DOMAIN_LOG, T, N, c.V, a->ldp, c.beam, c.blank, a->vocab.data(), c.max_len,
+                  c.nbest, out_paths, out_lens, out_scores, nullptr};
+    for (int ci = 0; ci < C; ci++) {
+        const int f0 = ci * Tc, f1 = (ci + 1) * Tc < T ? (ci + 1) * Tc : T;
+        const size_t row0 = (size_t)f0 * N;
+        const int rows = (f1 - f0) * N;
+        for (int l = 0; l < L; l++) {
+            cudaStream_t st = layer_stream(l);
+            const int in_l = l == 0 ? c.in : H;
+            const float *src = l == 0 ? x_dev : a->hiddens[l - 1];
+            float *xp = a->xproj_all + (size_t)l * T * N * H;
+            if (l > 0) GASR_CUDA(cudaStreamWaitEvent(st, a->sync_ev[(size_t)(l - 1) * C + ci], 0));
+            GASR_TRY(timed_begin(0, st));
+            GASR_TRY(launch_matmul(ctx, src + row0 * in_l, in_l, 0, a->w_ih[l], H, 0, xp + row0 * H, H, rows, in_l, H,
+                                   a->bias_all + (size_t)l * H, st));
+            GASR_TRY(timed_end(st));
+            RnnLayerArgs ra;
+            ra.cell = c.cell; ra.T = T; ra.N = N; ra.H = H; ra.reverse = 0;
+            ra.xproj = xp; ra.ldxp = H; ra.w_hh = a->w_hh[l]; ra.b_hh = a->b_hh[l];
+            ra.out = a->hiddens[l]; ra.ldo = H; ra.col0 = 0; ra.s0 = f0; ra.s1 = f1;
+            GASR_TRY(timed_begin(1, st));
+            GASR_TRY(launch_rnn_recurrence(ctx, ra, st));
+            GASR_TRY(timed_end(st));
+            GASR_CUDA(cudaEventRecord(a->sync_ev[(size_t)l * C + ci], st));
+        }
+        GASR_CUDA(cudaStreamWaitEvent(dec_st, a->sync_ev[(size_t)(L - 1) * C + ci], 0));
+        GASR_TRY(timed_begin(2, dec_st));
+        GASR_TRY(launch_linear(ctx, a->hiddens[L - 1] + row0 * H, H, a->fc_w, a->fc_b, a->logp + row0 * a->ldp, a->ldp,
+                               rows, H, c.V, GASR_ACT_LOGSOFTMAX, dec_st));
+        GASR_TRY(timed_end(dec_st));
+        ca.t0 = f0; ca.t1 = f1;
+        GASR_TRY(timed_begin(3, dec_st));
+        GASR_TRY(ctc_decode_launch(ctx, ca, dec_st));
+        GASR_TRY(timed_end(dec_st));
+    }
+    GASR_CUDA(cudaEventRecord(ev_dec_done, dec_st));
+    GASR_CUDA(cudaStreamWaitEvent(main_st, ev_dec_done, 0));
+    GASR_CUDA(cudaStreamSynchronize(main_st));
+    for (int i = 0; i < 4; i++) { a->stage_ms[i] = 0.0f; a->stage_launches[i] = 0; }
+    for (size_t i = 0; i < a->n_timed; i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a->t0_ev[i], a->t1_ev[i]);
+        a->stage_ms[a->t_tag[i]] += ms;
+        a->stage_launches[a->t_tag[i]] += 1;
+    }
+    ca.t0 = 0; ca.t1 = 0;
+    return ctc_decode_finish(ctx, ca);
+}
+
+int gasr_asr_run_device(gasr_asr *a, const float *x_dev, char *out_paths, int *out_lens, float *out_scores) {
+    GASR_CHECK(a != nullptr, "null gasr_asr");
+    gasr_ctx *ctx = a->ctx;
+    GASR_ENTER(ctx);
+    GASR_CHECK(a->have_weights, "gasr_asr_run: weights not set");
+    GASR_CHECK(x_dev && out_paths && out_lens && out_scores, "gasr_asr_run: null argument");
+    if (a->chunk > 0) return asr_run_pipelined(a, x_dev, out_paths, out_lens, out_scores);
+    return asr_run_sequential(a, x_dev, out_paths, out_lens, out_scores);
 }
 
 int gasr_asr_run_host(gasr_asr *a, const float *x_host, char *out_paths, int *out_lens, float *out_scores) {
@@ -561,6 +675,13 @@ int gasr_asr_logprobs(gasr_asr *a, const float **logp_dev, int *ldp) {
 int gasr_asr_stage_times(gasr_asr *a, float *ms4) {
     GASR_CHECK(a && ms4, "gasr_asr_stage_times: null argument");
     for (int i = 0; i < 4; i++) ms4[i] = a->stage_ms[i];
+    return GASR_OK;
+}
+
+int gasr_asr_stage_launches(gasr_asr *a, int *n4, int *chunk_frames) {
+    GASR_CHECK(a && n4, "gasr_asr_stage_launches: null argument");
+    for (int i = 0; i < 4; i++) n4[i] = a->stage_launches[i];
+    if (chunk_frames) *chunk_frames = a->chunk;
     return GASR_OK;
 }
 

@@ -87,12 +87,14 @@ struct RnnLayerArgs {
     const float *b_hh;    // [G*H] (GRU only: b_hn stays inside the reset product)
     float *out;           // [T*N, ldo] written at column offset col0
     int ldo, col0;
+    int s0 = 0, s1 = 0;   // steps [s0, s1) only (s1 = 0: all T); h before step s0 is read back from `out`
 };
 int launch_rnn_recurrence(gasr_ctx *ctx, const RnnLayerArgs &a, cudaStream_t st);
 
 struct CtcArgs {
     const float *scores; int domain, T, N, V, ld, beam, blank; const char *vocab_host; int max_len, nbest;
     char *out_paths; int *out_lens; float *out_scores; int *out_counts;   // host
+    int t0 = 0, t1 = 0;   // frames [t0, t1) only (t1 = 0: all T); the beam is parked in the ctx workspace between chunks
 };
 int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st);   // enqueue kernel + D2H into pinned staging
 int ctc_decode_finish(gasr_ctx *ctx, const CtcArgs &a);                    // after stream sync: unpack to caller buffers

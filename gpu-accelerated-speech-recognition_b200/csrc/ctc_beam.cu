@@ -82,6 +82,9 @@ struct CtcParams {
     int *out_lens;       // [N, nbest]
     float *out_scores;   // [N, nbest]
     int *out_counts;     // [N]
+    int t0, t1;          // frames [t0, t1) are decoded by this launch (time chunking; warp kernel only)
+    unsigned char *state;   // [N, state_stride] saved beam state between chunk launches
+    size_t state_stride;
 };
 
 constexpr int kNone = -1;
@@ -502,20 +505,30 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
     // every warp writes the same bytes; only __syncwarp ordering is needed for its own reads
     if (active) vch_s[lane] = p.vocab[lane];
     const char *vch = vch_s;
-    if (lane < Vp) child[lane] = 0;
-    if (lane == 0) {
-        parent[0] = -1; meta[0] = 0xff;
-        wb.sc[0][0] = DOMAIN ? 0.0f : 1.0f;
-        wb.node[0][0] = 0; wb.depth[0][0] = 0; wb.pk[0][0] = 0xff | (1 << 8);
-        wb.rel[0][0][0] = REL_EQ;
-    }
     int kept = 1, nodes = 1, cur = 0;
-    float lp_next = active ? S[lane] : 0.0f;
+    int4 *gstate = reinterpret_cast<int4 *>(p.state + (size_t)utt * p.state_stride);
+    constexpr int kStateVec = (int)(sizeof(WarpBeam<BMAX>) / sizeof(int4));
+    if (p.t0 == 0) {
+        if (lane < Vp) child[lane] = 0;
+        if (lane == 0) {
+            parent[0] = -1; meta[0] = 0xff;
+            wb.sc[0][0] = DOMAIN ? 0.0f : 1.0f;
+            wb.node[0][0] = 0; wb.depth[0][0] = 0; wb.pk[0][0] = 0xff | (1 << 8);
+            wb.rel[0][0][0] = REL_EQ;
+        }
+    } else {
+        // resume: the previous chunk launch left the beam in HBM
+        int4 *dst = reinterpret_cast<int4 *>(&wb);
+        for (int i = lane; i < kStateVec; i += 32) dst[i] = gstate[i];
+        const int4 hdr = gstate[kStateVec];
+        kept = hdr.x; nodes = hdr.y; cur = hdr.z;
+    }
+    float lp_next = active ? S[(size_t)p.t0 * frame_stride + lane] : 0.0f;
     __syncwarp();
 
-    for (int t = 0; t < p.T; t++) {
+    for (int t = p.t0; t < p.t1; t++) {
         const float lp = lp_next;
-        if (t + 1 < p.T && active) lp_next = S[(size_t)(t + 1) * frame_stride + lane];
+        if (t + 1 < p.t1 && active) lp_next = S[(size_t)(t + 1) * frame_stride + lane];
         const bool last_frame = (t == p.T - 1) && (t > 0);
         const int k = kept;
         const float *sc = wb.sc[cur];
@@ -725,6 +738,13 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
         __syncwarp();
     }
 
+    if (p.t1 < p.T) {
+        // more chunks follow: park the beam in HBM
+        const int4 *src = reinterpret_cast<const int4 *>(&wb);
+        for (int i = lane; i < kStateVec; i += 32) gstate[i] = src[i];
+        if (lane == 0) gstate[kStateVec] = make_int4(kept, nodes, cur, 0);
+        return;
+    }
     // ---- result (CTCBeamSearch.cu:290-298): kept states best first, path = labels of X -------------------------
     if (lane == 0 && p.out_counts) p.out_counts[utt] = kept;
     for (int r = lane; r < p.nbest; r += 32) {
@@ -761,7 +781,8 @@ static size_t ctc_smem_bytes(int B, int V, int Vp, int n_pad) {
 
 struct CtcLayout {
     int Vp, n_pad, cap, threads;
-    size_t smem, off_vocab, off_parent, off_meta, off_child, off_paths, off_lens, off_scores, off_counts, total;
+    size_t smem, off_vocab, off_parent, off_meta, off_child, off_state, state_stride, off_paths, off_lens, off_scores,
+        off_counts, total;
     size_t out_bytes;
 };
 
@@ -779,6 +800,8 @@ static int ctc_layout(const CtcArgs &a, CtcLayout &L) {
     L.off_parent = o; o = align_up(o + sizeof(int) * (size_t)a.N * L.cap, 256);
     L.off_meta = o; o = align_up(o + sizeof(int) * (size_t)a.N * L.cap, 256);
     L.off_child = o; o = align_up(o + sizeof(int) * (size_t)a.N * L.cap * L.Vp, 256);
+    L.state_stride = align_up(sizeof(WarpBeam<32>) + sizeof(int4), 256);
+    L.off_state = o; o = align_up(o + L.state_stride * (size_t)a.N, 256);
     L.total = o;
     size_t q = 0;
     L.off_paths = q; q = align_up(q + (size_t)a.N * a.nbest * a.max_len, 256);
@@ -815,7 +838,11 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
     GASR_TRY(pinned_reserve(ctx, L.out_bytes));
     unsigned char *ws = static_cast<unsigned char *>(ctx->ws_ctc.ptr);
     unsigned char *wo = static_cast<unsigned char *>(ctx->ws_out.ptr);
-    GASR_CUDA(cudaMemcpyAsync(ws + L.off_vocab, a.vocab_host, a.V, cudaMemcpyHostToDevice, st));
+    const int t0 = a.t0, t1 = a.t1 > 0 ? a.t1 : a.T;
+    const bool fast = a.beam <= 32 && a.V <= 32;
+    GASR_CHECK(t0 >= 0 && t0 < t1 && t1 <= a.T, "ctc_decode: bad frame range [%d, %d)", t0, t1);
+    GASR_CHECK(fast || (t0 == 0 && t1 == a.T), "ctc_decode: time-chunked decoding needs beam <= 32 and vocab <= 32");
+    if (t0 == 0) GASR_CUDA(cudaMemcpyAsync(ws + L.off_vocab, a.vocab_host, a.V, cudaMemcpyHostToDevice, st));
 
     CtcParams p;
     p.scores = a.scores; p.T = a.T; p.N = a.N; p.V = a.V; p.ld = a.ld; p.beam = a.beam; p.blank = a.blank;
@@ -828,9 +855,11 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
     p.out_lens = reinterpret_cast<int *>(wo + L.off_lens);
     p.out_scores = reinterpret_cast<float *>(wo + L.off_scores);
     p.out_counts = reinterpret_cast<int *>(wo + L.off_counts);
+    p.t0 = t0; p.t1 = t1;
+    p.state = ws + L.off_state; p.state_stride = L.state_stride;
 
-    GASR_CUDA(cudaMemsetAsync(wo + L.off_paths, 0, (size_t)a.N * a.nbest * a.max_len, st));
-    if (a.beam <= 32 && a.V <= 32) {
+    if (t1 == a.T) GASR_CUDA(cudaMemsetAsync(wo + L.off_paths, 0, (size_t)a.N * a.nbest * a.max_len, st));
+    if (fast) {
         // warp-per-utterance fast path; few warps per CTA when utterances are scarce (latency), 8 when plentiful
         int W = ceil_div(a.N, ctx->sm_count);
         if (W > 8) W = 8;
@@ -863,7 +892,7 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
     }
     GASR_CUDA(cudaGetLastError());
     ctx->launches += 1;
-    GASR_CUDA(cudaMemcpyAsync(ctx->pinned_out, wo, L.out_bytes, cudaMemcpyDeviceToHost, st));
+    if (t1 == a.T) GASR_CUDA(cudaMemcpyAsync(ctx->pinned_out, wo, L.out_bytes, cudaMemcpyDeviceToHost, st));
     return GASR_OK;
 }
 

@@ -101,6 +101,7 @@ struct RnnClusterParams {
     const float *w_hh;
     float *out; int ldo, col0;
     int T, N, H, CS, reverse;
+    int s0, s1;          // steps [s0, s1) of the T-step sequence are computed by this launch (time chunking)
 };
 
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
@@ -125,7 +126,20 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rnn_tanh_cluster_kernel(const R
         const int k = i / (RC_HC / 4), c4 = i % (RC_HC / 4);
         reinterpret_cast<float4 *>(Ws)[i] = __ldg(reinterpret_cast<const float4 *>(p.w_hh + (size_t)k * H + colbase) + c4);
     }
-    for (int i = tid; i < 2 * RC_NB * HS; i += RC_THREADS) hbuf[i] = 0.0f;   // h_0 = 0 (RNN.h:16-17)
+    // h before the first step of this launch: zeros for step 0 (h_0 = 0, RNN.h:16-17), otherwise the previous
+    // chunk's last output row, read back from HBM
+    for (int i = tid; i < 2 * RC_NB * HS; i += RC_THREADS) hbuf[i] = 0.0f;
+    if (p.s0 > 0) {
+        __syncthreads();
+        const int tp = p.reverse ? p.T - p.s0 : p.s0 - 1;
+        float *h0buf = hbuf + (size_t)(p.s0 & 1) * RC_NB * HS;
+        for (int i = tid; i < RC_NB * (H / 4); i += RC_THREADS) {
+            const int u = i / (H / 4), c4 = i % (H / 4);
+            if (n0 + u < p.N)
+                *reinterpret_cast<float4 *>(h0buf + (size_t)u * HS + c4 * 4) =
+                    *reinterpret_cast<const float4 *>(p.out + ((size_t)tp * p.N + n0 + u) * p.ldo + p.col0 + c4 * 4);
+        }
+    }
 
     // compute-phase mapping: warp -> (K quarter, column half); lane -> (utterance set, 4-column group)
     const int kq = warp & 3, ch = warp >> 2;
@@ -139,17 +153,17 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rnn_tanh_cluster_kernel(const R
 
     float4 xnext = make_float4(0.f, 0.f, 0.f, 0.f);
     {
-        const int t0 = p.reverse ? p.T - 1 : 0;
+        const int t0 = p.reverse ? p.T - 1 - p.s0 : p.s0;
         if (evalid) xnext = __ldg(reinterpret_cast<const float4 *>(p.xproj + ((size_t)t0 * p.N + en) * p.ldxp + colbase + ec));
     }
     cluster.sync();   // weights + zeroed h visible, all CTAs of the cluster are running
 
-    for (int s = 0; s < p.T; s++) {
+    for (int s = p.s0; s < p.s1; s++) {
         const int t = p.reverse ? p.T - 1 - s : s;
         const float *hc = hbuf + (size_t)(s & 1) * RC_NB * HS;
         float *hn = hbuf + (size_t)((s & 1) ^ 1) * RC_NB * HS;
         const float4 xcur = xnext;
-        if (s + 1 < p.T && evalid) {
+        if (s + 1 < p.s1 && evalid) {
             const int tn = p.reverse ? t - 1 : t + 1;
             xnext = __ldg(reinterpret_cast<const float4 *>(p.xproj + ((size_t)tn * p.N + en) * p.ldxp + colbase + ec));
         }
@@ -192,7 +206,7 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rnn_tanh_cluster_kernel(const R
             v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
         }
         v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w);
-        if (s + 1 < p.T) {
+        if (s + 1 < p.s1) {
             // broadcast this CTA's slice of h_t into every CTA's next-step buffer (DSMEM)
             float *dst_local = hn + (size_t)eu * HS + colbase + ec;
             for (int r = 0; r < CS; r++) {
@@ -230,6 +244,7 @@ int launch_rnn_recurrence(gasr_ctx *ctx, const RnnLayerArgs &a, cudaStream_t st)
         RnnClusterParams p;
         p.xproj = a.xproj; p.ldxp = a.ldxp; p.w_hh = a.w_hh; p.out = a.out; p.ldo = a.ldo; p.col0 = a.col0;
         p.T = a.T; p.N = a.N; p.H = a.H; p.CS = a.H / RC_HC; p.reverse = a.reverse;
+        p.s0 = a.s0; p.s1 = a.s1 > 0 ? a.s1 : a.T;
         const int groups = ceil_div(a.N, RC_NB);
         const size_t smem = cluster_smem_bytes(a.H);
         GASR_CUDA(cudaFuncSetAttribute(rnn_tanh_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -249,7 +264,7 @@ int launch_rnn_recurrence(gasr_ctx *ctx, const RnnLayerArgs &a, cudaStream_t st)
     // fallback: one kernel per timestep
     GASR_CHECK(a.N <= 65535, "rnn_recurrence: batch too large for the per-step path");
     dim3 grid(ceil_div(a.H, 128), a.N);
-    for (int s = 0; s < a.T; s++) {
+    for (int s = a.s0; s < (a.s1 > 0 ? a.s1 : a.T); s++) {
         const int t = a.reverse ? a.T - 1 - s : s;
         const int tp = a.reverse ? t + 1 : t - 1;
         const float *xp = a.xproj + (size_t)t * a.N * a.ldxp;

@@ -54,7 +54,7 @@ EXPORTS = [
     "gasr_memcpy_d2h", "gasr_memcpy_h2d_async", "gasr_memcpy_d2h_async", "gasr_memset_device", "gasr_memory_stats",
     "gasr_matmul", "gasr_matadd", "gasr_linear_forward", "gasr_log_softmax", "gasr_rnn_cell_forward",
     "gasr_rnn_forward", "gasr_ctc_decode", "gasr_ctc_decode_host", "gasr_asr_create", "gasr_asr_destroy",
-    "gasr_asr_set_weights", "gasr_asr_run_host", "gasr_asr_run_device", "gasr_asr_logprobs", "gasr_asr_stage_times",
+    "gasr_asr_set_weights", "gasr_asr_run_host", "gasr_asr_run_device", "gasr_asr_logprobs", "gasr_asr_stage_times", "gasr_asr_stage_launches",
 ]
 
 
@@ -453,6 +453,12 @@ class AsrPipeline:
         _check(_lib.gasr_asr_stage_times(self._h, ms))
         return list(ms)
 
+    def stage_launches(self):
+        n = (ctypes.c_int * 4)()
+        chunk = ctypes.c_int(0)
+        _check(_lib.gasr_asr_stage_launches(self._h, n, ctypes.byref(chunk)))
+        return list(n), chunk.value
+
 
 def _declare():
     vp, sz, ci, cf = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_float
@@ -490,6 +496,7 @@ def _declare():
     L.gasr_asr_run_device.argtypes = [vp, vp, ctypes.c_char_p, c_int_p, c_float_p]
     L.gasr_asr_logprobs.argtypes = [vp, c_void_pp, c_int_p]
     L.gasr_asr_stage_times.argtypes = [vp, c_float_p]
+    L.gasr_asr_stage_launches.argtypes = [vp, c_int_p, c_int_p]
 
 
 _declare()

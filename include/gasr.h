@@ -145,6 +145,10 @@ int gasr_asr_run_device(gasr_asr *asr, const float *x_dev, char *out_paths, int 
 int gasr_asr_logprobs(gasr_asr *asr, const float **logp_dev, int *ldp);
 /* Per-stage device times (ms) of the last run: projection, recurrence, linear+log-softmax, decode.  */
 int gasr_asr_stage_times(gasr_asr *asr, float *ms4);
+/* Kernel launches per stage in the last run (same order) and the pipeline chunk length in frames (0: the stages
+ * ran back to back on one stream; otherwise time chunks flowed through the stages on concurrent streams and a
+ * stage time is the sum of its launches' durations).                                                        */
+int gasr_asr_stage_launches(gasr_asr *asr, int *n4, int *chunk_frames);
 
 #ifdef __cplusplus
 }

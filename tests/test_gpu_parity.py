@@ -352,7 +352,8 @@ def test_gru_bidirectional_vs_oracle(gasr, ctx, O):
 
 
 # ---------------------------------------------------------------- end-to-end pipeline ----------------------
-@pytest.mark.parametrize("T,N,D,H,L,beam", [(60, 10, 161, 512, 3, 16), (33, 3, 20, 64, 1, 4)])
+@pytest.mark.parametrize("T,N,D,H,L,beam", [(60, 10, 161, 512, 3, 16), (33, 3, 20, 64, 1, 4), (230, 20, 40, 128, 3, 8),
+                                            (137, 5, 161, 512, 2, 32)])
 def test_pipeline_end_to_end(gasr, ctx, O, T, N, D, H, L, beam):
     import synth
     V = 29
