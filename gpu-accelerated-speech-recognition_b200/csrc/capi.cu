@@ -114,7 +114,7 @@ int gasr_ctx_create(int device, gasr_ctx **out) {
         delete ctx;
         return GASR_ERR_CUDA;
     }
-    for (int i = 0; i < 4; i++) cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking);
+    for (int i = 0; i < 6; i++) cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking);
     *out = ctx;
     return GASR_OK;
 }
@@ -127,7 +127,7 @@ int gasr_ctx_destroy(gasr_ctx *ctx) {
     Workspace *wss[] = {&ctx->ws_ctc, &ctx->ws_rnn, &ctx->ws_misc, &ctx->ws_out};
     for (Workspace *w : wss) if (w->ptr) cudaFree(w->ptr);
     if (ctx->pinned_out) cudaFreeHost(ctx->pinned_out);
-    for (int i = 0; i < 4; i++) if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+    for (int i = 0; i < 6; i++) if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
     cudaEventDestroy(ctx->ev_start);
     cudaEventDestroy(ctx->ev_stop);
     cudaStreamDestroy(ctx->stream);
@@ -568,9 +568,9 @@ static int asr_run_pipelined(gasr_asr *a, const float *x_dev, char *out_paths, i
     const gasr_asr_config &c = a->cfg;
     const int T = c.T, N = c.N, H = c.H, L = c.L, Tc = a->chunk;
     const int C = ceil_div(T, Tc);
-    cudaStream_t main_st = ctx->stream, dec_st = ctx->side[3];
+    cudaStream_t main_st = ctx->stream, dec_st = ctx->side[3], lin_st = ctx->side[4];
     auto layer_stream = [&](int l) { return ctx->side[l % 3]; };
-    const size_t need_ev = (size_t)L * C + 4;
+    const size_t need_ev = (size_t)(L + 1) * C + 4;
     while (a->sync_ev.size() < need_ev) {
         cudaEvent_t e;
         GASR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -589,10 +589,11 @@ static int asr_run_pipelined(gasr_asr *a, const float *x_dev, char *out_paths, i
     auto timed_end = [&](cudaStream_t st) -> int {
         return cudaEventRecord(a->t1_ev[a->n_timed++], st) == cudaSuccess ? GASR_OK : GASR_ERR_CUDA;
     };
-    cudaEvent_t ev_start = a->sync_ev[(size_t)L * C], ev_dec_done = a->sync_ev[(size_t)L * C + 1];
+    cudaEvent_t ev_start = a->sync_ev[(size_t)(L + 1) * C], ev_dec_done = a->sync_ev[(size_t)(L + 1) * C + 1];
     GASR_CUDA(cudaEventRecord(ev_start, main_st));
     for (int l = 0; l < L && l < 3; l++) GASR_CUDA(cudaStreamWaitEvent(layer_stream(l), ev_start, 0));
     GASR_CUDA(cudaStreamWaitEvent(dec_st, ev_start, 0));
+    GASR_CUDA(cudaStreamWaitEvent(lin_st, ev_start, 0));
     for (int l = 0; l < L; l++)   // (b_hh + b_ih), RNN_Cell.cu:10
         GASR_TRY(launch_matadd(ctx, a->b_ih[l], H, a->b_hh[l], H, a->bias_all + (size_t)l * H, H, 1, H, 1.0f, layer_stream(l)));
     CtcArgs ca = {a->logp, GASR_DOMAIN_LOG, T, N, c.V, a->ldp, c.beam, c.blank, a->vocab.data(), c.max_len,
@@ -620,11 +621,13 @@ static int asr_run_pipelined(gasr_asr *a, const float *x_dev, char *out_paths, i
             GASR_TRY(timed_end(st));
             GASR_CUDA(cudaEventRecord(a->sync_ev[(size_t)l * C + ci], st));
         }
-        GASR_CUDA(cudaStreamWaitEvent(dec_st, a->sync_ev[(size_t)(L - 1) * C + ci], 0));
-        GASR_TRY(timed_begin(2, dec_st));
+        GASR_CUDA(cudaStreamWaitEvent(lin_st, a->sync_ev[(size_t)(L - 1) * C + ci], 0));
+        GASR_TRY(timed_begin(2, lin_st));
         GASR_TRY(launch_linear(ctx, a->hiddens[L - 1] + row0 * H, H, a->fc_w, a->fc_b, a->logp + row0 * a->ldp, a->ldp,
-                               rows, H, c.V, GASR_ACT_LOGSOFTMAX, dec_st));
-        GASR_TRY(timed_end(dec_st));
+                               rows, H, c.V, GASR_ACT_LOGSOFTMAX, lin_st));
+        GASR_TRY(timed_end(lin_st));
+        GASR_CUDA(cudaEventRecord(a->sync_ev[(size_t)L * C + ci], lin_st));
+        GASR_CUDA(cudaStreamWaitEvent(dec_st, a->sync_ev[(size_t)L * C + ci], 0));
         ca.t0 = f0; ca.t1 = f1;
         GASR_TRY(timed_begin(3, dec_st));
         GASR_TRY(ctc_decode_launch(ctx, ca, dec_st));

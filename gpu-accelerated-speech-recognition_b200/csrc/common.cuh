@@ -50,7 +50,7 @@ struct gasr_ctx {
     int max_smem_optin = 0;
     int cluster_ok = 0;
     cudaStream_t stream = nullptr;       // main stream: every kernel of the C ABI is launched here
-    cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};  // pipeline side streams
+    cudaStream_t side[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // pipeline side streams
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     long long launches = 0;
     size_t device_bytes = 0, host_bytes = 0;

@@ -58,6 +58,40 @@ __device__ __forceinline__ float logaddexp_det(float a, float b) {
     return __fadd_rn(mx, l);
 }
 
+// Same function, same bits, without data-dependent branches (selects instead of early returns) so that several
+// independent evaluations interleave in one warp.
+__device__ __forceinline__ float logaddexp_det_bf(float a, float b) {
+    const float mx = a > b ? a : b;
+    const float mn = a > b ? b : a;
+    const float d0 = __fsub_rn(mn, mx);
+    const bool skip = !(d0 >= -17.5f);          // d < -17.5, mn = -inf (d = -inf) or both -inf (d = NaN)
+    const float d = skip ? 0.0f : d0;
+    const float n = rintf(__fmul_rn(d, 1.44269504088896341f));
+    float r = __fmaf_rn(n, -0.693359375f, d);
+    r = __fmaf_rn(n, 2.12194440e-4f, r);
+    float p = 1.9875691500e-4f;
+    p = __fmaf_rn(p, r, 1.3981999507e-3f);
+    p = __fmaf_rn(p, r, 8.3334519073e-3f);
+    p = __fmaf_rn(p, r, 4.1665795894e-2f);
+    p = __fmaf_rn(p, r, 1.6666665459e-1f);
+    p = __fmaf_rn(p, r, 5.0000001201e-1f);
+    const float r2 = __fmul_rn(r, r);
+    const float ex = __fadd_rn(__fmaf_rn(p, r2, r), 1.0f);
+    const float scale = __int_as_float(((int)n + 127) << 23);
+    const float e = __fmul_rn(ex, scale);
+    const float t = __fdiv_rn(e, __fadd_rn(2.0f, e));
+    const float w = __fmul_rn(t, t);
+    float q = 1.0f / 13.0f;
+    q = __fmaf_rn(q, w, 1.0f / 11.0f);
+    q = __fmaf_rn(q, w, 1.0f / 9.0f);
+    q = __fmaf_rn(q, w, 1.0f / 7.0f);
+    q = __fmaf_rn(q, w, 1.0f / 5.0f);
+    q = __fmaf_rn(q, w, 1.0f / 3.0f);
+    q = __fmaf_rn(q, w, 1.0f);
+    const float l = __fmul_rn(__fmul_rn(2.0f, t), q);
+    return skip ? mx : __fadd_rn(mx, l);
+}
+
 // order-preserving float -> uint32 (larger float => larger key); every real score maps to a key > 0
 __device__ __forceinline__ uint32_t f2ord(float f) {
     const uint32_t b = __float_as_uint(f);
@@ -82,6 +116,8 @@ struct CtcParams {
     int *out_lens;       // [N, nbest]
     float *out_scores;   // [N, nbest]
     int *out_counts;     // [N]
+    unsigned char cell_i[64], cell_j[64];   // prune lower-bound probe cells (parent rank, log-prob rank); warp kernel
+    int n_cells;         // 32 (one per lane) or 64
     int t0, t1;          // frames [t0, t1) are decoded by this launch (time chunking; warp kernel only)
     unsigned char *state;   // [N, state_stride] saved beam state between chunk launches
     size_t state_stride;
@@ -105,6 +141,10 @@ __device__ __forceinline__ float comb(float s, float p) {
 template <int DOMAIN>
 __device__ __forceinline__ float mrg(float a, float b) {
     return DOMAIN ? logaddexp_det(a, b) : __fadd_rn(a, b);
+}
+template <int DOMAIN>
+__device__ __forceinline__ float mrg_bf(float a, float b) {
+    return DOMAIN ? logaddexp_det_bf(a, b) : __fadd_rn(a, b);
 }
 
 // raw-string order of two candidates = (trie node, optional suffix char): walk both up to the lowest common
@@ -441,6 +481,11 @@ struct WarpBeam {
     int seli[BMAX], selv[BMAX];
     unsigned char rel[2][BMAX][BMAX];
     unsigned cand[BMAX][32];  // merged candidate keys staged [parent rank][vocab id]; 0 = absorbed / absent
+    float pairmm[BMAX / 2][32];   // merged scores of twin pairs (X,0)+(X,1), [pair][vocab id]
+    int pair_i[BMAX / 2], pair_tw[BMAX / 2];
+    int order[32];            // order[j] = vocab id with the j-th largest score this frame
+    unsigned surv_key[64];    // prune survivors (candidates >= the lower bound), in candidate-index order
+    int surv_iv[64];          // parent rank << 8 | vocab id
 };
 
 // the character at 0-based position pos of the label string of trie node nd (depth(nd) > pos); rare path
@@ -536,6 +581,17 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
         const unsigned char (*rel)[BMAX] = wb.rel[cur];
         const float lpb = __shfl_sync(FULL, lp, blank);
 
+        // ---- rank of this frame's scores over the vocabulary (independent of the beam) ------------------------
+        {
+            const unsigned mine = active ? f2ord(lp) : 0u;
+            int lr = 0;
+#pragma unroll
+            for (int u = 0; u < 32; u++) {
+                const unsigned x = __shfl_sync(FULL, mine, u);
+                lr += (x > mine || (x == mine && u < lane)) ? 1 : 0;
+            }
+            wb.order[lr] = lane;
+        }
         // ---- relations among kept states, read off the prefix-relation matrix (lane r owns state r) ---------
         int my_last = 0xff, my_eb = 1, my_tw = kNone, my_p0 = kNone, my_p1 = kNone;
         if (lane < k) {
@@ -552,8 +608,17 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
                 }
             }
             wb.tw[lane] = my_tw; wb.p0[lane] = my_p0; wb.p1[lane] = my_p1; wb.abs0[lane] = a0; wb.abs1[lane] = a1;
-            wb.pinfo[lane] = make_int4(__float_as_int(sc[lane]), __float_as_int(my_tw >= 0 ? sc[my_tw] : 0.0f),
-                                       pk[lane] | ((my_tw + 1) << 9), (int)a0);
+        }
+        // twin pairs (i < twin): their V merged scores are computed once, by the pair loop below
+        const unsigned pair_mask = __ballot_sync(FULL, lane < k && my_tw > lane);
+        const int npairs = __popc(pair_mask);
+        if (lane < k) {
+            int pidx = -1;
+            if (my_tw > lane) {
+                pidx = __popc(pair_mask & ((1u << lane) - 1u));
+                wb.pair_i[pidx] = lane; wb.pair_tw[pidx] = my_tw;
+            }
+            wb.pinfo[lane] = make_int4(__float_as_int(sc[lane]), pidx, pk[lane] | ((my_tw + 1) << 9), (int)wb.abs0[lane]);
         }
         // ---- "stay" candidates, one per (X,0) state, all lanes in parallel ------------------------------
         {
@@ -581,90 +646,183 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
         __syncwarp();
 
         // ---- merged candidate scores: val[i] of lane v  <->  candidate i*V + v -----------------------------
-        unsigned lmax = 0u;   // this lane's column maximum over the merged candidate keys
-#pragma unroll 4
-        for (int i = 0; i < k; i++) {
-            const int4 pi = wb.pinfo[i];
-            const float sci = __int_as_float(pi.x);
-            const int pki = pi.z & 0x1ff, twi = ((pi.z >> 9) & 0x3f) - 1;
-            const int ebi = (pki >> 8) & 1, lasti = pki & 0xff;
-            const float s = comb<DOMAIN>(sci, lp);
-            float acc = s;
-            bool dead = false;
-            const bool is_stay = (ebi == 0 && lane == lasti);
-            const bool is_blank = (lane == blank);
-            const bool member = twi >= 0 && (is_blank || ebi == 0 || lane != lasti);
-            if (!last_frame || !is_blank) {
-                if (twi >= 0) {
-                    if (twi < i) dead = member;
-                    else {
-                        const float mm = mrg<DOMAIN>(s, comb<DOMAIN>(__int_as_float(pi.y), lp));
-                        acc = member ? mm : s;
-                    }
-                }
-                if (!is_blank && (((unsigned)pi.w >> lane) & 1u)) dead = true;   // kept (X.v, 0) hosts this extend
-                if (last_frame && !dead && !is_stay && ((wb.abs1[i] >> lane) & 1u)) {
-                    // kept (X.v, 1): on the last frame its blank candidate strips to X.v as well
-                    for (int j = 0; j < k; j++) {
-                        const int R = rel[i][j];
-                        if (R == REL_PFX + lane && depth[j] == depth[i] + 1 && ((pk[j] >> 8) & 1))
-                            acc = mrg<DOMAIN>(acc, comb<DOMAIN>(sc[j], lpb));
-                    }
-                }
-            } else {
-                // blank candidate on the last frame: it strips to X, so the (X,0) stay slot or an extend slot
-                // that spells X hosts it; otherwise it stands alone
-                if (ebi == 0 || twi >= 0) dead = true;
-                else if (lasti != 0xff) {
-                    const int q0 = wb.p0[i], q1 = wb.p1[i];
-                    if (q1 >= 0 || (q0 >= 0 && (pk[q0] & 0xff) != lasti)) dead = true;
-                }
+        if (!last_frame) {
+            // twin merges first: branch-free and unrolled so that independent pairs interleave
+#pragma unroll 2
+            for (int q = 0; q < npairs; q++) {
+                const float sa = comb<DOMAIN>(sc[wb.pair_i[q]], lp), sb = comb<DOMAIN>(sc[wb.pair_tw[q]], lp);
+                wb.pairmm[q][lane] = mrg_bf<DOMAIN>(sa, sb);
             }
-            if (is_stay) { acc = wb.stay[i]; dead = false; }
-            const unsigned key = (active && !dead) ? f2ord(acc) : 0u;
-            wb.cand[i][lane] = key;
-            lmax = max(lmax, key);
+            __syncwarp();
+#pragma unroll 4
+            for (int i = 0; i < k; i++) {
+                const int4 pi = wb.pinfo[i];
+                const int pki = pi.z & 0x1ff, twi = ((pi.z >> 9) & 0x3f) - 1;
+                const int ebi = (pki >> 8) & 1, lasti = pki & 0xff;
+                const float s = comb<DOMAIN>(__int_as_float(pi.x), lp);
+                const bool is_stay = (ebi == 0 && lane == lasti);
+                const bool is_blank = (lane == blank);
+                const bool member = twi >= 0 && (is_blank || ebi == 0 || lane != lasti);
+                const bool dead = (member && twi < i) || (!is_blank && (((unsigned)pi.w >> lane) & 1u));
+                float acc = s;
+                if (pi.y >= 0) { const float mm = wb.pairmm[pi.y][lane]; acc = member ? mm : s; }
+                const float sv = wb.stay[i];
+                acc = is_stay ? sv : acc;
+                wb.cand[i][lane] = (active && (is_stay || !dead)) ? f2ord(acc) : 0u;
+            }
+        } else {
+            for (int i = 0; i < k; i++) {
+                const int4 pi = wb.pinfo[i];
+                const float sci = __int_as_float(pi.x);
+                const int pki = pi.z & 0x1ff, twi = ((pi.z >> 9) & 0x3f) - 1;
+                const int ebi = (pki >> 8) & 1, lasti = pki & 0xff;
+                const float s = comb<DOMAIN>(sci, lp);
+                float acc = s;
+                bool dead = false;
+                const bool is_stay = (ebi == 0 && lane == lasti);
+                const bool is_blank = (lane == blank);
+                const bool member = twi >= 0 && (is_blank || ebi == 0 || lane != lasti);
+                if (!last_frame || !is_blank) {
+                    if (twi >= 0) {
+                        if (twi < i) dead = member;
+                        else {
+                            const float mm = mrg<DOMAIN>(s, comb<DOMAIN>(sc[twi], lp));
+                            acc = member ? mm : s;
+                        }
+                    }
+                    if (!is_blank && (((unsigned)pi.w >> lane) & 1u)) dead = true;   // kept (X.v, 0) hosts this extend
+                    if (last_frame && !dead && !is_stay && ((wb.abs1[i] >> lane) & 1u)) {
+                        // kept (X.v, 1): on the last frame its blank candidate strips to X.v as well
+                        for (int j = 0; j < k; j++) {
+                            const int R = rel[i][j];
+                            if (R == REL_PFX + lane && depth[j] == depth[i] + 1 && ((pk[j] >> 8) & 1))
+                                acc = mrg<DOMAIN>(acc, comb<DOMAIN>(sc[j], lpb));
+                        }
+                    }
+                } else {
+                    // blank candidate on the last frame: it strips to X, so the (X,0) stay slot or an extend slot
+                    // that spells X hosts it; otherwise it stands alone
+                    if (ebi == 0 || twi >= 0) dead = true;
+                    else if (lasti != 0xff) {
+                        const int q0 = wb.p0[i], q1 = wb.p1[i];
+                        if (q1 >= 0 || (q0 >= 0 && (pk[q0] & 0xff) != lasti)) dead = true;
+                    }
+                }
+                if (is_stay) { acc = wb.stay[i]; dead = false; }
+                const unsigned key = (active && !dead) ? f2ord(acc) : 0u;
+                wb.cand[i][lane] = key;
+            }
         }
         __syncwarp();
 
-        // ---- prune: beam rounds of warp-max extraction -> kept states in rank order.  Column maxima live in
-        //      registers (lmax); the winning column is re-read with one row per lane, so a round is O(1) instructions.
-        //      Equal scores are ordered by raw string through rel[][] (reference: stable prob sort on top of the
-        //      string sort); at t = 0 ties keep vocabulary order (CTCBeamSearch.cu:390). -------------------------
+        // ---- prune (reference: stable descending prob sort on top of the ascending string sort, keep beam) --------
+        // (1) lower bound: parents are in score order and order[] ranks this frame's scores, so unmerged candidates
+        //     form a matrix sorted along both axes whose top-beam lies in the "staircase" (i+1)(j+1) <= beam.  The
+        //     beam-th largest key among probe cells of that staircase is a valid lower bound of the beam-th largest
+        //     merged key overall (merging only raises keys), and usually a tight one.
+        // (2) survivors = candidates >= bound, compacted in candidate-index order (a few more than beam);
+        // (3) exact rank of each survivor by all-pairs counting with the full order (score desc, raw string asc via
+        //     rel[][]; at t = 0 ties keep vocabulary order, CTCBeamSearch.cu:390): rank r < beam -> kept state r.
+        // If more than 64 candidates survive, fall back to beam rounds of warp-max extraction (same order).
         int m = 0;
-        for (; m < B; m++) {
-            const unsigned gmax = __reduce_max_sync(FULL, lmax);
-            if (gmax == 0u) break;
-            const unsigned any = __ballot_sync(FULL, lmax == gmax);
-            int wl = __ffs(any) - 1;
-            unsigned x = lane < k ? wb.cand[lane][wl] : 0u;          // column wl: row `lane`
-            const unsigned colmask = __ballot_sync(FULL, x == gmax);
-            int wi = __ffs(colmask) - 1;
-            if (t > 0 && (__popc(any) > 1 || __popc(colmask) > 1)) {
-                // exact tie: smallest raw string wins
-                int bi = -1, bs = 0;
-                if (lmax == gmax) {
-                    for (int i = 0; i < k; i++) {
-                        if (wb.cand[i][lane] != gmax) continue;
-                        const int si = cand_suffix_id(lane, blank, pk[i]);
-                        if (bi < 0 || cand_less_rel(rel[i][bi], si, bs, vch)) { bi = i; bs = si; }
-                    }
-                }
-                int bl = lane;
+        unsigned theta = 0u;
+        {
+            unsigned ck[2];
+            constexpr int cpl = BMAX <= 16 ? 1 : 2;
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const int oi = __shfl_xor_sync(FULL, bi, off), os = __shfl_xor_sync(FULL, bs, off);
-                    const int ol = __shfl_xor_sync(FULL, bl, off);
-                    if (oi >= 0 && (bi < 0 || cand_less_rel(rel[oi][bi], os, bs, vch))) { bi = oi; bs = os; bl = ol; }
-                }
-                wi = bi; wl = bl;
-                x = lane < k ? wb.cand[lane][wl] : 0u;
+            for (int q = 0; q < 2; q++) {
+                const int ci = p.cell_i[lane + 32 * q];
+                ck[q] = (q < cpl && ci < k) ? wb.cand[ci][wb.order[p.cell_j[lane + 32 * q]]] : 0u;
             }
-            if (lane == wi) { wb.cand[wi][wl] = 0u; x = 0u; }
-            const unsigned cmax = __reduce_max_sync(FULL, x);         // new maximum of the winning column
-            if (lane == wl) lmax = cmax;
-            if (lane == 0) { wb.selkey[m] = gmax; wb.seli[m] = wi; wb.selv[m] = wl; }
-            __syncwarp();
+            int cnt0 = 0, cnt1 = 0;
+#pragma unroll
+            for (int u = 0; u < 32; u++) {
+                const unsigned x0 = __shfl_sync(FULL, ck[0], u);
+                cnt0 += (x0 > ck[0] || (x0 == ck[0] && u < lane)) ? 1 : 0;
+                if (cpl > 1) {
+                    const unsigned x1 = __shfl_sync(FULL, ck[1], u);
+                    cnt0 += (x1 > ck[0]) ? 1 : 0;
+                    cnt1 += (x0 >= ck[1]) ? 1 : 0;
+                    cnt1 += (x1 > ck[1] || (x1 == ck[1] && u < lane)) ? 1 : 0;
+                }
+            }
+            unsigned th = (cnt0 == B - 1) ? ck[0] : 0u;
+            if (cpl > 1 && cnt1 == B - 1) th = ck[1];
+            theta = __reduce_max_sync(FULL, th);
+        }
+        int ns = 0;
+        for (int i = 0; i < k; i++) {
+            const unsigned key = wb.cand[i][lane];
+            const bool sv = key != 0u && key >= theta;
+            const unsigned mask = __ballot_sync(FULL, sv);
+            const int pos = ns + __popc(mask & ((1u << lane) - 1u));
+            if (sv && pos < 64) { wb.surv_key[pos] = key; wb.surv_iv[pos] = (i << 8) | lane; }
+            ns += __popc(mask);
+        }
+        __syncwarp();
+        if (ns <= 64) {
+            m = ns < B ? ns : B;
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int sidx = lane + 32 * q;
+                if (sidx < ns) {
+                    const unsigned key = wb.surv_key[sidx];
+                    const int iv = wb.surv_iv[sidx];
+                    const int mi = iv >> 8, mv = iv & 0xff;
+                    const int ms = cand_suffix_id(mv, blank, pk[mi]);
+                    int rank = 0;
+                    for (int o = 0; o < ns; o++) {
+                        const unsigned ok = wb.surv_key[o];
+                        if (ok > key) rank++;
+                        else if (ok == key && o != sidx) {
+                            if (t == 0) rank += o < sidx;
+                            else {
+                                const int oiv = wb.surv_iv[o];
+                                const int oi = oiv >> 8, ov = oiv & 0xff;
+                                rank += cand_less_rel(rel[oi][mi], cand_suffix_id(ov, blank, pk[oi]), ms, vch) ? 1 : 0;
+                            }
+                        }
+                    }
+                    if (rank < B) { wb.selkey[rank] = key; wb.seli[rank] = mi; wb.selv[rank] = mv; }
+                }
+            }
+        } else {
+            unsigned lmax = 0u;
+            for (int i = 0; i < k; i++) lmax = max(lmax, wb.cand[i][lane]);
+            for (m = 0; m < B; m++) {
+                const unsigned gmax = __reduce_max_sync(FULL, lmax);
+                if (gmax == 0u) break;
+                const unsigned any = __ballot_sync(FULL, lmax == gmax);
+                int wl = __ffs(any) - 1;
+                unsigned x = lane < k ? wb.cand[lane][wl] : 0u;          // column wl: row `lane`
+                const unsigned colmask = __ballot_sync(FULL, x == gmax);
+                int wi = __ffs(colmask) - 1;
+                if (t > 0 && (__popc(any) > 1 || __popc(colmask) > 1)) {
+                    // exact tie: smallest raw string wins
+                    int bi = -1, bs = 0;
+                    if (lmax == gmax) {
+                        for (int i = 0; i < k; i++) {
+                            if (wb.cand[i][lane] != gmax) continue;
+                            const int si = cand_suffix_id(lane, blank, pk[i]);
+                            if (bi < 0 || cand_less_rel(rel[i][bi], si, bs, vch)) { bi = i; bs = si; }
+                        }
+                    }
+                    int bl = lane;
+    #pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const int oi = __shfl_xor_sync(FULL, bi, off), os = __shfl_xor_sync(FULL, bs, off);
+                        const int ol = __shfl_xor_sync(FULL, bl, off);
+                        if (oi >= 0 && (bi < 0 || cand_less_rel(rel[oi][bi], os, bs, vch))) { bi = oi; bs = os; bl = ol; }
+                    }
+                    wi = bi; wl = bl;
+                    x = lane < k ? wb.cand[lane][wl] : 0u;
+                }
+                if (lane == wi) { wb.cand[wi][wl] = 0u; x = 0u; }
+                const unsigned cmax = __reduce_max_sync(FULL, x);         // new maximum of the winning column
+                if (lane == wl) lmax = cmax;
+                if (lane == 0) { wb.selkey[m] = gmax; wb.seli[m] = wi; wb.selv[m] = wl; }
+                __syncwarp();
+            }
         }
         __syncwarp();
 
@@ -857,6 +1015,19 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
     p.out_counts = reinterpret_cast<int *>(wo + L.off_counts);
     p.t0 = t0; p.t1 = t1;
     p.state = ws + L.off_state; p.state_stride = L.state_stride;
+    {
+        // probe cells of the prune lower bound: the (parent rank, score rank) pairs with the smallest (i+1)(j+1)
+        p.n_cells = a.beam <= 16 ? 32 : 64;
+        int taken = 0;
+        for (int prod = 1; taken < p.n_cells && prod <= a.beam * a.V; prod++)
+            for (int i = 0; i < a.beam && taken < p.n_cells; i++) {
+                if (prod % (i + 1)) continue;
+                const int j = prod / (i + 1) - 1;
+                if (j >= a.V) continue;
+                p.cell_i[taken] = (unsigned char)i; p.cell_j[taken] = (unsigned char)j; taken++;
+            }
+        for (; taken < 64; taken++) { p.cell_i[taken] = 255; p.cell_j[taken] = 0; }
+    }
 
     if (t1 == a.T) GASR_CUDA(cudaMemsetAsync(wo + L.off_paths, 0, (size_t)a.N * a.nbest * a.max_len, st));
     if (fast) {
