@@ -262,6 +262,7 @@ def main():
                          "traffic": None, "peak_source": peak_kind,
                          "algorithmic_bytes_per_launch": rec_bytes, "ms_per_launch": rec_ms_per_launch,
                          "launches_per_step": n_rec},
+            "decode_prune": dict(zip(("fallback_utt_frames", "survivors_total"), ctx.ctc_last_stats())),
             "pipeline": {"chunk_frames": chunk_frames, "launches_per_stage": launches_per_stage,
                          "note": "chunk_frames > 0: stages overlap on separate streams; stage times are sums of "
                                  "per-launch durations and may exceed ms_per_step"},

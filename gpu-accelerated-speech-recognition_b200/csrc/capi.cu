@@ -163,6 +163,13 @@ int gasr_timer_stop(gasr_ctx *ctx, float *ms) {
     return GASR_OK;
 }
 
+int gasr_ctc_last_stats(gasr_ctx *ctx, long long *fallback_frames, long long *survivors) {
+    GASR_ENTER(ctx);
+    if (fallback_frames) *fallback_frames = ctx->ctc_fallback_frames;
+    if (survivors) *survivors = ctx->ctc_survivors;
+    return GASR_OK;
+}
+
 int gasr_ctx_launch_count(gasr_ctx *ctx, long long *launches) {
     GASR_ENTER(ctx);
     GASR_CHECK(launches != nullptr, "null output");
@@ -297,6 +304,21 @@ int gasr_matadd(gasr_ctx *ctx, const float *x, int ldx, const float *y, int ldy,
     return launch_matadd(ctx, x, ldx, y, ldy, z, ldz, rows, cols, lambda, ctx->stream);
 }
 
+int gasr_xproj_gemm(gasr_ctx *ctx, const float *x, int ldx, const float *W, const float *bias, float *y, int ldy,
+                    int rows, int in, int out, int precision) {
+    GASR_ENTER(ctx);
+    GASR_CHECK(x && W && y && rows >= 0 && in >= 1 && out >= 1 && ldx >= in && ldy >= out, "xproj_gemm: bad arguments");
+    GASR_CHECK(precision == GASR_PREC_FP32 || precision == GASR_PREC_BF16, "xproj_gemm: unknown precision");
+    if (rows == 0) return GASR_OK;
+    if (!xproj_tc_supported(rows, in, out) || ldy % 4 != 0)
+        return launch_matmul(ctx, x, ldx, 0, W, out, 0, y, ldy, rows, in, out, bias, ctx->stream);
+    const size_t wb = xproj_tc_w_bytes(in, out), ab = xproj_tc_a_bytes(rows, in);
+    GASR_TRY(ws_reserve(ctx, ctx->ws_misc, wb + ab + 2048));
+    unsigned char *base = static_cast<unsigned char *>(ctx->ws_misc.ptr);
+    GASR_TRY(xproj_tc_prepare_weights(ctx, W, in, out, base, ctx->stream));
+    return launch_xproj_tc(ctx, x, ldx, rows, in, out, base, base + align_up(wb, 1024), bias, y, ldy, precision, ctx->stream);
+}
+
 int gasr_linear_forward(gasr_ctx *ctx, const float *x, int ldx, const float *W, const float *b, float *y, int ldy,
                         int rows, int in, int out, int act) {
     GASR_ENTER(ctx);
@@ -339,14 +361,25 @@ static int rnn_layer_direction(gasr_ctx *ctx, int cell, int T, int N, int in_l, 
                                const float *w_ih, const float *w_hh, const float *b_ih, const float *b_hh, int reverse,
                                float *out, int ldo, int col0, int precision, float *xproj, float *bias,
                                cudaStream_t st, StageEvents *prof) {
-    (void)precision;
     const int G = cell == GASR_CELL_GRU ? 3 : 1;
     if (cell == GASR_CELL_TANH) {
         GASR_TRY(launch_matadd(ctx, b_ih, H, b_hh, H, bias, H, 1, H, 1.0f, st));   // (b_hh + b_ih), RNN_Cell.cu:10
     } else {
         GASR_CUDA(cudaMemcpyAsync(bias, b_ih, sizeof(float) * G * H, cudaMemcpyDeviceToDevice, st));
     }
-    GASR_TRY(launch_matmul(ctx, src, ld_src, 0, w_ih, G * H, 0, xproj, G * H, T * N, in_l, G * H, bias, st));
+    const char *force = getenv("GASR_XPROJ");
+    const bool use_tc = !(force && force[0] == 's') && ld_src == in_l && xproj_tc_supported(T * N, in_l, G * H);
+    if (use_tc) {
+        // tensor-core path: W^T and A are split into bf16 hi/lo planes in the misc workspace
+        const size_t wb = xproj_tc_w_bytes(in_l, G * H), ab = xproj_tc_a_bytes(T * N, in_l);
+        GASR_TRY(ws_reserve(ctx, ctx->ws_misc, wb + ab + 2048));
+        unsigned char *base = static_cast<unsigned char *>(ctx->ws_misc.ptr);
+        GASR_TRY(xproj_tc_prepare_weights(ctx, w_ih, in_l, G * H, base, st));
+        GASR_TRY(launch_xproj_tc(ctx, src, ld_src, T * N, in_l, G * H, base, base + align_up(wb, 1024), bias, xproj, G * H,
+                                 precision, st));
+    } else {
+        GASR_TRY(launch_matmul(ctx, src, ld_src, 0, w_ih, G * H, 0, xproj, G * H, T * N, in_l, G * H, bias, st));
+    }
     if (prof) GASR_TRY(prof->mark(0, st));
     RnnLayerArgs a;
     a.cell = cell; a.T = T; a.N = N; a.H = H; a.reverse = reverse;
@@ -434,6 +467,8 @@ struct gasr_asr {
     // pipelined execution: time chunks flow through (layer 0 .. L-1, linear + decode) on separate streams
     int chunk = 0;                              // frames per chunk (0 = sequential path)
     float *xproj_all = nullptr, *bias_all = nullptr;   // [L][T*N*H], [L][H]
+    std::vector<void *> tc_abuf, tc_wbuf;       // per layer: bf16 hi/lo planes of the layer input / of W_ih^T
+    bool use_tc = false;
     std::vector<cudaEvent_t> sync_ev;           // cross-stream dependencies (no timing)
     std::vector<cudaEvent_t> t0_ev, t1_ev;      // per-launch timing pairs
     std::vector<int> t_tag;
@@ -486,6 +521,18 @@ int gasr_asr_create(gasr_ctx *ctx, const gasr_asr_config *cfg, const char *vocab
             a->chunk = want;
             alloc(&a->xproj_all, (size_t)cfg->L * rows * H);
             alloc(&a->bias_all, (size_t)cfg->L * H);
+            const char *force = getenv("GASR_XPROJ");
+            a->use_tc = !(force && force[0] == 's') && xproj_tc_supported((int)rows, cfg->in, H);
+            if (a->use_tc) {
+                a->tc_abuf.assign(cfg->L, nullptr); a->tc_wbuf.assign(cfg->L, nullptr);
+                for (int l = 0; l < cfg->L && st == GASR_OK; l++) {
+                    const int in_l = l == 0 ? cfg->in : H;
+                    const int nchunks = ceil_div(cfg->T, want);
+                    st = gasr_malloc_device(ctx, align_up(xproj_tc_a_bytes(want * cfg->N, in_l), 1024) * (size_t)nchunks + 1024,
+                                            &a->tc_abuf[l]);
+                    if (st == GASR_OK) st = gasr_malloc_device(ctx, xproj_tc_w_bytes(in_l, H) + 1024, &a->tc_wbuf[l]);
+                }
+            }
         }
     }
     if (st != GASR_OK) { gasr_asr_destroy(a); return st; }
@@ -501,6 +548,8 @@ int gasr_asr_destroy(gasr_asr *a) {
     for (auto v : {&a->w_ih, &a->w_hh, &a->b_ih, &a->b_hh, &a->hiddens})
         for (float *p : *v) if (p) gasr_free_device(ctx, p);
     for (float *p : {a->fc_w, a->fc_b, a->x_dev, a->logp, a->xproj_all, a->bias_all}) if (p) gasr_free_device(ctx, p);
+    for (void *p : a->tc_abuf) if (p) gasr_free_device(ctx, p);
+    for (void *p : a->tc_wbuf) if (p) gasr_free_device(ctx, p);
     for (cudaEvent_t e : a->sync_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : a->t0_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : a->t1_ev) cudaEventDestroy(e);
@@ -528,6 +577,9 @@ int gasr_asr_set_weights(gasr_asr *a, const float *const *w_ih, const float *con
             GASR_TRY(gasr_memcpy_h2d(ctx, a->b_hh[i], b_hh[i], sizeof(float) * G * H));
         }
     }
+    if (a->use_tc)
+        for (int l = 0; l < c.L; l++)
+            GASR_TRY(xproj_tc_prepare_weights(ctx, a->w_ih[l], l == 0 ? c.in : H, H, a->tc_wbuf[l], ctx->stream));
     GASR_TRY(gasr_memcpy_h2d(ctx, a->fc_w, fc_w, sizeof(float) * D * H * c.V));
     GASR_TRY(gasr_memcpy_h2d(ctx, a->fc_b, fc_b, sizeof(float) * c.V));
     a->have_weights = true;
@@ -609,8 +661,16 @@ static int asr_run_pipelined(gasr_asr *a, const float *x_dev, char *out_paths, i
             float *xp = a->xproj_all + (size_t)l * T * N * H;
             if (l > 0) GASR_CUDA(cudaStreamWaitEvent(st, a->sync_ev[(size_t)(l - 1) * C + ci], 0));
             GASR_TRY(timed_begin(0, st));
-            GASR_TRY(launch_matmul(ctx, src + row0 * in_l, in_l, 0, a->w_ih[l], H, 0, xp + row0 * H, H, rows, in_l, H,
-                                   a->bias_all + (size_t)l * H, st));
+            if (a->use_tc) {
+                // each chunk owns a disjoint slice of the layer's bf16 scratch planes
+                const size_t a_off = align_up(xproj_tc_a_bytes(Tc * N, in_l), 1024) * (size_t)ci;
+                GASR_TRY(launch_xproj_tc(ctx, src + row0 * in_l, in_l, rows, in_l, H, a->tc_wbuf[l],
+                                         static_cast<unsigned char *>(a->tc_abuf[l]) + a_off, a->bias_all + (size_t)l * H,
+                                         xp + row0 * H, H, c.precision, st));
+            } else {
+                GASR_TRY(launch_matmul(ctx, src + row0 * in_l, in_l, 0, a->w_ih[l], H, 0, xp + row0 * H, H, rows, in_l, H,
+                                       a->bias_all + (size_t)l * H, st));
+            }
             GASR_TRY(timed_end(st));
             RnnLayerArgs ra;
             ra.cell = c.cell; ra.T = T; ra.N = N; ra.H = H; ra.reverse = 0;

@@ -58,6 +58,7 @@ struct gasr_ctx {
     gasr::Workspace ws_ctc, ws_rnn, ws_misc, ws_out;
     void *pinned_out = nullptr;          // pinned staging for decode results
     size_t pinned_out_bytes = 0;
+    long long ctc_fallback_frames = 0, ctc_survivors = 0;   // diagnostics of the last decode
 };
 
 namespace gasr {
@@ -78,6 +79,14 @@ int launch_linear(gasr_ctx *ctx, const float *x, int ldx, const float *W, const 
 int launch_log_softmax(gasr_ctx *ctx, const float *x, int ldx, float *y, int ldy, int rows, int cols, cudaStream_t st);
 int launch_rnn_cell(gasr_ctx *ctx, const float *x, const float *h_prev, const float *w_ih, const float *w_hh,
                     const float *b_ih, const float *b_hh, float *out, int batch, int in, int hidden, cudaStream_t st);
+
+// tcgen05 / TMEM / TMA projection GEMM (xproj_gemm_tc.cu)
+bool xproj_tc_supported(int M, int K, int N);
+size_t xproj_tc_a_bytes(int M, int K);      // scratch for the bf16 hi/lo planes of A
+size_t xproj_tc_w_bytes(int K, int N);      // prepared (transposed, split) weights
+int xproj_tc_prepare_weights(gasr_ctx *ctx, const float *W, int K, int N, void *wbuf, cudaStream_t st);
+int launch_xproj_tc(gasr_ctx *ctx, const float *A, int lda, int M, int K, int N, const void *wbuf, void *abuf,
+                    const float *bias, float *C, int ldc, int precision, cudaStream_t st);
 
 struct RnnLayerArgs {
     int cell, T, N, H, reverse;

@@ -116,6 +116,7 @@ struct CtcParams {
     int *out_lens;       // [N, nbest]
     float *out_scores;   // [N, nbest]
     int *out_counts;     // [N]
+    int *out_stats;      // [N, 2]: frames that took the prune fallback, sum of prune survivors (diagnostics)
     unsigned char cell_i[64], cell_j[64];   // prune lower-bound probe cells (parent rank, log-prob rank); warp kernel
     int n_cells;         // 32 (one per lane) or 64
     int t0, t1;          // frames [t0, t1) are decoded by this launch (time chunking; warp kernel only)
@@ -551,6 +552,7 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
     if (active) vch_s[lane] = p.vocab[lane];
     const char *vch = vch_s;
     int kept = 1, nodes = 1, cur = 0;
+    int stat_surv = 0, stat_fallback = 0;
     int4 *gstate = reinterpret_cast<int4 *>(p.state + (size_t)utt * p.state_stride);
     constexpr int kStateVec = (int)(sizeof(WarpBeam<BMAX>) / sizeof(int4));
     if (p.t0 == 0) {
@@ -728,7 +730,7 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
         unsigned theta = 0u;
         {
             unsigned ck[2];
-            constexpr int cpl = BMAX <= 16 ? 1 : 2;
+            constexpr int cpl = 2;
 #pragma unroll
             for (int q = 0; q < 2; q++) {
                 const int ci = p.cell_i[lane + 32 * q];
@@ -749,8 +751,15 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
             unsigned th = (cnt0 == B - 1) ? ck[0] : 0u;
             if (cpl > 1 && cnt1 == B - 1) th = ck[1];
             theta = __reduce_max_sync(FULL, th);
+            // second bound: the best parent's beam best-ranked candidates, if none of them was absorbed
+            if (B <= 32 && B <= V) {
+                const unsigned r0 = lane < B ? wb.cand[0][wb.order[lane]] : 0xffffffffu;
+                const unsigned mn = __reduce_min_sync(FULL, r0);
+                theta = max(theta, mn);
+            }
         }
         int ns = 0;
+#pragma unroll 4
         for (int i = 0; i < k; i++) {
             const unsigned key = wb.cand[i][lane];
             const bool sv = key != 0u && key >= theta;
@@ -760,6 +769,8 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
             ns += __popc(mask);
         }
         __syncwarp();
+        stat_surv += ns;
+        stat_fallback += ns > 64;
         if (ns <= 64) {
             m = ns < B ? ns : B;
 #pragma unroll
@@ -900,8 +911,16 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
         // more chunks follow: park the beam in HBM
         const int4 *src = reinterpret_cast<const int4 *>(&wb);
         for (int i = lane; i < kStateVec; i += 32) gstate[i] = src[i];
-        if (lane == 0) gstate[kStateVec] = make_int4(kept, nodes, cur, 0);
+        if (lane == 0) {
+            gstate[kStateVec] = make_int4(kept, nodes, cur, 0);
+            if (p.t0 == 0) { p.out_stats[2 * utt] = stat_fallback; p.out_stats[2 * utt + 1] = stat_surv; }
+            else { p.out_stats[2 * utt] += stat_fallback; p.out_stats[2 * utt + 1] += stat_surv; }
+        }
         return;
+    }
+    if (lane == 0) {
+        if (p.t0 == 0) { p.out_stats[2 * utt] = stat_fallback; p.out_stats[2 * utt + 1] = stat_surv; }
+        else { p.out_stats[2 * utt] += stat_fallback; p.out_stats[2 * utt + 1] += stat_surv; }
     }
     // ---- result (CTCBeamSearch.cu:290-298): kept states best first, path = labels of X -------------------------
     if (lane == 0 && p.out_counts) p.out_counts[utt] = kept;
@@ -940,7 +959,7 @@ static size_t ctc_smem_bytes(int B, int V, int Vp, int n_pad) {
 struct CtcLayout {
     int Vp, n_pad, cap, threads;
     size_t smem, off_vocab, off_parent, off_meta, off_child, off_state, state_stride, off_paths, off_lens, off_scores,
-        off_counts, total;
+        off_counts, off_stats, total;
     size_t out_bytes;
 };
 
@@ -966,6 +985,7 @@ static int ctc_layout(const CtcArgs &a, CtcLayout &L) {
     L.off_lens = q; q = align_up(q + sizeof(int) * (size_t)a.N * a.nbest, 256);
     L.off_scores = q; q = align_up(q + sizeof(float) * (size_t)a.N * a.nbest, 256);
     L.off_counts = q; q = align_up(q + sizeof(int) * (size_t)a.N, 256);
+    L.off_stats = q; q = align_up(q + 2 * sizeof(int) * (size_t)a.N, 256);
     L.out_bytes = q;
     return GASR_OK;
 }
@@ -1013,11 +1033,13 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
     p.out_lens = reinterpret_cast<int *>(wo + L.off_lens);
     p.out_scores = reinterpret_cast<float *>(wo + L.off_scores);
     p.out_counts = reinterpret_cast<int *>(wo + L.off_counts);
+    p.out_stats = reinterpret_cast<int *>(wo + L.off_stats);
+    if (!fast) GASR_CUDA(cudaMemsetAsync(p.out_stats, 0, 2 * sizeof(int) * (size_t)a.N, st));
     p.t0 = t0; p.t1 = t1;
     p.state = ws + L.off_state; p.state_stride = L.state_stride;
     {
         // probe cells of the prune lower bound: the (parent rank, score rank) pairs with the smallest (i+1)(j+1)
-        p.n_cells = a.beam <= 16 ? 32 : 64;
+        p.n_cells = 64;
         int taken = 0;
         for (int prod = 1; taken < p.n_cells && prod <= a.beam * a.V; prod++)
             for (int i = 0; i < a.beam && taken < p.n_cells; i++) {
@@ -1076,6 +1098,11 @@ int ctc_decode_finish(gasr_ctx *ctx, const CtcArgs &a) {
     memcpy(a.out_lens, h + L.off_lens, sizeof(int) * (size_t)a.N * a.nbest);
     memcpy(a.out_scores, h + L.off_scores, sizeof(float) * (size_t)a.N * a.nbest);
     if (a.out_counts) memcpy(a.out_counts, h + L.off_counts, sizeof(int) * (size_t)a.N);
+    {
+        const int *stt = reinterpret_cast<const int *>(h + L.off_stats);
+        ctx->ctc_fallback_frames = 0; ctx->ctc_survivors = 0;
+        for (int n = 0; n < a.N; n++) { ctx->ctc_fallback_frames += stt[2 * n]; ctx->ctc_survivors += stt[2 * n + 1]; }
+    }
     int status = GASR_OK;
     for (size_t i = 0; i < (size_t)a.N * a.nbest; i++)
         if (a.out_lens[i] > a.max_len) status = GASR_ERR_TRUNCATED;

@@ -52,8 +52,8 @@ EXPORTS = [
     "gasr_ctx_sm_count", "gasr_timer_start", "gasr_timer_stop", "gasr_ctx_launch_count", "gasr_malloc_device",
     "gasr_free_device", "gasr_malloc_host", "gasr_free_host", "gasr_matrix_alloc", "gasr_memcpy_h2d",
     "gasr_memcpy_d2h", "gasr_memcpy_h2d_async", "gasr_memcpy_d2h_async", "gasr_memset_device", "gasr_memory_stats",
-    "gasr_matmul", "gasr_matadd", "gasr_linear_forward", "gasr_log_softmax", "gasr_rnn_cell_forward",
-    "gasr_rnn_forward", "gasr_ctc_decode", "gasr_ctc_decode_host", "gasr_asr_create", "gasr_asr_destroy",
+    "gasr_matmul", "gasr_matadd", "gasr_xproj_gemm", "gasr_linear_forward", "gasr_log_softmax", "gasr_rnn_cell_forward",
+    "gasr_rnn_forward", "gasr_ctc_decode", "gasr_ctc_last_stats", "gasr_ctc_decode_host", "gasr_asr_create", "gasr_asr_destroy",
     "gasr_asr_set_weights", "gasr_asr_run_host", "gasr_asr_run_device", "gasr_asr_logprobs", "gasr_asr_stage_times", "gasr_asr_stage_launches",
 ]
 
@@ -152,6 +152,11 @@ class Context:
         _check(_lib.gasr_timer_stop(self._h, ctypes.byref(ms)))
         return ms.value
 
+    def ctc_last_stats(self):
+        f, s = ctypes.c_longlong(0), ctypes.c_longlong(0)
+        _check(_lib.gasr_ctc_last_stats(self._h, ctypes.byref(f), ctypes.byref(s)))
+        return f.value, s.value
+
     def launch_count(self):
         n = ctypes.c_longlong(0)
         _check(_lib.gasr_ctx_launch_count(self._h, ctypes.byref(n)))
@@ -168,6 +173,9 @@ class Context:
 
     def matadd(self, x, ldx, y, ldy, z, ldz, rows, cols, lam):
         _check(_lib.gasr_matadd(self._h, x, ldx, y, ldy, z, ldz, rows, cols, ctypes.c_float(lam)))
+
+    def xproj_gemm(self, x, ldx, W, bias, y, ldy, rows, in_, out, precision=PREC_FP32):
+        _check(_lib.gasr_xproj_gemm(self._h, x, ldx, W, bias, y, ldy, rows, in_, out, precision))
 
     def linear(self, x, ldx, W, b, y, ldy, rows, in_, out, act):
         _check(_lib.gasr_linear_forward(self._h, x, ldx, W, b, y, ldy, rows, in_, out, act))
@@ -470,6 +478,7 @@ def _declare():
     L.gasr_timer_start.argtypes = [vp]
     L.gasr_timer_stop.argtypes = [vp, c_float_p]
     L.gasr_ctx_launch_count.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong)]
+    L.gasr_ctc_last_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong)]
     L.gasr_malloc_device.argtypes = [vp, sz, c_void_pp]
     L.gasr_free_device.argtypes = [vp, vp]
     L.gasr_malloc_host.argtypes = [vp, sz, c_void_pp]
@@ -482,6 +491,7 @@ def _declare():
     L.gasr_matmul.argtypes = [vp, vp, ci, ci, vp, ci, ci, vp, ci, ci, ci, ci]
     L.gasr_matadd.argtypes = [vp, vp, ci, vp, ci, vp, ci, ci, ci, cf]
     L.gasr_linear_forward.argtypes = [vp, vp, ci, vp, vp, vp, ci, ci, ci, ci, ci]
+    L.gasr_xproj_gemm.argtypes = [vp, vp, ci, vp, vp, vp, ci, ci, ci, ci, ci]
     L.gasr_log_softmax.argtypes = [vp, vp, ci, vp, ci, ci, ci]
     L.gasr_rnn_cell_forward.argtypes = [vp] + [vp] * 7 + [ci, ci, ci]
     L.gasr_rnn_forward.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp, ci]

@@ -78,6 +78,13 @@ int gasr_matmul(gasr_ctx *ctx, const float *x, int ldx, int trans_x, const float
 int gasr_matadd(gasr_ctx *ctx, const float *x, int ldx, const float *y, int ldy, float *z, int ldz, int rows,
                 int cols, float lambda);
 
+/* ---- batched input projection (the x*W_ih of RNN_Cell.cu:66, hoisted over all frames) --------------- */
+/* y[rows,out] = x[rows,in] * W[in,out] + bias on the tcgen05 tensor cores when out % 128 == 0 (operands split
+ * into bf16 hi/lo planes: GASR_PREC_FP32 accumulates hi*hi + hi*lo + lo*hi, GASR_PREC_BF16 hi*hi only);
+ * other shapes use the fp32 FFMA GEMM.  bias may be NULL.                                                 */
+int gasr_xproj_gemm(gasr_ctx *ctx, const float *x, int ldx, const float *W, const float *bias, float *y, int ldy,
+                    int rows, int in, int out, int precision);
+
 /* ---- Linear: Linear.cu:3-10,42-49 (+ log-softmax of baseline/model.py:49) ------------------------ */
 /* y[rows,out] = act(x[rows,in] * W[in,out] + b), one fused kernel.  act = GASR_ACT_*.               */
 int gasr_linear_forward(gasr_ctx *ctx, const float *x, int ldx, const float *W, const float *b, float *y,
@@ -113,6 +120,9 @@ int gasr_rnn_forward(gasr_ctx *ctx, int cell, int bidirectional, int T, int N, i
 int gasr_ctc_decode(gasr_ctx *ctx, const float *scores, int domain, int T, int N, int V, int ld, int beam,
                     int blank, const char *vocab, int max_len, int nbest, char *out_paths, int *out_lens,
                     float *out_scores, int *out_counts);
+/* Diagnostics of the last decode on this ctx: utterance-frames whose prune exceeded the 64-survivor fast path,
+ * and the sum of prune survivors over all utterance-frames (mean survivors = that / (N*T)).             */
+int gasr_ctc_last_stats(gasr_ctx *ctx, long long *fallback_frames, long long *survivors);
 /* Same with the scores in host memory (copied to the device inside the call).                       */
 int gasr_ctc_decode_host(gasr_ctx *ctx, const float *scores_host, int domain, int T, int N, int V, int beam,
                          int blank, const char *vocab, int max_len, int nbest, char *out_paths, int *out_lens,

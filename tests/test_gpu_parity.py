@@ -265,6 +265,26 @@ def test_matmul_variants_and_matadd(gasr, ctx, O):
         gasr.matrixMul(A, B, C)   # dimension mismatch is an error code, not exit(0)
 
 
+@pytest.mark.parametrize("rows,in_,out", [(1, 1, 128), (130, 161, 512), (1000, 512, 512), (257, 70, 256), (64, 2048, 128),
+                                         (50, 33, 96)])
+def test_xproj_gemm_tensor_core_vs_oracle(gasr, ctx, O, rows, in_, out):
+    """tcgen05 projection GEMM: fp32-grade mode within 1e-4 of the fp32 oracle, bf16 mode within its 2e-2 budget."""
+    rng = np.random.default_rng(rows * 7 + in_)
+    x = rng.uniform(-1, 1, size=(rows, in_)).astype(np.float32)
+    W = rng.uniform(-1, 1, size=(in_, out)).astype(np.float32) / np.float32(np.sqrt(in_))
+    b = rng.uniform(-1, 1, size=(out,)).astype(np.float32)
+    ref = O.matmul(x, W) + b
+    dx, dW, db, dy = ctx.to_device(x), ctx.to_device(W), ctx.to_device(b), ctx.malloc(rows * out * 4)
+    ctx.xproj_gemm(dx, in_, dW, db, dy, out, rows, in_, out, gasr.PREC_FP32)
+    got = ctx.to_host(dy, (rows, out))
+    assert np.abs(got - ref).max() < AM_TOL
+    ctx.xproj_gemm(dx, in_, dW, db, dy, out, rows, in_, out, gasr.PREC_BF16)
+    got = ctx.to_host(dy, (rows, out))
+    assert np.abs(got - ref).max() < 2e-2
+    for p in (dx, dW, db, dy):
+        ctx.free(p)
+
+
 @pytest.mark.parametrize("rows,in_,out,act", [(1, 5, 3, "relu"), (77, 64, 29, "logsoftmax"), (1000, 512, 29, "logsoftmax"),
                                               (130, 512, 32, "none"), (50, 300, 47, "logsoftmax"), (40, 2048, 47, "relu"),
                                               (64, 1600, 29, "logsoftmax")])

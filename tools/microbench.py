@@ -22,18 +22,23 @@ def main():
     ap.add_argument("--D", type=int, default=161)
     ap.add_argument("--L", type=int, default=1)
     ap.add_argument("--iters", type=int, default=5)
-    ap.add_argument("--kind", default="random", choices=["random", "peaky"])
+    ap.add_argument("--kind", default="random", choices=["random", "peaky", "flat"])
     a = ap.parse_args()
     ctx = gasr.Context(0)
     V = 29
     if a.stage == "ctc":
-        lp = (synth.random_logprobs if a.kind == "random" else synth.peaky_logprobs)(1234, a.T, a.N, V)
+        if a.kind == "flat":
+            lp = synth.random_logprobs(1234, a.T, a.N, V, scale=0.05)   # like a random-init model's outputs
+        else:
+            lp = (synth.random_logprobs if a.kind == "random" else synth.peaky_logprobs)(1234, a.T, a.N, V)
         d = ctx.to_device(lp)
         for it in range(a.iters):
             ctx.sync(); ctx.timer_start()
             p, s = ctx.ctc_decode(d, gasr.DOMAIN_LOG, a.T, a.N, V, V, a.beam, 0, synth.VOCAB29)
             ms = ctx.timer_stop()
-            print(f"ctc T={a.T} N={a.N} beam={a.beam}: {ms:.3f} ms  ({1e3 * ms / a.T:.2f} us/frame)  len0={len(p[0])}")
+            fb, sv = ctx.ctc_last_stats()
+            print(f"ctc T={a.T} N={a.N} beam={a.beam}: {ms:.3f} ms  ({1e3 * ms / a.T:.2f} us/frame)  len0={len(p[0])} "
+                  f"fallback_frames={fb} mean_survivors={sv / (a.T * a.N):.1f}")
     elif a.stage == "rnn":
         x = synth.spectrogram_batch(1, a.T, a.N, a.D)
         w = synth.rnn_weights(2, a.D, a.H, a.L)
@@ -64,7 +69,16 @@ def main():
             ctx.sync(); ctx.timer_start()
             ctx.matmul(dx, a.D, 0, dW, a.H, 0, dy, a.H, rows, a.D, a.H)
             ms = ctx.timer_stop()
-            print(f"gemm {rows}x{a.D}x{a.H}: {ms:.3f} ms  {2.0 * rows * a.D * a.H / ms / 1e9:.2f} TFLOP/s")
+            print(f"gemm simt {rows}x{a.D}x{a.H}: {ms:.3f} ms  {2.0 * rows * a.D * a.H / ms / 1e9:.2f} TFLOP/s")
+            ref = ctx.to_host(dy, (rows, a.H))
+            for prec, name in ((gasr.PREC_FP32, "tc 3xbf16"), (gasr.PREC_BF16, "tc bf16")):
+                ctx.sync(); ctx.timer_start()
+                ctx.xproj_gemm(dx, a.D, dW, None, dy, a.H, rows, a.D, a.H, prec)
+                ms = ctx.timer_stop()
+                got = ctx.to_host(dy, (rows, a.H))
+                err = float(np.abs(got - ref).max()) / float(np.abs(ref).max())
+                print(f"gemm {name} {rows}x{a.D}x{a.H}: {ms:.3f} ms  {2.0 * rows * a.D * a.H / ms / 1e9:.2f} TFLOP/s (algorithmic, "
+                      f"incl. operand split)  max rel err vs simt {err:.2e}")
     ctx.close()
 
 
