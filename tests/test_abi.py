@@ -85,3 +85,12 @@ def test_synth_is_deterministic_and_sharded_consistently():
     assert abs(np.abs(w1[1][0]).max()) <= 1 / np.sqrt(8)
     lp = synth.random_logprobs(5, 9, 2, 29)
     assert np.allclose(np.exp(lp.astype(np.float64)).sum(-1), 1.0, atol=1e-5)
+
+
+def test_cpp_headers_compile_without_cuda(tmp_path, gasr):
+    """The C++ mirror of the reference classes needs only g++ and libgasr.so (no CUDA headers on the caller side)."""
+    exe = str(tmp_path / "t")
+    r = subprocess.run(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "cpp", "test_modules.cpp"), "-o", exe, "-L" + PKG, "-lgasr",
+                        "-Wl,-rpath," + PKG], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

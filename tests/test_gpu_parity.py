@@ -394,3 +394,17 @@ def test_pipeline_end_to_end(gasr, ctx, O, T, N, D, H, L, beam):
     assert pipe.run_device(dx) == (paths, scores)
     ctx.free(dx)
     pipe.close()
+
+
+def test_cpp_module_mirror(tmp_path):
+    """include/*.h (cuMatrix, Linear, RNN_Cell, RNN, CTCBeamSearch, MemoryMonitor) compiled with plain g++ and linked
+    to libgasr.so: the reference's own drivers (nn_test.cpp, main.cpp) as assertions."""
+    import subprocess
+    pkg = os.path.join(ROOT, "gpu-accelerated-speech-recognition_b200")
+    exe = str(tmp_path / "test_modules")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "test_modules.cpp"), "-o", exe, "-L" + pkg, "-lgasr",
+                    "-Wl,-rpath," + pkg], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "all C++ module checks passed" in out.stdout
