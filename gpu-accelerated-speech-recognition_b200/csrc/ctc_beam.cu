@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -944,6 +945,466 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
     }
 }
 
+// =====================================================================================================
+// Latency path: ONE 128-THREAD CTA PER UTTERANCE (beam <= 32, vocabulary <= 32).  Same algorithm and data layout as
+// the warp kernel above, but the phases of a frame are spread over four warps so that the serial critical path
+// is short when utterances are scarce (cfg2: 64 per GPU):
+//   A  warp 0: twin / parent relations from node ids + "stay" candidates | warp 1: rank of the frame's scores |
+//      warps 2-3: prefix-relation matrix of the beam chosen in the previous frame (only tie-breaks need it)
+//   B  all warps: merged candidates, parent i on warp i % 4 (lane = vocab id)
+//   C  warps 0-1: staircase lower bound (32 probe cells each), warp 2: best-parent bound
+//   D  all warps: filter rows i % 4 == warp, survivors appended through a shared counter
+//   E  all warps: rank counting, "others" o % 4 == warp, partial ranks summed in shared memory
+//   F  warp 0: rank < beam -> kept state; trie lookup / allocation
+// =====================================================================================================
+template <int BMAX>
+struct CtaBeam {
+    float sc[2][BMAX];
+    int node[2][BMAX];
+    int pnode[2][BMAX];
+    int depth[2][BMAX];
+    int pk[2][BMAX];
+    int4 pinfo[BMAX];
+    int tw[BMAX], p0[BMAX], p1[BMAX];
+    unsigned abs0[BMAX], abs1[BMAX];
+    float stay[BMAX];
+    unsigned selkey[BMAX];
+    int seli[BMAX], selv[BMAX];
+    unsigned char rel[2][BMAX][BMAX];
+    unsigned cand[BMAX][32];
+    int order[32];
+    unsigned surv_key[64];
+    int surv_iv[64];
+    int rankc[64];
+    unsigned theta_part[4];
+    int ns, kept, nodes, sel_m;
+};
+
+// new prefix relation of kept states r, q (chosen from old states ar, aq with appended labels er, eq2; -1 = none)
+__device__ __forceinline__ int rel_child(int R, int er, int eq2, int dA, int dB, int nodeA, int nodeB, const char *vch,
+                                         const int *parent, const int *meta) {
+    if (R == REL_EQ) {
+        if (er < 0 && eq2 < 0) return REL_EQ;
+        if (er < 0) return REL_PFX + eq2;
+        if (eq2 < 0) return REL_RPFX + er;
+        if (er == eq2) return REL_EQ;
+        return ch_less(vch, er, eq2) ? REL_LT : REL_GT;
+    }
+    if (R == REL_LT || R == REL_GT) return R;
+    if (R < REL_RPFX) {                          // A proper prefix of B, B = A.y...
+        const int y = R - REL_PFX;
+        if (er < 0) return R;
+        if (er != y) return ch_less(vch, er, y) ? REL_LT : REL_GT;
+        if (dB == dA + 1) return eq2 < 0 ? REL_EQ : REL_PFX + eq2;
+        return REL_PFX + trie_char_at(parent, meta, nodeB, dA + 1);
+    }
+    const int y = R - REL_RPFX;                  // B proper prefix of A, A = B.y...
+    if (eq2 < 0) return R;
+    if (eq2 != y) return ch_less(vch, y, eq2) ? REL_LT : REL_GT;
+    if (dA == dB + 1) return er < 0 ? REL_EQ : REL_RPFX + er;
+    return REL_RPFX + trie_char_at(parent, meta, nodeA, dB + 1);
+}
+
+template <int DOMAIN, int BMAX>
+__global__ void __launch_bounds__(128) ctc_beam_cta_kernel(const CtcParams p) {
+    __shared__ __align__(16) CtaBeam<BMAX> cb;
+    __shared__ char vch_s[32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int utt = blockIdx.x;
+    const int V = p.V, B = p.beam, blank = p.blank, Vp = p.Vp;
+    constexpr unsigned FULL = 0xffffffffu;
+    const bool active = lane < V;
+    const char *vch = vch_s;
+
+    int *parent = p.parent + (size_t)utt * p.cap;
+    int *meta = p.meta + (size_t)utt * p.cap;
+    int *child = p.child + (size_t)utt * p.cap * Vp;
+    const float *S = p.scores + (size_t)utt * p.ld;
+    const size_t frame_stride = (size_t)p.N * p.ld;
+    int4 *gstate = reinterpret_cast<int4 *>(p.state + (size_t)utt * p.state_stride);
+    constexpr int kStateVec = (int)(sizeof(CtaBeam<BMAX>) / sizeof(int4));
+
+    if (tid < V) vch_s[tid] = p.vocab[tid];
+    int cur = 0;
+    int stat_surv = 0, stat_fallback = 0;
+    bool pending = false;      // the prefix relations of the current beam still have to be derived (phase A)
+    if (p.t0 == 0) {
+        if (tid < Vp) child[tid] = 0;
+        if (tid == 0) {
+            parent[0] = -1; meta[0] = 0xff;
+            cb.sc[0][0] = DOMAIN ? 0.0f : 1.0f;
+            cb.node[0][0] = 0; cb.pnode[0][0] = kNone; cb.depth[0][0] = 0; cb.pk[0][0] = 0xff | (1 << 8);
+            cb.rel[0][0][0] = REL_EQ;
+            cb.kept = 1; cb.nodes = 1;
+        }
+    } else {
+        int4 *dst = reinterpret_cast<int4 *>(&cb);
+        for (int i = tid; i < kStateVec; i += 128) dst[i] = gstate[i];
+        cur = gstate[kStateVec].x;
+    }
+    float lp_next = active ? S[(size_t)p.t0 * frame_stride + lane] : 0.0f;
+    __syncthreads();
+    int kept = cb.kept;
+
+    for (int t = p.t0; t < p.t1; t++) {
+        const float lp = lp_next;
+        if (t + 1 < p.t1 && active) lp_next = S[(size_t)(t + 1) * frame_stride + lane];
+        const bool last_frame = (t == p.T - 1) && (t > 0);
+        const int k = kept;
+        const float *sc = cb.sc[cur];
+        const int *node = cb.node[cur], *pnode = cb.pnode[cur], *pk = cb.pk[cur], *depth = cb.depth[cur];
+        const unsigned char (*rel)[BMAX] = cb.rel[cur];
+        const float lpb = __shfl_sync(FULL, lp, blank);
+
+        // ================= phase A =================
+        if (w == 0) {
+            // relations from node ids; with beam <= 16 two lanes share a state and split the scan
+            constexpr int HALVES = BMAX <= 16 ? 2 : 1;
+            const int r = HALVES == 2 ? (lane & 15) : lane, half = HALVES == 2 ? (lane >> 4) : 0;
+            int my_tw = kNone, my_p0 = kNone, my_p1 = kNone;
+            unsigned a0 = 0, a1 = 0;
+            int my_last = 0xff, my_eb = 1;
+            if (r < k) {
+                const int nd = node[r], pn = pnode[r];
+                my_last = pk[r] & 0xff; my_eb = (pk[r] >> 8) & 1;
+                const int jb = HALVES == 2 ? half * 8 : 0, je = HALVES == 2 ? min(k, jb + 8) : k;
+#pragma unroll 4
+                for (int j = jb; j < je; j++) {
+                    const int nj = node[j], pnj = pnode[j], pkj = pk[j];
+                    if (nj == nd && j != r) my_tw = j;
+                    if (nj == pn) { if ((pkj >> 8) & 1) my_p1 = j; else my_p0 = j; }
+                    if (pnj == nd) { const unsigned bit = 1u << (pkj & 0xff); if ((pkj >> 8) & 1) a1 |= bit; else a0 |= bit; }
+                }
+            }
+            if (HALVES == 2) {
+                my_tw = max(my_tw, __shfl_xor_sync(FULL, my_tw, 16));
+                my_p0 = max(my_p0, __shfl_xor_sync(FULL, my_p0, 16));
+                my_p1 = max(my_p1, __shfl_xor_sync(FULL, my_p1, 16));
+                a0 |= __shfl_xor_sync(FULL, a0, 16);
+                a1 |= __shfl_xor_sync(FULL, a1, 16);
+            }
+            const bool owner = r < k && half == 0;
+            if (owner) {
+                cb.tw[r] = my_tw; cb.p0[r] = my_p0; cb.p1[r] = my_p1; cb.abs0[r] = a0; cb.abs1[r] = a1;
+                cb.pinfo[r] = make_int4(__float_as_int(sc[r]), __float_as_int(my_tw >= 0 ? sc[my_tw] : 0.0f),
+                                        pk[r] | ((my_tw + 1) << 9), (int)a0);
+            }
+            // "stay" candidates, one per (X,0) state
+            const bool do_stay = owner && my_eb == 0;
+            const float lpv = __shfl_sync(FULL, lp, do_stay ? my_last : 0);
+            if (do_stay) {
+                int m0 = my_p0, m1 = my_p1, m2 = r, tmp;
+                if (m0 >= 0 && (pk[m0] & 0xff) == my_last) m0 = kNone;
+                if (m0 > m1) { tmp = m0; m0 = m1; m1 = tmp; }
+                if (m1 > m2) { tmp = m1; m1 = m2; m2 = tmp; }
+                if (m0 > m1) { tmp = m0; m0 = m1; m1 = tmp; }
+                float acc = comb<DOMAIN>(sc[m0 >= 0 ? m0 : (m1 >= 0 ? m1 : m2)], lpv);
+                if (m0 >= 0) acc = mrg<DOMAIN>(acc, comb<DOMAIN>(sc[m1], lpv));
+                if (m1 >= 0) acc = mrg<DOMAIN>(acc, comb<DOMAIN>(sc[m2], lpv));
+                if (last_frame) {
+                    int b0 = r, b1 = my_tw;
+                    if (b1 >= 0 && b1 < b0) { b0 = my_tw; b1 = r; }
+                    acc = mrg<DOMAIN>(acc, comb<DOMAIN>(sc[b0], lpb));
+                    if (b1 >= 0) acc = mrg<DOMAIN>(acc, comb<DOMAIN>(sc[b1], lpb));
+                }
+                cb.stay[r] = acc;
+            }
+            if (lane == 0) cb.ns = 0;
+        } else if (w == 1) {
+            const unsigned mine = active ? f2ord(lp) : 0u;
+            int lr = 0;
+#pragma unroll
+            for (int u = 0; u < 32; u++) {
+                const unsigned x = __shfl_sync(FULL, mine, u);
+                lr += (x > mine || (x == mine && u < lane)) ? 1 : 0;
+            }
+            cb.order[lr] = lane;
+            cb.rankc[lane] = 0; cb.rankc[lane + 32] = 0;
+        } else if (pending) {
+            // prefix relations of the current beam from the previous beam (buffers cur ^ 1) and last frame's choices
+            const int old = cur ^ 1;
+            for (int e = tid - 64; e < BMAX * BMAX; e += 64) {
+                const int r = e / BMAX, q = e % BMAX;
+                if (r >= k || q >= k) continue;
+                const int ar = cb.seli[r], aq = cb.seli[q];
+                const int er = cand_ext_id(cb.selv[r], blank, cb.pk[old][ar]);
+                const int eq2 = cand_ext_id(cb.selv[q], blank, cb.pk[old][aq]);
+                cb.rel[cur][r][q] = (unsigned char)rel_child(cb.rel[old][ar][aq], er, eq2, cb.depth[old][ar], cb.depth[old][aq],
+                                                             cb.node[old][ar], cb.node[old][aq], vch, parent, meta);
+            }
+        }
+        __syncthreads();
+
+        // ================= phase B: merged candidates =================
+        if (!last_frame) {
+            for (int i = w; i < k; i += 4) {
+                const int4 pi = cb.pinfo[i];
+                const int pki = pi.z & 0x1ff, twi = ((pi.z >> 9) & 0x3f) - 1;
+                const int ebi = (pki >> 8) & 1, lasti = pki & 0xff;
+                const float s = comb<DOMAIN>(__int_as_float(pi.x), lp);
+                const bool is_stay = (ebi == 0 && lane == lasti);
+                const bool is_blank = (lane == blank);
+                const bool member = twi >= 0 && (is_blank || ebi == 0 || lane != lasti);
+                const bool dead = (member && twi < i) || (!is_blank && (((unsigned)pi.w >> lane) & 1u));
+                float acc = s;
+                if (twi > i) {   // uniform per warp: this parent hosts the twin pair
+                    const float mm = mrg_bf<DOMAIN>(s, comb<DOMAIN>(__int_as_float(pi.y), lp));
+                    acc = member ? mm : s;
+                }
+                const float sv = cb.stay[i];
+                acc = is_stay ? sv : acc;
+                cb.cand[i][lane] = (active && (is_stay || !dead)) ? f2ord(acc) : 0u;
+            }
+        } else if (w == 0) {
+            for (int i = 0; i < k; i++) {
+                const int pki = pk[i], twi = cb.tw[i];
+                const int ebi = (pki >> 8) & 1, lasti = pki & 0xff;
+                const float s = comb<DOMAIN>(sc[i], lp);
+                float acc = s;
+                bool dead = false;
+                const bool is_stay = (ebi == 0 && lane == lasti);
+                const bool is_blank = (lane == blank);
+                const bool member = twi >= 0 && (is_blank || ebi == 0 || lane != lasti);
+                if (!is_blank) {
+                    if (twi >= 0) {
+                        if (twi < i) dead = member;
+                        else {
+                            const float mm = mrg<DOMAIN>(s, comb<DOMAIN>(sc[twi], lp));
+                            acc = member ? mm : s;
+                        }
+                    }
+                    if ((cb.abs0[i] >> lane) & 1u) dead = true;
+                    if (!dead && !is_stay && ((cb.abs1[i] >> lane) & 1u)) {
+                        // kept (X.v, 1): on the last frame its blank candidate strips to X.v as well
+                        const int nd = node[i];
+                        for (int j = 0; j < k; j++)
+                            if (pnode[j] == nd && (pk[j] & 0xff) == lane && ((pk[j] >> 8) & 1))
+                                acc = mrg<DOMAIN>(acc, comb<DOMAIN>(sc[j], lpb));
+                    }
+                } else {
+                    if (ebi == 0 || twi >= 0) dead = true;
+                    else if (lasti != 0xff) {
+                        const int q0 = cb.p0[i], q1 = cb.p1[i];
+                        if (q1 >= 0 || (q0 >= 0 && (pk[q0] & 0xff) != lasti)) dead = true;
+                    }
+                }
+                if (is_stay) { acc = cb.stay[i]; dead = false; }
+                cb.cand[i][lane] = (active && !dead) ? f2ord(acc) : 0u;
+            }
+        }
+        __syncthreads();
+
+        // ================= phase C: lower bound of the beam-th largest merged key =================
+        if (w < 2) {
+            const int ci0 = p.cell_i[lane], ci1 = p.cell_i[lane + 32];
+            const unsigned k0 = ci0 < k ? cb.cand[ci0][cb.order[p.cell_j[lane]]] : 0u;
+            const unsigned k1 = ci1 < k ? cb.cand[ci1][cb.order[p.cell_j[lane + 32]]] : 0u;
+            const unsigned mine = w == 0 ? k0 : k1;
+            int cnt = 0;
+#pragma unroll
+            for (int u = 0; u < 32; u++) {
+                const unsigned x0 = __shfl_sync(FULL, k0, u), x1 = __shfl_sync(FULL, k1, u);
+                if (w == 0) { cnt += (x0 > mine || (x0 == mine && u < lane)) ? 1 : 0; cnt += (x1 > mine) ? 1 : 0; }
+                else { cnt += (x0 >= mine) ? 1 : 0; cnt += (x1 > mine || (x1 == mine && u < lane)) ? 1 : 0; }
+            }
+            const unsigned th = __reduce_max_sync(FULL, cnt == B - 1 ? mine : 0u);
+            if (lane == 0) cb.theta_part[w] = th;
+        } else if (w == 2) {
+            unsigned mn = 0u;
+            if (B <= V) mn = __reduce_min_sync(FULL, lane < B ? cb.cand[0][cb.order[lane]] : 0xffffffffu);
+            if (lane == 0) cb.theta_part[2] = mn;
+        }
+        __syncthreads();
+        const unsigned theta = max(max(cb.theta_part[0], cb.theta_part[1]), cb.theta_part[2]);
+
+        // ================= phase D: survivors =================
+        for (int i = w; i < k; i += 4) {
+            const unsigned key = cb.cand[i][lane];
+            const bool sv = key != 0u && key >= theta;
+            const unsigned mask = __ballot_sync(FULL, sv);
+            int base = 0;
+            if (lane == 0 && mask) base = atomicAdd(&cb.ns, __popc(mask));
+            base = __shfl_sync(FULL, base, 0);
+            const int pos = base + __popc(mask & ((1u << lane) - 1u));
+            if (sv && pos < 64) { cb.surv_key[pos] = key; cb.surv_iv[pos] = (i << 8) | lane; }
+        }
+        __syncthreads();
+        const int ns = cb.ns;
+        if (tid == 0) { stat_surv += ns; stat_fallback += ns > 64; }
+
+        // ================= phase E: exact order of the survivors =================
+        int m = 0;
+        if (ns <= 64) {
+            m = ns < B ? ns : B;
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int sidx = lane + 32 * q;
+                if (sidx < ns) {
+                    const unsigned key = cb.surv_key[sidx];
+                    const int iv = cb.surv_iv[sidx];
+                    const int mi = iv >> 8, mv = iv & 0xff;
+                    const int ms = cand_suffix_id(mv, blank, pk[mi]);
+                    int rank = 0;
+                    for (int o = w; o < ns; o += 4) {
+                        const unsigned ok = cb.surv_key[o];
+                        if (ok > key) rank++;
+                        else if (ok == key && o != sidx) {
+                            const int oiv = cb.surv_iv[o];
+                            if (t == 0) rank += oiv < iv;
+                            else {
+                                const int oi = oiv >> 8, ov = oiv & 0xff;
+                                rank += cand_less_rel(rel[oi][mi], cand_suffix_id(ov, blank, pk[oi]), ms, vch) ? 1 : 0;
+                            }
+                        }
+                    }
+                    if (rank) atomicAdd(&cb.rankc[sidx], rank);
+                }
+            }
+            __syncthreads();
+            if (w == 0) {
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const int sidx = lane + 32 * q;
+                    if (sidx < ns) {
+                        const int rank = cb.rankc[sidx];
+                        if (rank < B) {
+                            const int iv = cb.surv_iv[sidx];
+                            cb.selkey[rank] = cb.surv_key[sidx]; cb.seli[rank] = iv >> 8; cb.selv[rank] = iv & 0xff;
+                        }
+                    }
+                }
+            }
+        } else {
+            // more than 64 survivors (loose bound): beam rounds of warp-max extraction on warp 0
+            if (w == 0) {
+                unsigned lmax = 0u;
+                for (int i = 0; i < k; i++) lmax = max(lmax, cb.cand[i][lane]);
+                for (m = 0; m < B; m++) {
+                    const unsigned gmax = __reduce_max_sync(FULL, lmax);
+                    if (gmax == 0u) break;
+                    const unsigned any = __ballot_sync(FULL, lmax == gmax);
+                    int wl = __ffs(any) - 1;
+                    unsigned x = lane < k ? cb.cand[lane][wl] : 0u;
+                    const unsigned colmask = __ballot_sync(FULL, x == gmax);
+                    int wi = __ffs(colmask) - 1;
+                    if (t > 0 && (__popc(any) > 1 || __popc(colmask) > 1)) {
+                        int bi = -1, bs = 0;
+                        if (lmax == gmax) {
+                            for (int i = 0; i < k; i++) {
+                                if (cb.cand[i][lane] != gmax) continue;
+                                const int si = cand_suffix_id(lane, blank, pk[i]);
+                                if (bi < 0 || cand_less_rel(rel[i][bi], si, bs, vch)) { bi = i; bs = si; }
+                            }
+                        }
+                        int bl = lane;
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) {
+                            const int oi = __shfl_xor_sync(FULL, bi, off), os = __shfl_xor_sync(FULL, bs, off);
+                            const int ol = __shfl_xor_sync(FULL, bl, off);
+                            if (oi >= 0 && (bi < 0 || cand_less_rel(rel[oi][bi], os, bs, vch))) { bi = oi; bs = os; bl = ol; }
+                        }
+                        wi = bi; wl = bl;
+                        x = lane < k ? cb.cand[lane][wl] : 0u;
+                    }
+                    if (lane == wi) { cb.cand[wi][wl] = 0u; x = 0u; }
+                    const unsigned cmax = __reduce_max_sync(FULL, x);
+                    if (lane == wl) lmax = cmax;
+                    if (lane == 0) { cb.selkey[m] = gmax; cb.seli[m] = wi; cb.selv[m] = wl; }
+                    __syncwarp();
+                }
+                if (lane == 0) cb.sel_m = m;
+            }
+            __syncthreads();
+            m = cb.sel_m;
+        }
+        __syncthreads();
+
+        // ================= phase F: the selected candidates become the next kept states =================
+        const int nxt = cur ^ 1;
+        if (w == 0) {
+            bool need_new = false;
+            int i = 0, v = 0, nd = 0, pn = 0, dp = 0, npk = 0;
+            if (lane < m) {
+                i = cb.seli[lane]; v = cb.selv[lane];
+                const int pki = pk[i];
+                const int ebi = (pki >> 8) & 1, lasti = pki & 0xff;
+                if (v == blank) { nd = node[i]; pn = pnode[i]; dp = depth[i]; npk = lasti | (1 << 8); }
+                else if (ebi == 0 && v == lasti) { nd = node[i]; pn = pnode[i]; dp = depth[i]; npk = lasti; }
+                else {
+                    pn = node[i]; dp = depth[i] + 1; npk = v;
+                    nd = child[(size_t)pn * Vp + v];
+                    need_new = nd == 0;
+                }
+            }
+            const unsigned nb = __ballot_sync(FULL, need_new);
+            const int nodes = cb.nodes;
+            if (need_new) {
+                nd = nodes + __popc(nb & ((1u << lane) - 1u));
+                parent[nd] = pn;
+                meta[nd] = (dp << 8) | v;
+                child[(size_t)pn * Vp + v] = nd;
+                int4 *row = reinterpret_cast<int4 *>(child + (size_t)nd * Vp);
+                for (int q = 0; q < Vp / 4; q++) row[q] = make_int4(0, 0, 0, 0);
+            }
+            if (lane < m) {
+                cb.sc[nxt][lane] = ord2f(cb.selkey[lane]);
+                cb.node[nxt][lane] = nd; cb.pnode[nxt][lane] = pn; cb.depth[nxt][lane] = dp; cb.pk[nxt][lane] = npk;
+            }
+            __syncwarp();
+            if (lane == 0) { cb.nodes = nodes + __popc(nb); cb.kept = m; }
+        }
+        __syncthreads();
+        kept = m;
+        cur = nxt;
+        pending = true;
+    }
+
+    // the prefix relations of the final beam of this launch (a later chunk's tie-breaks need them)
+    if (pending && p.t1 < p.T) {
+        const int old = cur ^ 1, k = kept;
+        for (int e = tid; e < BMAX * BMAX; e += 128) {
+            const int r = e / BMAX, q = e % BMAX;
+            if (r >= k || q >= k) continue;
+            const int ar = cb.seli[r], aq = cb.seli[q];
+            const int er = cand_ext_id(cb.selv[r], blank, cb.pk[old][ar]);
+            const int eq2 = cand_ext_id(cb.selv[q], blank, cb.pk[old][aq]);
+            cb.rel[cur][r][q] = (unsigned char)rel_child(cb.rel[old][ar][aq], er, eq2, cb.depth[old][ar], cb.depth[old][aq],
+                                                         cb.node[old][ar], cb.node[old][aq], vch, parent, meta);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (p.t0 == 0) { p.out_stats[2 * utt] = stat_fallback; p.out_stats[2 * utt + 1] = stat_surv; }
+        else { p.out_stats[2 * utt] += stat_fallback; p.out_stats[2 * utt + 1] += stat_surv; }
+    }
+    if (p.t1 < p.T) {
+        const int4 *src = reinterpret_cast<const int4 *>(&cb);
+        for (int i = tid; i < kStateVec; i += 128) gstate[i] = src[i];
+        if (tid == 0) gstate[kStateVec] = make_int4(cur, 0, 0, 0);
+        return;
+    }
+    // ---- result (CTCBeamSearch.cu:290-298) ----
+    if (tid == 0 && p.out_counts) p.out_counts[utt] = kept;
+    for (int r = tid; r < p.nbest; r += 128) {
+        char *out = p.out_paths + ((size_t)utt * p.nbest + r) * p.max_len;
+        int len = 0;
+        float scv = 0.0f;
+        if (r < kept) {
+            int nd = cb.node[cur][r];
+            const int dpt = cb.depth[cur][r];
+            len = dpt;
+            if (p.T == 1 && ((cb.pk[cur][r] >> 8) & 1)) { if (len < p.max_len) out[len] = vch[blank]; len += 1; }
+            for (int pos = dpt - 1; pos >= 0; pos--) {
+                if (pos < p.max_len) out[pos] = vch[meta[nd] & 0xff];
+                nd = parent[nd];
+            }
+            scv = cb.sc[cur][r];
+        }
+        p.out_lens[(size_t)utt * p.nbest + r] = len;
+        p.out_scores[(size_t)utt * p.nbest + r] = scv;
+    }
+}
+
 static size_t ctc_smem_bytes(int B, int V, int Vp, int n_pad) {
     size_t s = sizeof(unsigned long long) * n_pad + sizeof(float) * Vp;
     s += (sizeof(float) + 2 * sizeof(int)) * 2 * B;   // score, node, pnode (x2 buffers)
@@ -977,7 +1438,7 @@ static int ctc_layout(const CtcArgs &a, CtcLayout &L) {
     L.off_parent = o; o = align_up(o + sizeof(int) * (size_t)a.N * L.cap, 256);
     L.off_meta = o; o = align_up(o + sizeof(int) * (size_t)a.N * L.cap, 256);
     L.off_child = o; o = align_up(o + sizeof(int) * (size_t)a.N * L.cap * L.Vp, 256);
-    L.state_stride = align_up(sizeof(WarpBeam<32>) + sizeof(int4), 256);
+    L.state_stride = align_up((sizeof(CtaBeam<32>) > sizeof(WarpBeam<32>) ? sizeof(CtaBeam<32>) : sizeof(WarpBeam<32>)) + sizeof(int4), 256);
     L.off_state = o; o = align_up(o + L.state_stride * (size_t)a.N, 256);
     L.total = o;
     size_t q = 0;
@@ -1052,7 +1513,19 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
     }
 
     if (t1 == a.T) GASR_CUDA(cudaMemsetAsync(wo + L.off_paths, 0, (size_t)a.N * a.nbest * a.max_len, st));
-    if (fast) {
+    const char *force_k = getenv("GASR_CTC_KERNEL");
+    const bool use_cta = fast && (force_k ? force_k[0] == 'c' : a.N <= 2 * ctx->sm_count);
+    if (use_cta) {
+        // latency path: a 128-thread CTA per utterance (state parked per utterance needs sizeof(CtaBeam) <= stride)
+        // 20 KB of (unused) dynamic shared memory keeps these CTAs off the SMs whose shared memory is filled by a
+        // recurrence CTA (208 KB) when the pipeline runs both at once
+        const size_t pad = 20480;
+        if (a.domain == GASR_DOMAIN_LOG) {
+            if (a.beam <= 16) ctc_beam_cta_kernel<1, 16><<<a.N, 128, pad, st>>>(p); else ctc_beam_cta_kernel<1, 32><<<a.N, 128, pad, st>>>(p);
+        } else {
+            if (a.beam <= 16) ctc_beam_cta_kernel<0, 16><<<a.N, 128, pad, st>>>(p); else ctc_beam_cta_kernel<0, 32><<<a.N, 128, pad, st>>>(p);
+        }
+    } else if (fast) {
         // warp-per-utterance fast path; few warps per CTA when utterances are scarce (latency), 8 when plentiful
         int W = ceil_div(a.N, ctx->sm_count);
         if (W > 8) W = 8;
