@@ -8,7 +8,7 @@
 // rnn_tanh_cluster_kernel: one thread-block cluster (CS = H/64 CTAs, <= 8) per group of 16 utterances.  CTA c
 // keeps the 64-column slice W_hh[:, 64c:64c+64] resident in shared memory for the whole sequence (128 KB at
 // H = 512) plus a double-buffered copy of the group's full h (16 x H fp32).  Per step each CTA computes its
-// [16 x 64] slice (4-way split-K over warps, 4x4 register tiles, operands read as 128-bit shared loads),
+// [16 x 64] slice (8-way split-K over 16 warps, 4x4 register tiles, operands read as 128-bit shared loads),
 // reduces the partials, adds xproj (prefetched one step ahead), applies tanh, stores h_t to HBM and broadcasts
 // its slice into every CTA's shared memory through DSMEM; one cluster barrier per step.  Per step a CTA touches
 // HBM only for its xproj slice and its output slice.
@@ -17,6 +17,7 @@
 // with W_hh streamed from L2.
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -94,7 +95,8 @@ __global__ void gru_step_kernel(const float *__restrict__ xp, int ldxp, const fl
 // ---- persistent cluster kernel (tanh) ------------------------------------------------------------------------
 constexpr int RC_NB = 16;     // utterances per cluster
 constexpr int RC_HC = 64;     // hidden columns per CTA
-constexpr int RC_THREADS = 256;
+constexpr int RC_THREADS = 512;   // 16 warps: 8-way split-K x 2 column halves (4 warps per scheduler hide the LDS latency)
+constexpr int RC_KSPLIT = 8;
 
 struct RnnClusterParams {
     const float *xproj; int ldxp;
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rnn_tanh_cluster_kernel(const R
     const int HS = H + 4;                          // padded h row (keeps 128-bit loads of 4 rows conflict-free)
     float *Ws = smem;                              // [H][64]
     float *hbuf = Ws + (size_t)H * RC_HC;          // [2][16][HS]
-    float *red = hbuf + 2 * RC_NB * HS;            // [4][16][64]
+    float *red = hbuf + 2 * RC_NB * HS;            // [RC_KSPLIT][16][64]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rank = (int)cluster.block_rank();
     const int group = blockIdx.x / CS;
@@ -142,14 +144,15 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rnn_tanh_cluster_kernel(const R
     }
 
     // compute-phase mapping: warp -> (K quarter, column half); lane -> (utterance set, 4-column group)
-    const int kq = warp & 3, ch = warp >> 2;
+    const int kq = warp & (RC_KSPLIT - 1), ch = warp / RC_KSPLIT;
     const int cgp = lane & 7, ug = lane >> 3;      // utterances ug, ug+4, ug+8, ug+12
-    const int kbeg = kq * (H / 4), kend = kbeg + H / 4;
+    const int kbeg = kq * (H / RC_KSPLIT), kend = kbeg + H / RC_KSPLIT;
     const float *wcol = Ws + ch * 32 + cgp * 4;
     // epilogue mapping: thread -> (utterance, 4 columns)
-    const int eu = tid >> 4, ec = (tid & 15) * 4;
+    const bool epi = tid < 256;                    // the first 8 warps also run the epilogue (one float4 each)
+    const int eu = (tid & 255) >> 4, ec = (tid & 15) * 4;
     const int en = n0 + eu;
-    const bool evalid = en < p.N;
+    const bool evalid = epi && en < p.N;
 
     float4 xnext = make_float4(0.f, 0.f, 0.f, 0.f);
     {
@@ -200,13 +203,15 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rnn_tanh_cluster_kernel(const R
         __syncthreads();
         // ---- reduce the 4 K quarters, add xproj, tanh, publish --------------------------------------------
         float4 v = xcur;
+        if (epi) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const float4 r = *reinterpret_cast<const float4 *>(red + ((size_t)q * RC_NB + eu) * RC_HC + ec);
-            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+            for (int q = 0; q < RC_KSPLIT; q++) {
+                const float4 r = *reinterpret_cast<const float4 *>(red + ((size_t)q * RC_NB + eu) * RC_HC + ec);
+                v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+            }
+            v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w);
         }
-        v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w);
-        if (s + 1 < p.s1) {
+        if (epi && s + 1 < p.s1) {
             // broadcast this CTA's slice of h_t into every CTA's next-step buffer (DSMEM)
             float *dst_local = hn + (size_t)eu * HS + colbase + ec;
             for (int r = 0; r < CS; r++) {
@@ -218,6 +223,160 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rnn_tanh_cluster_kernel(const R
         if (evalid) *reinterpret_cast<float4 *>(p.out + ((size_t)t * p.N + en) * p.ldo + p.col0 + colbase + ec) = v;
         cluster_wait();
     }
+}
+
+// ---- persistent cluster kernel, tensor-core variant (default) ---------------------------------------------------
+// Same decomposition (cluster of H/64 CTAs per 16 utterances, one cluster barrier per step), but the weights never
+// touch shared memory: every warp keeps its 8-column slice of W_hh for ALL k as bf16 hi/lo MMA B-fragments in
+// registers (128 registers at H = 512), h lives in shared memory as bf16 hi/lo planes and is read with ldmatrix, and
+// the step is 3 x H/16 mma.sync.m16n8k16 (hi*hi + hi*lo + lo*hi, fp32 accumulate: fp32-grade, like the projection).
+// Shared memory traffic per step drops from W + h fragments (broadcast loads, ~6k wavefronts) to h only (2k).
+#include <cuda_bf16.h>
+
+constexpr int RM_THREADS = 256;
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_pair(float x, float y, uint32_t &hi, uint32_t &lo) {
+    const __nv_bfloat16 xh = __float2bfloat16_rn(x), yh = __float2bfloat16_rn(y);
+    const __nv_bfloat162 h2 = __halves2bfloat162(xh, yh);
+    const __nv_bfloat162 l2 = __halves2bfloat162(__float2bfloat16_rn(x - __bfloat162float(xh)),
+                                                 __float2bfloat16_rn(y - __bfloat162float(yh)));
+    hi = *reinterpret_cast<const uint32_t *>(&h2);
+    lo = *reinterpret_cast<const uint32_t *>(&l2);
+}
+
+template <int H>
+__global__ void __launch_bounds__(RM_THREADS, 1) rnn_tanh_mma_kernel(const RnnClusterParams p) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    cg::cluster_group cluster = cg::this_cluster();
+    constexpr int KS = H / 16;                       // k-steps of the m16n8k16 MMA
+    constexpr int HSB = H * 2 + 16;                  // bytes of one bf16 h row (+16: ldmatrix rows hit distinct banks)
+    constexpr int PLANE = RC_NB * HSB;               // one plane (hi or lo) of one buffer
+    // layout: [buf 0/1][plane hi/lo][16 rows][HSB] | staging [plane][16 rows][128 B]
+    unsigned char *hbuf = smraw;
+    uint32_t *stage = reinterpret_cast<uint32_t *>(smraw + 4 * PLANE);
+    const int CS = p.CS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tg = lane & 3;
+    const int rank = (int)cluster.block_rank();
+    const int group = blockIdx.x / CS;
+    const int n0 = group * RC_NB;
+    const int colbase = rank * RC_HC;
+
+    // ---- resident weights: B fragments of W_hh[:, colbase + 8*warp + g] for every k-step, bf16 hi and lo ----------
+    uint32_t bhi[KS][2], blo[KS][2];
+    {
+        const float *wc = p.w_hh + colbase + 8 * warp + g;
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) {
+            const int k = 16 * ks + 2 * tg;
+            split_pair(__ldg(wc + (size_t)k * H), __ldg(wc + (size_t)(k + 1) * H), bhi[ks][0], blo[ks][0]);
+            split_pair(__ldg(wc + (size_t)(k + 8) * H), __ldg(wc + (size_t)(k + 9) * H), bhi[ks][1], blo[ks][1]);
+        }
+    }
+    // ---- h before the first step: zeros (h_0 = 0, RNN.h:16-17) or the previous chunk's last output row ------------
+    for (int i = tid; i < 4 * PLANE / 4; i += RM_THREADS) reinterpret_cast<uint32_t *>(hbuf)[i] = 0u;
+    if (p.s0 > 0) {
+        __syncthreads();
+        const int tp = p.reverse ? p.T - p.s0 : p.s0 - 1;
+        unsigned char *b0 = hbuf + (size_t)(p.s0 & 1) * 2 * PLANE;
+        for (int i = tid; i < RC_NB * (H / 2); i += RM_THREADS) {
+            const int u = i / (H / 2), c = (i % (H / 2)) * 2;
+            if (n0 + u < p.N) {
+                const float2 v = *reinterpret_cast<const float2 *>(p.out + ((size_t)tp * p.N + n0 + u) * p.ldo + p.col0 + c);
+                uint32_t hi, lo;
+                split_pair(v.x, v.y, hi, lo);
+                *reinterpret_cast<uint32_t *>(b0 + (size_t)u * HSB + c * 2) = hi;
+                *reinterpret_cast<uint32_t *>(b0 + PLANE + (size_t)u * HSB + c * 2) = lo;
+            }
+        }
+    }
+    // ---- per-lane roles --------------------------------------------------------------------------------------------
+    // ldmatrix: lanes 0-7 rows 0-7 k+0 | 8-15 rows 8-15 k+0 | 16-23 rows 0-7 k+8 | 24-31 rows 8-15 k+8  (A fragment order)
+    const uint32_t lm_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * HSB + ((lane >> 4) & 1) * 16);
+    const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(hbuf);
+    // accumulator fragment: rows g and g+8 (utterances), columns 8*warp + 2*tg + {0,1}
+    const int ecol = 8 * warp + 2 * tg;
+    const int u0 = n0 + g, u1 = n0 + g + 8;
+    const bool v0 = u0 < p.N, v1 = u1 < p.N;
+    float2 xn0 = make_float2(0.f, 0.f), xn1 = make_float2(0.f, 0.f);
+    {
+        const int t0 = p.reverse ? p.T - 1 - p.s0 : p.s0;
+        if (v0) xn0 = __ldg(reinterpret_cast<const float2 *>(p.xproj + ((size_t)t0 * p.N + u0) * p.ldxp + colbase + ecol));
+        if (v1) xn1 = __ldg(reinterpret_cast<const float2 *>(p.xproj + ((size_t)t0 * p.N + u1) * p.ldxp + colbase + ecol));
+    }
+    cluster.sync();
+
+    for (int s = p.s0; s < p.s1; s++) {
+        const int t = p.reverse ? p.T - 1 - s : s;
+        const uint32_t cur = hbase + (uint32_t)((s & 1) * 2 * PLANE) + lm_off;
+        unsigned char *nxt = hbuf + (size_t)((s & 1) ^ 1) * 2 * PLANE;
+        const float2 xc0 = xn0, xc1 = xn1;
+        if (s + 1 < p.s1) {
+            const int tn = p.reverse ? t - 1 : t + 1;
+            if (v0) xn0 = __ldg(reinterpret_cast<const float2 *>(p.xproj + ((size_t)tn * p.N + u0) * p.ldxp + colbase + ecol));
+            if (v1) xn1 = __ldg(reinterpret_cast<const float2 *>(p.xproj + ((size_t)tn * p.N + u1) * p.ldxp + colbase + ecol));
+        }
+        // ---- h_{t-1} * W_hh slice: three independent accumulator chains (one per split term) ----------------------
+        float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) {
+            uint32_t ah[4], al[4];
+            ldmatrix_x4(ah, cur + ks * 32);
+            ldmatrix_x4(al, cur + PLANE + ks * 32);
+            mma_bf16_16816(c0, ah, bhi[ks][0], bhi[ks][1]);
+            mma_bf16_16816(c1, ah, blo[ks][0], blo[ks][1]);
+            mma_bf16_16816(c2, al, bhi[ks][0], bhi[ks][1]);
+        }
+        // ---- + xproj, tanh, publish --------------------------------------------------------------------------------
+        float2 r0, r1;
+        r0.x = tanhf(xc0.x + (c0[0] + (c1[0] + c2[0]))); r0.y = tanhf(xc0.y + (c0[1] + (c1[1] + c2[1])));
+        r1.x = tanhf(xc1.x + (c0[2] + (c1[2] + c2[2]))); r1.y = tanhf(xc1.y + (c0[3] + (c1[3] + c2[3])));
+        if (s + 1 < p.s1) {
+            uint32_t hi, lo;
+            split_pair(r0.x, r0.y, hi, lo);
+            stage[g * 32 + 4 * warp + tg] = hi; stage[512 + g * 32 + 4 * warp + tg] = lo;
+            split_pair(r1.x, r1.y, hi, lo);
+            stage[(g + 8) * 32 + 4 * warp + tg] = hi; stage[512 + (g + 8) * 32 + 4 * warp + tg] = lo;
+        }
+        __syncthreads();
+        if (s + 1 < p.s1) {
+            // 4 KB slice (2 planes x 16 rows x 128 B) -> every CTA's next-step buffer: one 16-byte chunk per thread
+            const int pl = tid >> 7, row = (tid >> 3) & 15, c16 = tid & 7;
+            const int4 chunk = reinterpret_cast<const int4 *>(stage)[tid];
+            unsigned char *dst_local = nxt + (size_t)pl * PLANE + (size_t)row * HSB + colbase * 2 + c16 * 16;
+            for (int r = 0; r < CS; r++) *reinterpret_cast<int4 *>(cluster.map_shared_rank(dst_local, r)) = chunk;
+        }
+        cluster_arrive();
+        if (v0) *reinterpret_cast<float2 *>(p.out + ((size_t)t * p.N + u0) * p.ldo + p.col0 + colbase + ecol) = r0;
+        if (v1) *reinterpret_cast<float2 *>(p.out + ((size_t)t * p.N + u1) * p.ldo + p.col0 + colbase + ecol) = r1;
+        cluster_wait();
+    }
+}
+
+template <int H>
+static int launch_rnn_mma(const RnnClusterParams &p, int groups, cudaStream_t st) {
+    const size_t smem = 4 * (size_t)RC_NB * (H * 2 + 16) + 4096;
+    GASR_CUDA(cudaFuncSetAttribute(rnn_tanh_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(groups * p.CS);
+    cfg.blockDim = dim3(RM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    GASR_CUDA(cudaLaunchKernelEx(&cfg, rnn_tanh_mma_kernel<H>, p));
+    return GASR_OK;
 }
 
 static bool cluster_kernel_supported(const gasr_ctx *ctx, const RnnLayerArgs &a) {
@@ -232,7 +391,7 @@ static bool cluster_kernel_supported(const gasr_ctx *ctx, const RnnLayerArgs &a)
 }
 
 static size_t cluster_smem_bytes(int H) {
-    return sizeof(float) * ((size_t)H * RC_HC + 2 * RC_NB * (H + 4) + 4 * RC_NB * RC_HC);
+    return sizeof(float) * ((size_t)H * RC_HC + 2 * RC_NB * (H + 4) + RC_KSPLIT * RC_NB * RC_HC);
 }
 
 int launch_rnn_recurrence(gasr_ctx *ctx, const RnnLayerArgs &a, cudaStream_t st) {
@@ -246,6 +405,16 @@ int launch_rnn_recurrence(gasr_ctx *ctx, const RnnLayerArgs &a, cudaStream_t st)
         p.T = a.T; p.N = a.N; p.H = a.H; p.CS = a.H / RC_HC; p.reverse = a.reverse;
         p.s0 = a.s0; p.s1 = a.s1 > 0 ? a.s1 : a.T;
         const int groups = ceil_div(a.N, RC_NB);
+        const char *force = getenv("GASR_RNN");
+        if (!(force && force[0] == 'f') && a.ldxp % 2 == 0 && a.ldo % 2 == 0) {
+            int rc = GASR_OK;
+            if (a.H == 512) rc = launch_rnn_mma<512>(p, groups, st);
+            else if (a.H == 256) rc = launch_rnn_mma<256>(p, groups, st);
+            else if (a.H == 128) rc = launch_rnn_mma<128>(p, groups, st);
+            else rc = launch_rnn_mma<64>(p, groups, st);
+            if (rc == GASR_OK) ctx->launches += 1;
+            return rc;
+        }
         const size_t smem = cluster_smem_bytes(a.H);
         GASR_CUDA(cudaFuncSetAttribute(rnn_tanh_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaLaunchConfig_t cfg = {};
