@@ -118,7 +118,7 @@ struct CtcParams {
     float *out_scores;   // [N, nbest]
     int *out_counts;     // [N]
     int *out_stats;      // [N, 2]: frames that took the prune fallback, sum of prune survivors (diagnostics)
-    unsigned char cell_i[64], cell_j[64];   // prune lower-bound probe cells (parent rank, log-prob rank); warp kernel
+    unsigned char cell_i[128], cell_j[128]; // prune lower-bound probe cells (parent rank, score rank), by rising (i+1)(j+1)
     int n_cells;         // 32 (one per lane) or 64
     int t0, t1;          // frames [t0, t1) are decoded by this launch (time chunking; warp kernel only)
     unsigned char *state;   // [N, state_stride] saved beam state between chunk launches
@@ -976,7 +976,8 @@ struct CtaBeam {
     unsigned surv_key[64];
     int surv_iv[64];
     int rankc[64];
-    unsigned theta_part[4];
+    unsigned ckey[128];
+    unsigned theta;
     int ns, kept, nodes, sel_m;
 };
 
@@ -1027,7 +1028,6 @@ __global__ void __launch_bounds__(128) ctc_beam_cta_kernel(const CtcParams p) {
     if (tid < V) vch_s[tid] = p.vocab[tid];
     int cur = 0;
     int stat_surv = 0, stat_fallback = 0;
-    bool pending = false;      // the prefix relations of the current beam still have to be derived (phase A)
     if (p.t0 == 0) {
         if (tid < Vp) child[tid] = 0;
         if (tid == 0) {
@@ -1109,29 +1109,19 @@ __global__ void __launch_bounds__(128) ctc_beam_cta_kernel(const CtcParams p) {
                 }
                 cb.stay[r] = acc;
             }
-            if (lane == 0) cb.ns = 0;
+            if (lane == 0) { cb.ns = 0; cb.theta = 0u; }
         } else if (w == 1) {
-            const unsigned mine = active ? f2ord(lp) : 0u;
-            int lr = 0;
+            if (t == p.t0) {   // later frames: ranked at the end of the previous frame, in the shadow of phase F
+                const unsigned mine = active ? f2ord(lp) : 0u;
+                int lr = 0;
 #pragma unroll
-            for (int u = 0; u < 32; u++) {
-                const unsigned x = __shfl_sync(FULL, mine, u);
-                lr += (x > mine || (x == mine && u < lane)) ? 1 : 0;
+                for (int u = 0; u < 32; u++) {
+                    const unsigned x = __shfl_sync(FULL, mine, u);
+                    lr += (x > mine || (x == mine && u < lane)) ? 1 : 0;
+                }
+                cb.order[lr] = lane;
             }
-            cb.order[lr] = lane;
             cb.rankc[lane] = 0; cb.rankc[lane + 32] = 0;
-        } else if (pending) {
-            // prefix relations of the current beam from the previous beam (buffers cur ^ 1) and last frame's choices
-            const int old = cur ^ 1;
-            for (int e = tid - 64; e < BMAX * BMAX; e += 64) {
-                const int r = e / BMAX, q = e % BMAX;
-                if (r >= k || q >= k) continue;
-                const int ar = cb.seli[r], aq = cb.seli[q];
-                const int er = cand_ext_id(cb.selv[r], blank, cb.pk[old][ar]);
-                const int eq2 = cand_ext_id(cb.selv[q], blank, cb.pk[old][aq]);
-                cb.rel[cur][r][q] = (unsigned char)rel_child(cb.rel[old][ar][aq], er, eq2, cb.depth[old][ar], cb.depth[old][aq],
-                                                             cb.node[old][ar], cb.node[old][aq], vch, parent, meta);
-            }
         }
         __syncthreads();
 
@@ -1195,38 +1185,59 @@ __global__ void __launch_bounds__(128) ctc_beam_cta_kernel(const CtcParams p) {
         __syncthreads();
 
         // ================= phase C: lower bound of the beam-th largest merged key =================
-        if (w < 2) {
-            const int ci0 = p.cell_i[lane], ci1 = p.cell_i[lane + 32];
-            const unsigned k0 = ci0 < k ? cb.cand[ci0][cb.order[p.cell_j[lane]]] : 0u;
-            const unsigned k1 = ci1 < k ? cb.cand[ci1][cb.order[p.cell_j[lane + 32]]] : 0u;
-            const unsigned mine = w == 0 ? k0 : k1;
+        // probe cells -> shared memory; then every cell counts how many probe keys precede it (two threads per cell
+        // when 64 cells are probed), and the cell of rank beam-1 is the bound
+        {
+            constexpr int NC = BMAX <= 16 ? 64 : 128;
+            constexpr int TPC = 128 / NC;                     // threads per cell
+            const int c = tid / TPC;
+            const int ci = p.cell_i[c];
+            const unsigned mine = ci < k ? cb.cand[ci][cb.order[p.cell_j[c]]] : 0u;
+            if (TPC == 1 || (tid & 1) == 0) cb.ckey[c] = mine;
+            if (tid == 0 && B <= V) cb.theta = 0u;
+            __syncthreads();
+            const int span = NC / TPC, ob = (tid % TPC) * span;
             int cnt = 0;
-#pragma unroll
-            for (int u = 0; u < 32; u++) {
-                const unsigned x0 = __shfl_sync(FULL, k0, u), x1 = __shfl_sync(FULL, k1, u);
-                if (w == 0) { cnt += (x0 > mine || (x0 == mine && u < lane)) ? 1 : 0; cnt += (x1 > mine) ? 1 : 0; }
-                else { cnt += (x0 >= mine) ? 1 : 0; cnt += (x1 > mine || (x1 == mine && u < lane)) ? 1 : 0; }
+#pragma unroll 8
+            for (int o = ob; o < ob + span; o++) {
+                const unsigned x = cb.ckey[o];
+                cnt += (x > mine || (x == mine && o < c)) ? 1 : 0;
             }
-            const unsigned th = __reduce_max_sync(FULL, cnt == B - 1 ? mine : 0u);
-            if (lane == 0) cb.theta_part[w] = th;
-        } else if (w == 2) {
-            unsigned mn = 0u;
-            if (B <= V) mn = __reduce_min_sync(FULL, lane < B ? cb.cand[0][cb.order[lane]] : 0xffffffffu);
-            if (lane == 0) cb.theta_part[2] = mn;
+            if (TPC == 2) cnt += __shfl_xor_sync(FULL, cnt, 1);
+            if (cnt == B - 1 && mine != 0u && (TPC == 1 || (tid & 1) == 0)) atomicMax(&cb.theta, mine);
+            // second bound: the best parent's beam best-ranked candidates, if none of them was absorbed
+            if (w == 3 && B <= V) {
+                const unsigned mn = __reduce_min_sync(FULL, lane < B ? cb.cand[0][cb.order[lane]] : 0xffffffffu);
+                if (lane == 0 && mn != 0u) atomicMax(&cb.theta, mn);
+            }
         }
         __syncthreads();
-        const unsigned theta = max(max(cb.theta_part[0], cb.theta_part[1]), cb.theta_part[2]);
+        const unsigned theta = cb.theta;
 
         // ================= phase D: survivors =================
-        for (int i = w; i < k; i += 4) {
-            const unsigned key = cb.cand[i][lane];
-            const bool sv = key != 0u && key >= theta;
-            const unsigned mask = __ballot_sync(FULL, sv);
+        {
+            unsigned keys4[(BMAX + 3) / 4], masks4[(BMAX + 3) / 4];
+            int total = 0;
+#pragma unroll
+            for (int q = 0; q < (BMAX + 3) / 4; q++) {
+                const int i = w + 4 * q;
+                const unsigned key = i < k ? cb.cand[i][lane] : 0u;
+                const bool sv = key != 0u && key >= theta;
+                keys4[q] = key;
+                masks4[q] = __ballot_sync(FULL, sv);
+                total += __popc(masks4[q]);
+            }
             int base = 0;
-            if (lane == 0 && mask) base = atomicAdd(&cb.ns, __popc(mask));
+            if (lane == 0 && total) base = atomicAdd(&cb.ns, total);
             base = __shfl_sync(FULL, base, 0);
-            const int pos = base + __popc(mask & ((1u << lane) - 1u));
-            if (sv && pos < 64) { cb.surv_key[pos] = key; cb.surv_iv[pos] = (i << 8) | lane; }
+#pragma unroll
+            for (int q = 0; q < (BMAX + 3) / 4; q++) {
+                const int pos = base + __popc(masks4[q] & ((1u << lane) - 1u));
+                if (((masks4[q] >> lane) & 1u) && pos < 64) {
+                    cb.surv_key[pos] = keys4[q]; cb.surv_iv[pos] = ((w + 4 * q) << 8) | lane;
+                }
+                base += __popc(masks4[q]);
+            }
         }
         __syncthreads();
         const int ns = cb.ns;
@@ -1352,27 +1363,35 @@ __global__ void __launch_bounds__(128) ctc_beam_cta_kernel(const CtcParams p) {
             }
             __syncwarp();
             if (lane == 0) { cb.nodes = nodes + __popc(nb); cb.kept = m; }
+        } else if (w == 1) {
+            // rank of the NEXT frame's scores (independent of the beam)
+            if (t + 1 < p.t1) {
+                const unsigned mine = active ? f2ord(lp_next) : 0u;
+                int lr = 0;
+#pragma unroll
+                for (int u = 0; u < 32; u++) {
+                    const unsigned x = __shfl_sync(FULL, mine, u);
+                    lr += (x > mine || (x == mine && u < lane)) ? 1 : 0;
+                }
+                cb.order[lr] = lane;
+            }
+        } else {
+            // prefix relations of the new beam from the current one and this frame's choices (only tie-breaks read them)
+            for (int e = tid - 64; e < BMAX * BMAX; e += 64) {
+                const int r = e / BMAX, q = e % BMAX;
+                if (r >= m || q >= m) continue;
+                const int ar = cb.seli[r], aq = cb.seli[q];
+                const int er = cand_ext_id(cb.selv[r], blank, pk[ar]);
+                const int eq2 = cand_ext_id(cb.selv[q], blank, pk[aq]);
+                cb.rel[nxt][r][q] = (unsigned char)rel_child(rel[ar][aq], er, eq2, depth[ar], depth[aq], node[ar], node[aq], vch,
+                                                             parent, meta);
+            }
         }
         __syncthreads();
         kept = m;
         cur = nxt;
-        pending = true;
     }
 
-    // the prefix relations of the final beam of this launch (a later chunk's tie-breaks need them)
-    if (pending && p.t1 < p.T) {
-        const int old = cur ^ 1, k = kept;
-        for (int e = tid; e < BMAX * BMAX; e += 128) {
-            const int r = e / BMAX, q = e % BMAX;
-            if (r >= k || q >= k) continue;
-            const int ar = cb.seli[r], aq = cb.seli[q];
-            const int er = cand_ext_id(cb.selv[r], blank, cb.pk[old][ar]);
-            const int eq2 = cand_ext_id(cb.selv[q], blank, cb.pk[old][aq]);
-            cb.rel[cur][r][q] = (unsigned char)rel_child(cb.rel[old][ar][aq], er, eq2, cb.depth[old][ar], cb.depth[old][aq],
-                                                         cb.node[old][ar], cb.node[old][aq], vch, parent, meta);
-        }
-        __syncthreads();
-    }
     if (tid == 0) {
         if (p.t0 == 0) { p.out_stats[2 * utt] = stat_fallback; p.out_stats[2 * utt + 1] = stat_surv; }
         else { p.out_stats[2 * utt] += stat_fallback; p.out_stats[2 * utt + 1] += stat_surv; }
@@ -1498,9 +1517,11 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
     if (!fast) GASR_CUDA(cudaMemsetAsync(p.out_stats, 0, 2 * sizeof(int) * (size_t)a.N, st));
     p.t0 = t0; p.t1 = t1;
     p.state = ws + L.off_state; p.state_stride = L.state_stride;
+    const char *force_k = getenv("GASR_CTC_KERNEL");
+    const bool use_cta = fast && (force_k ? force_k[0] == 'c' : a.N <= 2 * ctx->sm_count);
     {
         // probe cells of the prune lower bound: the (parent rank, score rank) pairs with the smallest (i+1)(j+1)
-        p.n_cells = 64;
+        p.n_cells = (use_cta && a.beam > 16) ? 128 : 64;
         int taken = 0;
         for (int prod = 1; taken < p.n_cells && prod <= a.beam * a.V; prod++)
             for (int i = 0; i < a.beam && taken < p.n_cells; i++) {
@@ -1509,12 +1530,10 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
                 if (j >= a.V) continue;
                 p.cell_i[taken] = (unsigned char)i; p.cell_j[taken] = (unsigned char)j; taken++;
             }
-        for (; taken < 64; taken++) { p.cell_i[taken] = 255; p.cell_j[taken] = 0; }
+        for (; taken < 128; taken++) { p.cell_i[taken] = 255; p.cell_j[taken] = 0; }
     }
 
     if (t1 == a.T) GASR_CUDA(cudaMemsetAsync(wo + L.off_paths, 0, (size_t)a.N * a.nbest * a.max_len, st));
-    const char *force_k = getenv("GASR_CTC_KERNEL");
-    const bool use_cta = fast && (force_k ? force_k[0] == 'c' : a.N <= 2 * ctx->sm_count);
     if (use_cta) {
         // latency path: a 128-thread CTA per utterance (state parked per utterance needs sizeof(CtaBeam) <= stride)
         // 20 KB of (unused) dynamic shared memory keeps these CTAs off the SMs whose shared memory is filled by a
