@@ -364,7 +364,10 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rnn_tanh_mma_kernel(const RnnCl
 
 template <int H>
 static int launch_rnn_mma(const RnnClusterParams &p, int groups, cudaStream_t st) {
-    const size_t smem = 4 * (size_t)RC_NB * (H * 2 + 16) + 4096;
+    // the kernel needs 4 h planes + 4 KB of staging; asking for 200 KB keeps every other CTA (GEMM, Linear, decoder) off
+    // the SMs of the cluster, whose per-step barrier makes it latency critical
+    size_t smem = 4 * (size_t)RC_NB * (H * 2 + 16) + 4096;
+    if (smem < 200 * 1024) smem = 200 * 1024;
     GASR_CUDA(cudaFuncSetAttribute(rnn_tanh_mma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(groups * p.CS);
