@@ -5,7 +5,13 @@
 
 #include <vector>
 
+#include <chrono>
+#include <vector>
+
 #include "common.cuh"
+#include "rnn_stream.cuh"
+#include "stream.cuh"
+#include "tc_common.cuh"
 
 namespace gasr {
 
@@ -469,6 +475,19 @@ struct gasr_asr {
     float *xproj_all = nullptr, *bias_all = nullptr;   // [L][T*N*H], [L][H]
     std::vector<void *> tc_abuf, tc_wbuf;       // per layer: bf16 hi/lo planes of the layer input / of W_ih^T
     bool use_tc = false;
+    // streaming execution (stream_*): persistent kernels coupled by progress counters, no kernel boundaries in time
+    bool stream_ok = false;
+    int stream_fpb = 0, stream_blocks = 0, stream_gemm_ctas = 0;
+    void *x_planes = nullptr;                   // bf16 hi/lo planes of the input batch [rows, Kp]
+    std::vector<void *> h_planes;               // per layer: bf16 hi/lo planes of the hidden sequence [rows, H] x 2
+    void *fc_wbuf = nullptr;                    // W_fc^T hi/lo planes, padded to 32 output rows
+    float *fc_b_pad = nullptr;
+    unsigned *flags = nullptr;                  // [h_done L][xp_ready L][lp_ready][x_ready][misc 16] x blocks
+    size_t flags_bytes = 0;
+    int *host_words = nullptr, *host_words_dev = nullptr;   // mapped host memory: [0] go, [1] error
+    int epoch = 0;
+    gasr::XsMaps xs_maps;
+    cudaEvent_t ev_go = nullptr, ev_r0 = nullptr, ev_r1 = nullptr, ev_g0 = nullptr, ev_g1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
     std::vector<cudaEvent_t> sync_ev;           // cross-stream dependencies (no timing)
     std::vector<cudaEvent_t> t0_ev, t1_ev;      // per-launch timing pairs
     std::vector<int> t_tag;
@@ -535,6 +554,36 @@ int gasr_asr_create(gasr_ctx *ctx, const gasr_asr_config *cfg, const char *vocab
             }
         }
     }
+    if (st == GASR_OK && a->chunk > 0 && a->use_tc) {
+        // streaming envelope: whole blocks of 128 rows, the persistent recurrence's cluster budget, one output tile
+        int want_stream = 1;
+        if (const char *e = getenv("GASR_STREAM")) want_stream = atoi(e);
+        const int N = cfg->N, L = cfg->L;
+        if (want_stream && cfg->beam <= 32 && cfg->V <= 32 && N % 16 == 0 && 128 % N == 0 && L + 1 <= XS_MAX_TARGETS && L <= RS_MAX_LAYERS &&
+            rnn_stream_supported(ctx, H, N, L) && H % 128 == 0 && ((size_t)cfg->T * N) % 128 == 0 && ctx->sm_count >= 132) {
+            a->stream_fpb = 128 / N;
+            a->stream_blocks = (int)(rows / 128);
+            a->stream_gemm_ctas = 20;
+            if (const char *e = getenv("GASR_STREAM_GEMM_CTAS")) a->stream_gemm_ctas = atoi(e);
+            auto allocv = [&](void **p, size_t bytes) { if (st == GASR_OK) st = gasr_malloc_device(ctx, bytes, p); };
+            allocv(&a->x_planes, xproj_tc_a_bytes((int)rows, cfg->in) + 1024);
+            a->h_planes.assign(L, nullptr);
+            for (int l = 0; l < L; l++) allocv(&a->h_planes[l], xproj_tc_a_bytes((int)rows, H) + 1024);
+            allocv(&a->fc_wbuf, xproj_tc_w_bytes(H, 32) + 1024);
+            alloc(&a->fc_b_pad, 32);
+            a->flags_bytes = sizeof(unsigned) * ((size_t)(2 * L + 2) * a->stream_blocks + 16);
+            allocv((void **)&a->flags, a->flags_bytes);
+            if (st == GASR_OK && cudaHostAlloc((void **)&a->host_words, 64, cudaHostAllocMapped) != cudaSuccess) st = GASR_ERR_CUDA;
+            if (st == GASR_OK && cudaHostGetDevicePointer((void **)&a->host_words_dev, a->host_words, 0) != cudaSuccess) st = GASR_ERR_CUDA;
+            if (st == GASR_OK) {
+                a->host_words[0] = 0; a->host_words[1] = 0;
+                for (cudaEvent_t *e : {&a->ev_r0, &a->ev_r1, &a->ev_g0, &a->ev_g1, &a->ev_d0, &a->ev_d1})
+                    if (cudaEventCreate(e) != cudaSuccess) st = GASR_ERR_CUDA;
+                if (cudaEventCreateWithFlags(&a->ev_go, cudaEventDisableTiming) != cudaSuccess) st = GASR_ERR_CUDA;
+            }
+            a->stream_ok = st == GASR_OK;
+        }
+    }
     if (st != GASR_OK) { gasr_asr_destroy(a); return st; }
     *out = a;
     return GASR_OK;
@@ -550,6 +599,10 @@ int gasr_asr_destroy(gasr_asr *a) {
     for (float *p : {a->fc_w, a->fc_b, a->x_dev, a->logp, a->xproj_all, a->bias_all}) if (p) gasr_free_device(ctx, p);
     for (void *p : a->tc_abuf) if (p) gasr_free_device(ctx, p);
     for (void *p : a->tc_wbuf) if (p) gasr_free_device(ctx, p);
+    for (void *p : a->h_planes) if (p) gasr_free_device(ctx, p);
+    for (void *p : {a->x_planes, a->fc_wbuf, (void *)a->fc_b_pad, (void *)a->flags}) if (p) gasr_free_device(ctx, p);
+    if (a->host_words) cudaFreeHost(a->host_words);
+    for (cudaEvent_t e : {a->ev_go, a->ev_r0, a->ev_r1, a->ev_g0, a->ev_g1, a->ev_d0, a->ev_d1}) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : a->sync_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : a->t0_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : a->t1_ev) cudaEventDestroy(e);
@@ -582,6 +635,31 @@ int gasr_asr_set_weights(gasr_asr *a, const float *const *w_ih, const float *con
             GASR_TRY(xproj_tc_prepare_weights(ctx, a->w_ih[l], l == 0 ? c.in : H, H, a->tc_wbuf[l], ctx->stream));
     GASR_TRY(gasr_memcpy_h2d(ctx, a->fc_w, fc_w, sizeof(float) * D * H * c.V));
     GASR_TRY(gasr_memcpy_h2d(ctx, a->fc_b, fc_b, sizeof(float) * c.V));
+    if (a->stream_ok) {
+        // output layer as a 32-column GEMM target: W_fc padded to [H, 32] -> W^T hi/lo planes; bias padded with zeros
+        std::vector<float> wpad((size_t)H * 32, 0.0f), bpad(32, 0.0f);
+        for (int k = 0; k < H; k++) for (int v = 0; v < c.V; v++) wpad[(size_t)k * 32 + v] = fc_w[(size_t)k * c.V + v];
+        for (int v = 0; v < c.V; v++) bpad[v] = fc_b[v];
+        GASR_TRY(ws_reserve(ctx, ctx->ws_misc, sizeof(float) * (size_t)H * 32 + 256));
+        GASR_TRY(gasr_memcpy_h2d(ctx, ctx->ws_misc.ptr, wpad.data(), sizeof(float) * (size_t)H * 32));
+        GASR_TRY(xproj_tc_prepare_weights(ctx, static_cast<const float *>(ctx->ws_misc.ptr), H, 32, a->fc_wbuf, ctx->stream));
+        GASR_TRY(gasr_memcpy_h2d(ctx, a->fc_b_pad, bpad.data(), sizeof(float) * 32));
+        for (int l = 0; l < c.L; l++)   // (b_hh + b_ih), RNN_Cell.cu:10
+            GASR_TRY(launch_matadd(ctx, a->b_ih[l], H, a->b_hh[l], H, a->bias_all + (size_t)l * H, H, 1, H, 1.0f, ctx->stream));
+        GASR_CUDA(cudaStreamSynchronize(ctx->stream));
+        // TMA descriptors: target l < L = projection of layer l (A = planes of layer l-1 / of x), target L = output layer
+        const int rows = c.T * c.N;
+        for (int tg = 0; tg <= c.L; tg++) {
+            const int K = tg == 0 ? c.in : H, Kp = ceil_div(K, TC_BK) * TC_BK;
+            unsigned char *ab = static_cast<unsigned char *>(tg == 0 ? a->x_planes : a->h_planes[tg - 1]);
+            unsigned char *wb = static_cast<unsigned char *>(tg < c.L ? a->tc_wbuf[tg] : a->fc_wbuf);
+            const int nout = tg < c.L ? H : 32;
+            GASR_TRY(tc_make_map(&a->xs_maps.m[4 * tg + 0], ab, rows, Kp, TC_BM));
+            GASR_TRY(tc_make_map(&a->xs_maps.m[4 * tg + 1], ab + xproj_tc_a_bytes(rows, K) / 2, rows, Kp, TC_BM));
+            GASR_TRY(tc_make_map(&a->xs_maps.m[4 * tg + 2], wb, nout, Kp, tg < c.L ? TC_BN : 32));
+            GASR_TRY(tc_make_map(&a->xs_maps.m[4 * tg + 3], wb + xproj_tc_w_bytes(K, nout) / 2, nout, Kp, tg < c.L ? TC_BN : 32));
+        }
+    }
     a->have_weights = true;
     return GASR_OK;
 }
@@ -707,12 +785,172 @@ static int asr_run_pipelined(gasr_asr *a, const float *x_dev, char *out_paths, i
     return ctc_decode_finish(ctx, ca);
 }
 
+// Streaming path: three persistent kernels -- the layer stack's recurrence (rnn_stream.cu), the projection / output
+// layer GEMM (xproj_stream.cu) and the decoder (ctc_beam.cu, CTA kernel) -- run concurrently for the whole sequence and
+// hand 128-row blocks (a few frames of the batch) to each other through counters in HBM.
+static int asr_run_streaming(gasr_asr *a, const float *x_dev, char *out_paths, int *out_lens, float *out_scores) {
+    gasr_ctx *ctx = a->ctx;
+    const gasr_asr_config &c = a->cfg;
+    const int T = c.T, N = c.N, H = c.H, L = c.L, nb = a->stream_blocks, rows = T * N;
+    cudaStream_t main_st = ctx->stream, rec_st = ctx->side[0], gemm_st = ctx->side[1], dec_st = ctx->side[3];
+    unsigned *h_done = a->flags, *xp_ready = a->flags + (size_t)L * nb, *lp_ready = a->flags + (size_t)2 * L * nb;
+    unsigned *x_ready = lp_ready + nb, *misc = x_ready + nb;
+    const int rec_ctas_per_layer = ceil_div(N, 16) * (H / 64);
+    a->epoch += 1;
+    a->host_words[1] = 0;
+    // everything that may synchronise the device (allocations, function attributes) happens before the first persistent
+    // kernel starts: once they run they wait for each other, not for the host
+    CtcArgs ca = {a->logp, GASR_DOMAIN_LOG, T, N, c.V, a->ldp, c.beam, c.blank, a->vocab.data(), c.max_len,
+                  c.nbest, out_paths, out_lens, out_scores, nullptr};
+    GASR_TRY(ctc_decode_reserve(ctx, ca));
+    {
+        XsParams prep = {};
+        prep.n_targets = 1; prep.abort = misc + 1;
+        XsTarget &t = prep.target[0];
+        t.kind = XS_KIND_XPROJ; t.C = a->xproj_all; t.ldc = H; t.src_done = x_ready; t.dst_ready = xp_ready; t.kblocks = 1; t.bn = TC_BN; t.terms = 3; t.n_tiles = 1;
+        GASR_TRY(launch_xproj_stream(ctx, a->xs_maps, prep, 0, gemm_st));
+    }
+    GASR_CUDA(cudaMemsetAsync(a->flags, 0, a->flags_bytes, main_st));
+    GASR_CUDA(cudaMemsetAsync(x_ready, 0xff, sizeof(unsigned) * nb, main_st));
+    GASR_TRY(xproj_tc_split_rows(ctx, x_dev, c.in, rows, c.in, a->x_planes, main_st));
+    GASR_CUDA(cudaEventRecord(a->ev_go, main_st));
+    const bool dbg = getenv("GASR_STREAM_DEBUG") != nullptr;
+    if (dbg) { GASR_CUDA(cudaStreamSynchronize(main_st)); fprintf(stderr, "[stream] prep ok\n"); }
+
+    // ---- recurrence: all layers, one launch ------------------------------------------------------------------------
+    RnnStreamParams rp = {};
+    rp.T = T; rp.N = N; rp.L = L; rp.groups = ceil_div(N, 16); rp.frames_per_block = a->stream_fpb;
+    rp.xp_need = XS_EPI_WARPS * (H / TC_BN);
+    rp.error = a->host_words_dev + 1; rp.abort = misc + 1; rp.started = misc; rp.host_go = a->host_words_dev; rp.epoch = a->epoch;
+    for (int l = 0; l < L; l++) {
+        RnnStreamLayer &y = rp.layer[l];
+        y.xproj = a->xproj_all + (size_t)l * rows * H; y.ldxp = H; y.w_hh = a->w_hh[l];
+        y.out = nullptr; y.ldo = H;
+        y.out_hi = static_cast<__nv_bfloat16 *>(a->h_planes[l]);
+        y.out_lo = reinterpret_cast<__nv_bfloat16 *>(static_cast<unsigned char *>(a->h_planes[l]) + xproj_tc_a_bytes(rows, H) / 2);
+        y.ldp = H;
+        y.xp_ready = xp_ready + (size_t)l * nb;
+        y.h_done = h_done + (size_t)l * nb;
+    }
+    GASR_CUDA(cudaStreamWaitEvent(rec_st, a->ev_go, 0));
+    GASR_CUDA(cudaEventRecord(a->ev_r0, rec_st));
+    GASR_TRY(launch_rnn_stream(ctx, rp, H, rec_st));
+    GASR_CUDA(cudaEventRecord(a->ev_r1, rec_st));
+    {   // the recurrence needs whole SMs in cluster-sized groups: everything else is launched once it is resident
+        const auto t0 = std::chrono::steady_clock::now();
+        volatile int *go = a->host_words;
+        while (*go != a->epoch) {
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 10.0) {
+                cudaStreamSynchronize(rec_st);
+                set_error("streaming pipeline: the recurrence kernel did not become resident");
+                return GASR_ERR_CUDA;
+            }
+        }
+    }
+    if (dbg) {
+        cudaError_t q = cudaStreamQuery(rec_st);
+        fprintf(stderr, "[stream] recurrence resident, query: %s\n", cudaGetErrorString(q));
+        if (q != cudaSuccess && q != cudaErrorNotReady) { set_error("recurrence kernel failed: %s", cudaGetErrorString(q)); return GASR_ERR_CUDA; }
+        if (getenv("GASR_STREAM_DEBUG")[0] == '2') {
+            q = cudaStreamSynchronize(rec_st);
+            fprintf(stderr, "[stream] recurrence alone: %s, error word %d\n", cudaGetErrorString(q), a->host_words[1]);
+            return GASR_ERR_CUDA;
+        }
+    }
+    // ---- projection + output-layer GEMM -------------------------------------------------------------------------------
+    XsParams xp = {};
+    xp.M = rows; xp.n_blocks = nb; xp.n_targets = L + 1; xp.error = a->host_words_dev + 1; xp.abort = misc + 1;
+    // CTAs per target in proportion to its operand traffic per block (the tile engine is L2->smem bound)
+    int gemm_ctas = 0;
+    {
+        double w[XS_MAX_TARGETS], wsum = 0.0;
+        for (int tg = 0; tg <= L; tg++) {
+            const int K = tg == 0 ? c.in : H, bn = tg < L ? TC_BN : 32, nt = tg < L ? H / TC_BN : 1;
+            w[tg] = (double)nt * ceil_div(K, TC_BK) * (128 + bn);
+            wsum += w[tg];
+        }
+        for (int tg = 0; tg <= L; tg++) {
+            int n = (int)(a->stream_gemm_ctas * w[tg] / wsum + 0.5);
+            if (n < 1) n = 1;
+            if (tg == L && n < 2) n = 2;
+            xp.target[tg].cta0 = gemm_ctas; xp.target[tg].nctas = n;
+            gemm_ctas += n;
+        }
+    }
+    for (int tg = 0; tg <= L; tg++) {
+        XsTarget &t = xp.target[tg];
+        const int K = tg == 0 ? c.in : H;
+        t.kblocks = ceil_div(K, TC_BK); t.terms = c.precision == GASR_PREC_BF16 ? 1 : 3;
+        t.src_done = tg == 0 ? x_ready : h_done + (size_t)(tg - 1) * nb;
+        t.src_need = tg == 0 ? 1 : rec_ctas_per_layer;
+        if (tg < L) {
+            t.kind = XS_KIND_XPROJ; t.n_tiles = H / TC_BN; t.bn = TC_BN; t.V = 0;
+            t.C = a->xproj_all + (size_t)tg * rows * H; t.ldc = H; t.bias = a->bias_all + (size_t)tg * H;
+            t.dst_ready = xp_ready + (size_t)tg * nb;
+        } else {
+            t.kind = XS_KIND_LOGSOFTMAX; t.n_tiles = 1; t.bn = 32; t.V = c.V; t.terms = 3;
+            t.C = a->logp; t.ldc = a->ldp; t.bias = a->fc_b_pad; t.dst_ready = lp_ready;
+        }
+    }
+    if (dbg && getenv("GASR_DEBUG_TERMS")) for (int tg = 0; tg <= L; tg++) xp.target[tg].terms = atoi(getenv("GASR_DEBUG_TERMS"));
+    if (dbg && getenv("GASR_DEBUG_SAMEMAP")) for (int tg = 0; tg <= L; tg++) xp.target[tg].kind |= 32;
+    if (dbg && getenv("GASR_DEBUG_PRINT")) for (int tg = 0; tg <= L; tg++) xp.target[tg].kind |= 64;
+    if (dbg && getenv("GASR_DEBUG_NOEPI")) for (int tg = 0; tg <= L; tg++) xp.target[tg].kind |= 16;
+    if (dbg && getenv("GASR_STREAM_DEBUG")[0] == '3') {
+        // tile-engine throughput: every dependency preset, the GEMM kernel alone
+        cudaStreamSynchronize(rec_st);
+        GASR_CUDA(cudaMemsetAsync(a->flags, 0xff, sizeof(unsigned) * (size_t)L * nb, gemm_st));
+        GASR_CUDA(cudaMemsetAsync(misc, 0, 64, gemm_st));
+        a->host_words[1] = 0;
+        GASR_CUDA(cudaEventRecord(a->ev_g0, gemm_st));
+        GASR_TRY(launch_xproj_stream(ctx, a->xs_maps, xp, gemm_ctas, gemm_st));
+        GASR_CUDA(cudaEventRecord(a->ev_g1, gemm_st));
+        GASR_CUDA(cudaStreamSynchronize(gemm_st));
+        float ms = 0; cudaEventElapsedTime(&ms, a->ev_g0, a->ev_g1);
+        fprintf(stderr, "[stream] gemm alone: %.3f ms, %d CTAs:", ms, gemm_ctas);
+        for (int tg = 0; tg <= L; tg++) fprintf(stderr, " target %d -> %d CTAs", tg, xp.target[tg].nctas);
+        fprintf(stderr, " (error word %d)\n", a->host_words[1]);
+        return GASR_ERR_CUDA;
+    }
+    GASR_CUDA(cudaStreamWaitEvent(gemm_st, a->ev_go, 0));
+    GASR_CUDA(cudaEventRecord(a->ev_g0, gemm_st));
+    GASR_TRY(launch_xproj_stream(ctx, a->xs_maps, xp, gemm_ctas, gemm_st));
+    GASR_CUDA(cudaEventRecord(a->ev_g1, gemm_st));
+    if (dbg) {
+        cudaError_t q = cudaStreamSynchronize(gemm_st);
+        fprintf(stderr, "[stream] gemm done: %s, error word %d\n", cudaGetErrorString(q), a->host_words[1]);
+        q = cudaStreamSynchronize(rec_st);
+        fprintf(stderr, "[stream] recurrence done: %s, error word %d\n", cudaGetErrorString(q), a->host_words[1]);
+    }
+    // ---- decoder ----------------------------------------------------------------------------------------------------------
+    ca.lp_ready = lp_ready; ca.lp_need = XS_EPI_WARPS; ca.lp_fpb = a->stream_fpb; ca.error = a->host_words_dev + 1; ca.abort = misc + 1;
+    GASR_CUDA(cudaStreamWaitEvent(dec_st, a->ev_go, 0));
+    GASR_CUDA(cudaEventRecord(a->ev_d0, dec_st));
+    GASR_TRY(ctc_decode_launch(ctx, ca, dec_st));
+    GASR_CUDA(cudaEventRecord(a->ev_d1, dec_st));
+    GASR_CUDA(cudaStreamWaitEvent(main_st, a->ev_r1, 0));
+    GASR_CUDA(cudaStreamWaitEvent(main_st, a->ev_g1, 0));
+    GASR_CUDA(cudaStreamWaitEvent(main_st, a->ev_d1, 0));
+    GASR_CUDA(cudaStreamSynchronize(main_st));
+    if (a->host_words[1] != 0) {
+        set_error("streaming pipeline: watchdog fired (code %d): a persistent kernel waited too long for its producer", a->host_words[1]);
+        return GASR_ERR_CUDA;
+    }
+    for (int i = 0; i < 4; i++) { a->stage_ms[i] = 0.0f; a->stage_launches[i] = 0; }
+    cudaEventElapsedTime(&a->stage_ms[0], a->ev_g0, a->ev_g1); a->stage_launches[0] = 1;
+    cudaEventElapsedTime(&a->stage_ms[1], a->ev_r0, a->ev_r1); a->stage_launches[1] = 1;
+    cudaEventElapsedTime(&a->stage_ms[3], a->ev_d0, a->ev_d1); a->stage_launches[3] = 1;
+    ca.lp_ready = nullptr;
+    return ctc_decode_finish(ctx, ca);
+}
+
 int gasr_asr_run_device(gasr_asr *a, const float *x_dev, char *out_paths, int *out_lens, float *out_scores) {
     GASR_CHECK(a != nullptr, "null gasr_asr");
     gasr_ctx *ctx = a->ctx;
     GASR_ENTER(ctx);
     GASR_CHECK(a->have_weights, "gasr_asr_run: weights not set");
     GASR_CHECK(x_dev && out_paths && out_lens && out_scores, "gasr_asr_run: null argument");
+    if (a->stream_ok) return asr_run_streaming(a, x_dev, out_paths, out_lens, out_scores);
     if (a->chunk > 0) return asr_run_pipelined(a, x_dev, out_paths, out_lens, out_scores);
     return asr_run_sequential(a, x_dev, out_paths, out_lens, out_scores);
 }

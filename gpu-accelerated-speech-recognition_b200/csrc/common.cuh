@@ -59,6 +59,7 @@ struct gasr_ctx {
     void *pinned_out = nullptr;          // pinned staging for decode results
     size_t pinned_out_bytes = 0;
     long long ctc_fallback_frames = 0, ctc_survivors = 0;   // diagnostics of the last decode
+    unsigned attr_mask = 0;              // kernels whose function attributes are set (setting them is not stream-safe)
 };
 
 namespace gasr {
@@ -85,6 +86,7 @@ bool xproj_tc_supported(int M, int K, int N);
 size_t xproj_tc_a_bytes(int M, int K);      // scratch for the bf16 hi/lo planes of A
 size_t xproj_tc_w_bytes(int K, int N);      // prepared (transposed, split) weights
 int xproj_tc_prepare_weights(gasr_ctx *ctx, const float *W, int K, int N, void *wbuf, cudaStream_t st);
+int xproj_tc_split_rows(gasr_ctx *ctx, const float *A, int lda, int M, int K, void *abuf, cudaStream_t st);
 int launch_xproj_tc(gasr_ctx *ctx, const float *A, int lda, int M, int K, int N, const void *wbuf, void *abuf,
                     const float *bias, float *C, int ldc, int precision, cudaStream_t st);
 
@@ -104,7 +106,10 @@ struct CtcArgs {
     const float *scores; int domain, T, N, V, ld, beam, blank; const char *vocab_host; int max_len, nbest;
     char *out_paths; int *out_lens; float *out_scores; int *out_counts;   // host
     int t0 = 0, t1 = 0;   // frames [t0, t1) only (t1 = 0: all T); the beam is parked in the ctx workspace between chunks
+    // streaming pipeline: scores of frame t may be read once lp_ready[t / lp_fpb] >= lp_need (device counters)
+    const unsigned *lp_ready = nullptr; int lp_need = 0, lp_fpb = 1; int *error = nullptr; volatile unsigned *abort = nullptr;
 };
+int ctc_decode_reserve(gasr_ctx *ctx, const CtcArgs &a);                  // allocations only (device-synchronising)
 int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st);   // enqueue kernel + D2H into pinned staging
 int ctc_decode_finish(gasr_ctx *ctx, const CtcArgs &a);                    // after stream sync: unpack to caller buffers
 

@@ -123,6 +123,11 @@ struct CtcParams {
     int t0, t1;          // frames [t0, t1) are decoded by this launch (time chunking; warp kernel only)
     unsigned char *state;   // [N, state_stride] saved beam state between chunk launches
     size_t state_stride;
+    // streaming (CTA kernel only): frame t may be read once lp_ready[t / lp_fpb] >= lp_need (null: everything is ready)
+    const unsigned *lp_ready;
+    int lp_need, lp_fpb;
+    int *error;
+    volatile unsigned *abort;
 };
 
 constexpr int kNone = -1;
@@ -1042,13 +1047,47 @@ __global__ void __launch_bounds__(128) ctc_beam_cta_kernel(const CtcParams p) {
         for (int i = tid; i < kStateVec; i += 128) dst[i] = gstate[i];
         cur = gstate[kStateVec].x;
     }
-    float lp_next = active ? S[(size_t)p.t0 * frame_stride + lane] : 0.0f;
+    // streaming: the log-probabilities are produced while this kernel runs; every warp tracks how many frames are
+    // known complete (ready_frames) and samples the next block's counter one block early (flag_next)
+    const volatile unsigned *lpr = p.lp_ready;
+    const bool streaming = lpr != nullptr;
+    int ready_frames = streaming ? 0 : p.T;
+    unsigned flag_next = 0;
+    auto frames_ready = [&](int t) {                     // returns once frame t may be read
+        while (t >= ready_frames) {
+            const int blk = ready_frames / p.lp_fpb;
+            unsigned v = __shfl_sync(FULL, flag_next, 0);
+            if (v < (unsigned)p.lp_need) {
+                unsigned long long t_start = 0;
+                do {
+                    if (lane == 0) v = lpr[blk];
+                    v = __shfl_sync(FULL, v, 0);
+                    if (v < (unsigned)p.lp_need) {
+                        unsigned long long now;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        if (t_start == 0) t_start = now;
+                        if ((p.abort && *p.abort) || now - t_start > 2000000000ull) {
+                            if (p.abort) *p.abort = 1u; if (p.error) { *reinterpret_cast<volatile int *>(p.error) = 4; __threadfence_system(); } break; }   // watchdog: give up waiting
+                        __nanosleep(200);
+                    }
+                } while (v < (unsigned)p.lp_need);
+            }
+            ready_frames = (blk + 1) * p.lp_fpb;
+            flag_next = 0;
+            if (ready_frames < p.T && lane == 0) flag_next = lpr[blk + 1];
+        }
+    };
+    if (streaming) frames_ready(p.t0);
+    float lp_next = active ? __ldcg(S + (size_t)p.t0 * frame_stride + lane) : 0.0f;
     __syncthreads();
     int kept = cb.kept;
 
     for (int t = p.t0; t < p.t1; t++) {
         const float lp = lp_next;
-        if (t + 1 < p.t1 && active) lp_next = S[(size_t)(t + 1) * frame_stride + lane];
+        if (t + 1 < p.t1) {
+            if (streaming) frames_ready(t + 1);
+            if (active) lp_next = __ldcg(S + (size_t)(t + 1) * frame_stride + lane);
+        }
         const bool last_frame = (t == p.T - 1) && (t > 0);
         const int k = kept;
         const float *sc = cb.sc[cur];
@@ -1470,6 +1509,18 @@ static int ctc_layout(const CtcArgs &a, CtcLayout &L) {
     return GASR_OK;
 }
 
+// Grow the decoder's workspaces for this problem size (allocation synchronises the device: the streaming pipeline
+// calls this before its persistent kernels start).
+int ctc_decode_reserve(gasr_ctx *ctx, const CtcArgs &a) {
+    if (a.N == 0) return GASR_OK;
+    CtcLayout L;
+    ctc_layout(a, L);
+    GASR_TRY(ws_reserve(ctx, ctx->ws_ctc, L.total));
+    GASR_TRY(ws_reserve(ctx, ctx->ws_out, L.out_bytes));
+    GASR_TRY(pinned_reserve(ctx, L.out_bytes));
+    return GASR_OK;
+}
+
 int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
     GASR_CHECK(a.scores != nullptr && a.vocab_host != nullptr, "ctc_decode: null scores/vocab");
     GASR_CHECK(a.T >= 1 && a.N >= 0, "ctc_decode: T must be >= 1 and N >= 0 (T=%d N=%d)", a.T, a.N);
@@ -1517,8 +1568,10 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
     if (!fast) GASR_CUDA(cudaMemsetAsync(p.out_stats, 0, 2 * sizeof(int) * (size_t)a.N, st));
     p.t0 = t0; p.t1 = t1;
     p.state = ws + L.off_state; p.state_stride = L.state_stride;
+    p.lp_ready = a.lp_ready; p.lp_need = a.lp_need; p.lp_fpb = a.lp_fpb > 0 ? a.lp_fpb : 1; p.error = a.error; p.abort = a.abort;
     const char *force_k = getenv("GASR_CTC_KERNEL");
-    const bool use_cta = fast && (force_k ? force_k[0] == 'c' : a.N <= 2 * ctx->sm_count);
+    const bool use_cta = fast && (a.lp_ready != nullptr || (force_k ? force_k[0] == 'c' : a.N <= 2 * ctx->sm_count));
+    GASR_CHECK(a.lp_ready == nullptr || (fast && t0 == 0 && t1 == a.T), "ctc_decode: streaming needs beam <= 32, vocab <= 32, whole sequence");
     {
         // probe cells of the prune lower bound: the (parent rank, score rank) pairs with the smallest (i+1)(j+1)
         p.n_cells = (use_cta && a.beam > 16) ? 128 : 64;

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "rnn_stream.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -409,6 +410,16 @@ int launch_rnn_recurrence(gasr_ctx *ctx, const RnnLayerArgs &a, cudaStream_t st)
         p.s0 = a.s0; p.s1 = a.s1 > 0 ? a.s1 : a.T;
         const int groups = ceil_div(a.N, RC_NB);
         const char *force = getenv("GASR_RNN");
+        // whole-sequence calls: the latency-optimised persistent kernel (rnn_stream.cu); chunk-resumed calls and the
+        // envelope outside it (more than 16 co-resident clusters) stay on the kernels below
+        if (!(force && (force[0] == 'f' || force[0] == 'm')) && !a.reverse && p.s0 == 0 && p.s1 == a.T &&
+            rnn_stream_supported(ctx, a.H, a.N, 1) && a.col0 == 0) {
+            RnnStreamParams sp = {};
+            sp.T = a.T; sp.N = a.N; sp.L = 1; sp.groups = groups; sp.frames_per_block = 1; sp.xp_need = 0; sp.error = nullptr;
+            sp.layer[0].xproj = a.xproj; sp.layer[0].ldxp = a.ldxp; sp.layer[0].w_hh = a.w_hh;
+            sp.layer[0].out = a.out; sp.layer[0].ldo = a.ldo;
+            return launch_rnn_stream(ctx, sp, a.H, st);
+        }
         if (!(force && force[0] == 'f') && a.ldxp % 2 == 0 && a.ldo % 2 == 0) {
             int rc = GASR_OK;
             if (a.H == 512) rc = launch_rnn_mma<512>(p, groups, st);

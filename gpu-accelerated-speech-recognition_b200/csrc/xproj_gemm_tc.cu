@@ -23,55 +23,9 @@
 #include <stdint.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace gasr {
-
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 3, TC_THREADS = 192;
-constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 2;              // 16 KB: one [128 x 64] bf16 tile
-constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;             // A_hi, A_lo, B_hi, B_lo
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-// K-major, SWIZZLE_128B shared-memory matrix descriptor of a [rows x 64 bf16] tile (1024-byte aligned):
-// start address >> 4 | LBO = 1 (16 B, unused for swizzled K-major) | SBO = 1024 B between 8-row groups |
-// version 1 (Blackwell) | layout type 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
 
 struct TcParams {
     int M, N, kblocks, terms;     // terms = 3 (fp32-grade) or 1 (bf16)
@@ -236,12 +190,12 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D bf16 tensor [rows, Kp] row-major, box [128 rows x 64 cols], 128-byte swizzle
-static int make_map(CUtensorMap *map, const void *base, int rows, int Kp) {
+int tc_make_map(CUtensorMap *map, const void *base, int rows, int Kp, int box_rows) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return GASR_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -268,6 +222,20 @@ int xproj_tc_prepare_weights(gasr_ctx *ctx, const float *W, int K, int N, void *
     return GASR_OK;
 }
 
+// fp32 A[M, K] -> bf16 hi/lo planes [M, Kp] in abuf (hi at abuf, lo at abuf + xproj_tc_a_bytes(M, K) / 2)
+int xproj_tc_split_rows(gasr_ctx *ctx, const float *A, int lda, int M, int K, void *abuf, cudaStream_t st) {
+    const int Kp = ceil_div(K, TC_BK) * TC_BK;
+    __nv_bfloat16 *a_hi = static_cast<__nv_bfloat16 *>(abuf);
+    __nv_bfloat16 *a_lo = reinterpret_cast<__nv_bfloat16 *>(static_cast<unsigned char *>(abuf) + xproj_tc_a_bytes(M, K) / 2);
+    const size_t total = (size_t)M * (Kp / 2);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    split_rows_kernel<<<blocks, 256, 0, st>>>(A, lda, M, K, Kp, a_hi, a_lo);
+    GASR_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return GASR_OK;
+}
+
 // C[M, N] = A[M, K] * W + bias with W prepared by xproj_tc_prepare_weights; abuf is scratch of xproj_tc_a_bytes(M, K).
 int launch_xproj_tc(gasr_ctx *ctx, const float *A, int lda, int M, int K, int N, const void *wbuf, void *abuf,
                     const float *bias, float *C, int ldc, int precision, cudaStream_t st) {
@@ -287,10 +255,10 @@ int launch_xproj_tc(gasr_ctx *ctx, const float *A, int lda, int M, int K, int N,
         ctx->launches += 1;
     }
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-    GASR_TRY(make_map(&ma_hi, a_hi, M, Kp));
-    GASR_TRY(make_map(&ma_lo, a_lo, M, Kp));
-    GASR_TRY(make_map(&mb_hi, w_hi, N, Kp));
-    GASR_TRY(make_map(&mb_lo, w_lo, N, Kp));
+    GASR_TRY(tc_make_map(&ma_hi, a_hi, M, Kp, TC_BM));
+    GASR_TRY(tc_make_map(&ma_lo, a_lo, M, Kp, TC_BM));
+    GASR_TRY(tc_make_map(&mb_hi, w_hi, N, Kp, TC_BM));
+    GASR_TRY(tc_make_map(&mb_lo, w_lo, N, Kp, TC_BM));
     TcParams p;
     p.M = M; p.N = N; p.kblocks = Kp / TC_BK; p.terms = precision == GASR_PREC_BF16 ? 1 : 3;
     p.C = C; p.ldc = ldc; p.bias = bias;

@@ -372,8 +372,10 @@ def test_gru_bidirectional_vs_oracle(gasr, ctx, O):
 
 
 # ---------------------------------------------------------------- end-to-end pipeline ----------------------
+# the last three shapes sit inside the streaming envelope (persistent kernels coupled by progress counters)
 @pytest.mark.parametrize("T,N,D,H,L,beam", [(60, 10, 161, 512, 3, 16), (33, 3, 20, 64, 1, 4), (230, 20, 40, 128, 3, 8),
-                                            (137, 5, 161, 512, 2, 32)])
+                                            (137, 5, 161, 512, 2, 32), (104, 16, 40, 128, 2, 8), (120, 32, 161, 256, 3, 32),
+                                            (200, 64, 161, 512, 3, 16)])
 def test_pipeline_end_to_end(gasr, ctx, O, T, N, D, H, L, beam):
     import synth
     V = 29
