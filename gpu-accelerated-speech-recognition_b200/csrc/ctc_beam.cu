@@ -1493,8 +1493,8 @@ struct Cta2Beam {
     unsigned char rel[2][BMAX][BMAX];
     unsigned cand[BMAX][32];
     unsigned ckey[128];
-    unsigned surv_key[64];
-    int surv_iv[64];
+    unsigned surv_key[128];
+    int surv_iv[128];
     float lpring[2][32];
     int order[2][32], rankof[2][32];
     unsigned theta;
@@ -1503,11 +1503,11 @@ struct Cta2Beam {
 };
 
 template <int MW> __device__ __forceinline__ void cta2_bar_main() { asm volatile("bar.sync 1, %0;" ::"n"(MW * 32) : "memory"); }
-template <int MW> __device__ __forceinline__ void cta2_bar_all() { asm volatile("bar.sync 2, %0;" ::"n"(MW * 32 + 32) : "memory"); }
+template <int MW> __device__ __forceinline__ void cta2_bar_all() { asm volatile("bar.sync 2, %0;" ::"n"(MW * 32 + 64) : "memory"); }
 
-// MW = number of main warps (4 or 8); the aux warp is warp MW
+// MW = number of main warps; warp MW fetches and ranks the log-probabilities, warp MW + 1 owns the trie
 template <int DOMAIN, int BMAX, int MW>
-__global__ void __launch_bounds__(MW * 32 + 32) ctc_beam_cta2_kernel(const CtcParams p) {
+__global__ void __launch_bounds__(MW * 32 + 64) ctc_beam_cta2_kernel(const CtcParams p) {
     constexpr int MT = MW * 32;                          // main threads
     __shared__ __align__(16) Cta2Beam<BMAX> cb;
     __shared__ char vch_s[32];
@@ -1529,7 +1529,7 @@ __global__ void __launch_bounds__(MW * 32 + 32) ctc_beam_cta2_kernel(const CtcPa
     if (tid < Vp) child[tid] = 0;
     if (tid < BMAX) { cb.tw[tid] = kNone; cb.p0[tid] = kNone; cb.p1[tid] = kNone; cb.abs0[tid] = 0u; cb.abs1[tid] = 0u; }
     if (tid < 128) cb.ckey[tid] = 0u;
-    for (int i = tid; i < BMAX * 32; i += MT + 32) cb.cellmap[i] = p.cellmap[i];
+    for (int i = tid; i < BMAX * 32; i += MT + 64) cb.cellmap[i] = p.cellmap[i];
     if (tid == 0) {
         parent[0] = -1; meta[0] = 0xff;
         cb.sc[0][0] = DOMAIN ? 0.0f : 1.0f;
@@ -1539,7 +1539,7 @@ __global__ void __launch_bounds__(MW * 32 + 32) ctc_beam_cta2_kernel(const CtcPa
     }
 
     if (w == MW) {
-        // =============================== auxiliary warp ===============================
+        // =============================== fetch warp: log-probabilities one frame ahead ===============================
         const volatile unsigned *lpr = p.lp_ready;
         int ready_frames = lpr != nullptr ? 0 : T;
         auto fetch_frame = [&](int t) {                  // log-probabilities of frame t -> ring slot t & 1, ranked
@@ -1578,9 +1578,18 @@ __global__ void __launch_bounds__(MW * 32 + 32) ctc_beam_cta2_kernel(const CtcPa
         };
         fetch_frame(0);
         __syncthreads();
-        int cur = 0, kept = 1;
         for (int t = 0; t < T; t++) {
             if (t + 1 < T) fetch_frame(t + 1);
+            cta2_bar_all<MW>();
+        }
+        cta2_bar_all<MW>();
+        return;
+    }
+    if (w == MW + 1) {
+        // =============================== trie warp: one frame behind the beam ===============================
+        __syncthreads();
+        int cur = 0, kept = 1;
+        for (int t = 0; t < T; t++) {
             cta2_bar_all<MW>();                              // frame t's selection is visible; my previous trie work is done
             // ---- trie: the selected candidates become nodes (lookup, allocate on a miss) ----
             const int nxt = cur ^ 1, sb = t & 1;
@@ -1646,7 +1655,8 @@ __global__ void __launch_bounds__(MW * 32 + 32) ctc_beam_cta2_kernel(const CtcPa
     int stat_surv = 0, stat_fallback = 0;
     constexpr int NC = BMAX <= 16 ? 64 : 128;
     constexpr int TPC = MT / NC;                         // threads per probe cell
-    constexpr int TPS = MT / 64;                         // threads per survivor in the ranking phase
+    constexpr int TPS = MT / 64;                         // threads per survivor in the ranking phase (halved above 64 survivors)
+    static_assert(TPS >= 2, "the ranking phase needs at least two threads per survivor slot");
 
     for (int t = 0; t < T; t++) {
         const int k = kept, slot = t & 1, sb = t & 1, nxt = cur ^ 1;
@@ -1797,7 +1807,7 @@ __global__ void __launch_bounds__(MW * 32 + 32) ctc_beam_cta2_kernel(const CtcPa
 #pragma unroll
             for (int q = 0; q < RPW; q++) {
                 const int pos = base + __popc(masks4[q] & ((1u << lane) - 1u));
-                if (((masks4[q] >> lane) & 1u) && pos < 64) {
+                if (((masks4[q] >> lane) & 1u) && pos < 128) {
                     cb.surv_key[pos] = keys4[q]; cb.surv_iv[pos] = ((w + MW * q) << 8) | lane;
                 }
                 base += __popc(masks4[q]);
@@ -1807,13 +1817,15 @@ __global__ void __launch_bounds__(MW * 32 + 32) ctc_beam_cta2_kernel(const CtcPa
         }
         cta2_bar_main<MW>();
         const int ns = cb.ns;
-        if (tid == 0) { stat_surv += ns; stat_fallback += ns > 64; }
+        if (tid == 0) { stat_surv += ns; stat_fallback += ns > 128; }
 
         // ================= phase E: exact order of the survivors, straight into their slots =================
         int m = 0;
-        if (ns <= 64) {
+        if (ns <= 128) {
             m = ns < B ? ns : B;
-            const int sidx = tid / TPS, half = tid % TPS;
+            // TPS threads share a survivor (fewer when the bound was loose and survivors are many)
+            const int tps = ns <= 64 ? TPS : TPS / 2;
+            const int sidx = tid / tps, half = tid % tps;
             int rank = 0;
             unsigned key = 0u;
             int iv = 0;
@@ -1822,7 +1834,7 @@ __global__ void __launch_bounds__(MW * 32 + 32) ctc_beam_cta2_kernel(const CtcPa
                 iv = cb.surv_iv[sidx];
                 const int mi = iv >> 8, mv = iv & 0xff;
                 const int ms = cand_suffix_id(mv, blank, pk[mi]);
-                for (int o = half; o < ns; o += TPS) {
+                for (int o = half; o < ns; o += tps) {
                     const unsigned ok = cb.surv_key[o];
                     if (ok > key) rank++;
                     else if (ok == key && o != sidx) {
@@ -1836,13 +1848,16 @@ __global__ void __launch_bounds__(MW * 32 + 32) ctc_beam_cta2_kernel(const CtcPa
                 }
             }
 #pragma unroll
-            for (int off = 1; off < TPS; off <<= 1) rank += __shfl_xor_sync(FULL, rank, off);
+            for (int off = 1; off < TPS; off <<= 1) {
+                const int other = __shfl_xor_sync(FULL, rank, off);
+                if (off < tps) rank += other;
+            }
             if (sidx < ns && half == 0 && rank < B) {
                 cb.selkey[sb][rank] = key; cb.seli[sb][rank] = iv >> 8; cb.selv[sb][rank] = iv & 0xff;
             }
             if (tid == 0) cb.sel_m[sb] = m;
         } else {
-            // more than 64 survivors (loose bound): beam rounds of warp-max extraction on warp 0
+            // more than 128 survivors (very loose bound): beam rounds of warp-max extraction on warp 0
             if (w == 0) {
                 unsigned lmax = 0u;
                 for (int i = 0; i < k; i++) lmax = max(lmax, cb.cand[i][lane]);
@@ -2062,14 +2077,17 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
     if (t1 == a.T) GASR_CUDA(cudaMemsetAsync(wo + L.off_paths, 0, (size_t)a.N * a.nbest * a.max_len, st));
     const bool whole = t0 == 0 && t1 == a.T;
     if (use_cta && whole && !(force_k && force_k[0] == 'c')) {
-        // latency path, second generation: 8 main warps + 1 trie / prefetch warp per utterance, whole sequence
-        const size_t pad = 20480;
+        // latency path, second generation: 8 main warps + fetch warp + trie warp per utterance, whole sequence.  No
+        // shared-memory padding: in the streaming pipeline these CTAs may share an SM with a GEMM CTA (whose few
+        // threads leave the issue slots free); the recurrence CTAs fill their SMs' register file, so nothing lands there.
+        const size_t pad = getenv("GASR_CTC_PAD") ? (size_t)atoi(getenv("GASR_CTC_PAD")) : 0;
         const char *mw_env = getenv("GASR_CTC_MW");
         const int mw = mw_env ? atoi(mw_env) : 8;
 #define GASR_CTA2(DOM, BM)                                                                          \
     do {                                                                                            \
-        if (mw == 4) ctc_beam_cta2_kernel<DOM, BM, 4><<<a.N, 160, pad, st>>>(p);                    \
-        else ctc_beam_cta2_kernel<DOM, BM, 8><<<a.N, 288, pad, st>>>(p);                            \
+        if (mw == 4) ctc_beam_cta2_kernel<DOM, BM, 4><<<a.N, 192, pad, st>>>(p);                    \
+        else if (mw == 16) ctc_beam_cta2_kernel<DOM, BM, 16><<<a.N, 576, pad, st>>>(p);             \
+        else ctc_beam_cta2_kernel<DOM, BM, 8><<<a.N, 320, pad, st>>>(p);                            \
     } while (0)
         if (a.domain == GASR_DOMAIN_LOG) {
             if (a.beam <= 16) GASR_CTA2(1, 16); else GASR_CTA2(1, 32);
