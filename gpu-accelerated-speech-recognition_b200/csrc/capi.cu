@@ -487,7 +487,7 @@ struct gasr_asr {
     int *host_words = nullptr, *host_words_dev = nullptr;   // mapped host memory: [0] go, [1] error
     int epoch = 0;
     gasr::XsMaps xs_maps;
-    cudaEvent_t ev_go = nullptr, ev_r0 = nullptr, ev_r1 = nullptr, ev_g0 = nullptr, ev_g1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
+    cudaEvent_t ev_cp = nullptr, ev_go = nullptr, ev_r0 = nullptr, ev_r1 = nullptr, ev_g0 = nullptr, ev_g1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
     std::vector<cudaEvent_t> sync_ev;           // cross-stream dependencies (no timing)
     std::vector<cudaEvent_t> t0_ev, t1_ev;      // per-launch timing pairs
     std::vector<int> t_tag;
@@ -563,7 +563,7 @@ int gasr_asr_create(gasr_ctx *ctx, const gasr_asr_config *cfg, const char *vocab
             rnn_stream_supported(ctx, H, N, L) && H % 128 == 0 && ((size_t)cfg->T * N) % 128 == 0 && ctx->sm_count >= 132) {
             a->stream_fpb = 128 / N;
             a->stream_blocks = (int)(rows / 128);
-            a->stream_gemm_ctas = 20;
+            a->stream_gemm_ctas = 24;
             if (const char *e = getenv("GASR_STREAM_GEMM_CTAS")) a->stream_gemm_ctas = atoi(e);
             auto allocv = [&](void **p, size_t bytes) { if (st == GASR_OK) st = gasr_malloc_device(ctx, bytes, p); };
             allocv(&a->x_planes, xproj_tc_a_bytes((int)rows, cfg->in) + 1024);
@@ -580,6 +580,7 @@ int gasr_asr_create(gasr_ctx *ctx, const gasr_asr_config *cfg, const char *vocab
                 for (cudaEvent_t *e : {&a->ev_r0, &a->ev_r1, &a->ev_g0, &a->ev_g1, &a->ev_d0, &a->ev_d1})
                     if (cudaEventCreate(e) != cudaSuccess) st = GASR_ERR_CUDA;
                 if (cudaEventCreateWithFlags(&a->ev_go, cudaEventDisableTiming) != cudaSuccess) st = GASR_ERR_CUDA;
+                if (cudaEventCreateWithFlags(&a->ev_cp, cudaEventDisableTiming) != cudaSuccess) st = GASR_ERR_CUDA;
             }
             a->stream_ok = st == GASR_OK;
         }
@@ -602,7 +603,7 @@ int gasr_asr_destroy(gasr_asr *a) {
     for (void *p : a->h_planes) if (p) gasr_free_device(ctx, p);
     for (void *p : {a->x_planes, a->fc_wbuf, (void *)a->fc_b_pad, (void *)a->flags}) if (p) gasr_free_device(ctx, p);
     if (a->host_words) cudaFreeHost(a->host_words);
-    for (cudaEvent_t e : {a->ev_go, a->ev_r0, a->ev_r1, a->ev_g0, a->ev_g1, a->ev_d0, a->ev_d1}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {a->ev_cp, a->ev_go, a->ev_r0, a->ev_r1, a->ev_g0, a->ev_g1, a->ev_d0, a->ev_d1}) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : a->sync_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : a->t0_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : a->t1_ev) cudaEventDestroy(e);
@@ -788,7 +789,8 @@ static int asr_run_pipelined(gasr_asr *a, const float *x_dev, char *out_paths, i
 // Streaming path: three persistent kernels -- the layer stack's recurrence (rnn_stream.cu), the projection / output
 // layer GEMM (xproj_stream.cu) and the decoder (ctc_beam.cu, CTA kernel) -- run concurrently for the whole sequence and
 // hand 128-row blocks (a few frames of the batch) to each other through counters in HBM.
-static int asr_run_streaming(gasr_asr *a, const float *x_dev, char *out_paths, int *out_lens, float *out_scores) {
+static int asr_run_streaming(gasr_asr *a, const float *x_dev, const float *x_host, char *out_paths, int *out_lens,
+                             float *out_scores) {
     gasr_ctx *ctx = a->ctx;
     const gasr_asr_config &c = a->cfg;
     const int T = c.T, N = c.N, H = c.H, L = c.L, nb = a->stream_blocks, rows = T * N;
@@ -811,9 +813,27 @@ static int asr_run_streaming(gasr_asr *a, const float *x_dev, char *out_paths, i
         GASR_TRY(launch_xproj_stream(ctx, a->xs_maps, prep, 0, gemm_st));
     }
     GASR_CUDA(cudaMemsetAsync(a->flags, 0, a->flags_bytes, main_st));
-    GASR_CUDA(cudaMemsetAsync(x_ready, 0xff, sizeof(unsigned) * nb, main_st));
-    GASR_TRY(xproj_tc_split_rows(ctx, x_dev, c.in, rows, c.in, a->x_planes, main_st));
-    GASR_CUDA(cudaEventRecord(a->ev_go, main_st));
+    if (x_host == nullptr) {
+        GASR_CUDA(cudaMemsetAsync(x_ready, 0xff, sizeof(unsigned) * nb, main_st));
+        GASR_TRY(xproj_tc_split_rows(ctx, x_dev, c.in, rows, c.in, a->x_planes, main_st));
+        GASR_CUDA(cudaEventRecord(a->ev_go, main_st));
+    } else {
+        // host input: the batch is copied in slices on the copy stream; each slice is split into its bf16 planes and
+        // then marked ready, so the pipeline starts after the first slice and the rest of the copy hides behind it
+        GASR_CUDA(cudaEventRecord(a->ev_go, main_st));
+        cudaStream_t cp_st = ctx->side[2];
+        GASR_CUDA(cudaStreamWaitEvent(cp_st, a->ev_go, 0));
+        const int slices = nb >= 16 ? 16 : 1;
+        for (int sidx = 0; sidx < slices; sidx++) {
+            const int b0 = (int)((long long)nb * sidx / slices), b1 = (int)((long long)nb * (sidx + 1) / slices);
+            if (b1 == b0) continue;
+            const size_t r0 = (size_t)b0 * 128, nr = (size_t)(b1 - b0) * 128;
+            GASR_CUDA(cudaMemcpyAsync(a->x_dev + r0 * c.in, x_host + r0 * c.in, sizeof(float) * nr * c.in, cudaMemcpyHostToDevice, cp_st));
+            GASR_TRY(xproj_tc_split_rows_range(ctx, a->x_dev, c.in, rows, (int)r0, (int)nr, c.in, a->x_planes, cp_st));
+            GASR_CUDA(cudaMemsetAsync(x_ready + b0, 0xff, sizeof(unsigned) * (size_t)(b1 - b0), cp_st));
+        }
+        GASR_CUDA(cudaEventRecord(a->ev_cp, cp_st));
+    }
     const bool dbg = getenv("GASR_STREAM_DEBUG") != nullptr;
     if (dbg) { GASR_CUDA(cudaStreamSynchronize(main_st)); fprintf(stderr, "[stream] prep ok\n"); }
 
@@ -910,6 +930,24 @@ static int asr_run_streaming(gasr_asr *a, const float *x_dev, char *out_paths, i
         fprintf(stderr, "[stream] gemm alone: %.3f ms, %d CTAs:", ms, gemm_ctas);
         for (int tg = 0; tg <= L; tg++) fprintf(stderr, " target %d -> %d CTAs", tg, xp.target[tg].nctas);
         fprintf(stderr, " (error word %d)\n", a->host_words[1]);
+        if (getenv("GASR_DEBUG_REC_ALONE")) {
+            // the recurrence alone: every projection block is already counted complete
+            a->epoch += 1; rp.epoch = a->epoch;
+            const int variant = atoi(getenv("GASR_DEBUG_REC_ALONE"));
+            for (int l = 0; l < L; l++) {
+                if (variant & 2) rp.layer[l].h_done = nullptr;
+                if (variant & 4) rp.layer[l].xp_ready = nullptr;
+                if (variant & 8) { rp.layer[l].out_hi = nullptr; rp.layer[l].out_lo = nullptr; rp.layer[l].out = a->hiddens[l]; }
+            }
+            GASR_CUDA(cudaMemsetAsync(misc, 0, 64, rec_st));
+            GASR_CUDA(cudaMemsetAsync(h_done, 0, sizeof(unsigned) * (size_t)L * nb, rec_st));
+            GASR_CUDA(cudaEventRecord(a->ev_r0, rec_st));
+            GASR_TRY(launch_rnn_stream(ctx, rp, H, rec_st));
+            GASR_CUDA(cudaEventRecord(a->ev_r1, rec_st));
+            GASR_CUDA(cudaStreamSynchronize(rec_st));
+            cudaEventElapsedTime(&ms, a->ev_r0, a->ev_r1);
+            fprintf(stderr, "[stream] recurrence alone (all layers, inputs ready): %.3f ms (error word %d)\n", ms, a->host_words[1]);
+        }
         return GASR_ERR_CUDA;
     }
     GASR_CUDA(cudaStreamWaitEvent(gemm_st, a->ev_go, 0));
@@ -931,6 +969,7 @@ static int asr_run_streaming(gasr_asr *a, const float *x_dev, char *out_paths, i
     GASR_CUDA(cudaStreamWaitEvent(main_st, a->ev_r1, 0));
     GASR_CUDA(cudaStreamWaitEvent(main_st, a->ev_g1, 0));
     GASR_CUDA(cudaStreamWaitEvent(main_st, a->ev_d1, 0));
+    if (x_host != nullptr) GASR_CUDA(cudaStreamWaitEvent(main_st, a->ev_cp, 0));
     GASR_CUDA(cudaStreamSynchronize(main_st));
     if (a->host_words[1] != 0) {
         set_error("streaming pipeline: watchdog fired (code %d): a persistent kernel waited too long for its producer", a->host_words[1]);
@@ -950,7 +989,7 @@ int gasr_asr_run_device(gasr_asr *a, const float *x_dev, char *out_paths, int *o
     GASR_ENTER(ctx);
     GASR_CHECK(a->have_weights, "gasr_asr_run: weights not set");
     GASR_CHECK(x_dev && out_paths && out_lens && out_scores, "gasr_asr_run: null argument");
-    if (a->stream_ok) return asr_run_streaming(a, x_dev, out_paths, out_lens, out_scores);
+    if (a->stream_ok) return asr_run_streaming(a, x_dev, nullptr, out_paths, out_lens, out_scores);
     if (a->chunk > 0) return asr_run_pipelined(a, x_dev, out_paths, out_lens, out_scores);
     return asr_run_sequential(a, x_dev, out_paths, out_lens, out_scores);
 }
@@ -961,6 +1000,9 @@ int gasr_asr_run_host(gasr_asr *a, const float *x_host, char *out_paths, int *ou
     GASR_ENTER(ctx);
     GASR_CHECK(x_host != nullptr, "gasr_asr_run_host: null input");
     const gasr_asr_config &c = a->cfg;
+    GASR_CHECK(a->have_weights, "gasr_asr_run: weights not set");
+    GASR_CHECK(out_paths && out_lens && out_scores, "gasr_asr_run: null argument");
+    if (a->stream_ok) return asr_run_streaming(a, a->x_dev, x_host, out_paths, out_lens, out_scores);
     GASR_CUDA(cudaMemcpyAsync(a->x_dev, x_host, sizeof(float) * (size_t)c.T * c.N * c.in, cudaMemcpyHostToDevice,
                               ctx->stream));
     return gasr_asr_run_device(a, a->x_dev, out_paths, out_lens, out_scores);

@@ -87,6 +87,8 @@ size_t xproj_tc_a_bytes(int M, int K);      // scratch for the bf16 hi/lo planes
 size_t xproj_tc_w_bytes(int K, int N);      // prepared (transposed, split) weights
 int xproj_tc_prepare_weights(gasr_ctx *ctx, const float *W, int K, int N, void *wbuf, cudaStream_t st);
 int xproj_tc_split_rows(gasr_ctx *ctx, const float *A, int lda, int M, int K, void *abuf, cudaStream_t st);
+int xproj_tc_split_rows_range(gasr_ctx *ctx, const float *A, int lda, int M_total, int row0, int nrows, int K, void *abuf,
+                              cudaStream_t st);
 int launch_xproj_tc(gasr_ctx *ctx, const float *A, int lda, int M, int K, int N, const void *wbuf, void *abuf,
                     const float *bias, float *C, int ldc, int precision, cudaStream_t st);
 

@@ -35,6 +35,7 @@ constexpr int RS_NB = 16;                  // utterances per cluster
 constexpr int RS_SUB = 8;                  // utterances per sub-batch (MMA N)
 constexpr int RS_HC = 64;                  // hidden columns per CTA
 constexpr int RS_MATH_WARPS = 8;
+constexpr int RS_SIGNAL_BLOCKS = 2;        // progress is published once per this many blocks
 constexpr int RS_THREADS = 32 * RS_MATH_WARPS;
 constexpr unsigned long long RS_TIMEOUT_NS = 2000000000ull;   // watchdog for every spin on a flag
 
@@ -224,6 +225,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_stream_kernel(const RnnStre
     const uint32_t bar0 = sbase + LT::OFF_BAR;
     const int r0 = (lane >> 4) * (CS / 2);               // lanes 0-15 serve the first half of the cluster, 16-31 the second
     uint32_t phase_bits = 0;                             // bit (sub*2+par): parity of the next phase to wait for
+    int pend_hi = -1;                                    // lane 0: highest block whose completion this warp still has to publish
 
     cluster.sync();
     if (p.started != nullptr && tid == 0) {
@@ -284,6 +286,11 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_stream_kernel(const RnnStre
             const float a0 = kh == 0 ? c[0] + o.x : o.x + c[2];
             const float a1 = kh == 0 ? c[1] + o.y : o.y + c[3];
             const float v0 = tanhf((sub ? xc10 : xc00) + a0), v1 = tanhf((sub ? xc11 : xc01) + a1);
+            if (sub == 0 && pend_hi >= 0) {        // (lane 0 of one warp per CTA, once per RS_SIGNAL_BLOCKS blocks)
+                __threadfence();
+                for (int b2 = pend_hi - (RS_SIGNAL_BLOCKS - 1); b2 <= pend_hi; b2++) atomicAdd(L.h_done + b2, 1u);
+                pend_hi = -1;
+            }
             // ---- publish: fp32 output, bf16 planes, DSMEM all-gather ------------------------------------------------
             if (out_base != nullptr) {
                 if (vmask & (sub ? 4u : 1u)) out_base[ooff + sub * ldo8] = v0;
@@ -309,14 +316,23 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_stream_kernel(const RnnStre
         }
         ooff += ostep;
         poff += pstep;
-        // progress: the warp that completes a block last makes the CTA's outputs visible (fence) and counts the block
+        // progress: the warp that completes a block last owes the consumers a fence + count for it.  The fence waits for
+        // the CTA's outstanding stores, so it is DEFERRED to the middle of the next step (pend_hi), when those stores have
+        // long been acknowledged, and issued once per RS_SIGNAL_BLOCKS blocks.
         if (L.h_done != nullptr && ((s + 1) % fpb == 0 || !more)) {
             __syncwarp();
             if (lane == 0) {
                 __threadfence_block();
                 const int blk = s / fpb;
                 const int last = (atomicAdd(const_cast<int *>(ctl + (blk & 1)), 1) & (RS_MATH_WARPS - 1)) == RS_MATH_WARPS - 1;
-                if (last) { __threadfence(); atomicAdd(L.h_done + blk, 1u); }
+                if (last && ((blk + 1) % RS_SIGNAL_BLOCKS == 0 || !more)) {
+                    pend_hi = blk;
+                    if (!more) {
+                        __threadfence();
+                        for (int b2 = blk - blk % RS_SIGNAL_BLOCKS; b2 <= blk; b2++) atomicAdd(L.h_done + b2, 1u);
+                        pend_hi = -1;
+                    }
+                }
             }
         }
     }

@@ -236,6 +236,21 @@ int xproj_tc_split_rows(gasr_ctx *ctx, const float *A, int lda, int M, int K, vo
     return GASR_OK;
 }
 
+// rows [row0, row0 + nrows) of fp32 A[M, K] -> the same rows of the bf16 hi/lo planes of a full-size abuf (M_total rows)
+int xproj_tc_split_rows_range(gasr_ctx *ctx, const float *A, int lda, int M_total, int row0, int nrows, int K, void *abuf,
+                              cudaStream_t st) {
+    const int Kp = ceil_div(K, TC_BK) * TC_BK;
+    __nv_bfloat16 *a_hi = static_cast<__nv_bfloat16 *>(abuf) + (size_t)row0 * Kp;
+    __nv_bfloat16 *a_lo = reinterpret_cast<__nv_bfloat16 *>(static_cast<unsigned char *>(abuf) + xproj_tc_a_bytes(M_total, K) / 2) + (size_t)row0 * Kp;
+    const size_t total = (size_t)nrows * (Kp / 2);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
+    split_rows_kernel<<<blocks, 256, 0, st>>>(A + (size_t)row0 * lda, lda, nrows, K, Kp, a_hi, a_lo);
+    GASR_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return GASR_OK;
+}
+
 // C[M, N] = A[M, K] * W + bias with W prepared by xproj_tc_prepare_weights; abuf is scratch of xproj_tc_a_bytes(M, K).
 int launch_xproj_tc(gasr_ctx *ctx, const float *A, int lda, int M, int K, int N, const void *wbuf, void *abuf,
                     const float *bias, float *C, int ldc, int precision, cudaStream_t st) {
