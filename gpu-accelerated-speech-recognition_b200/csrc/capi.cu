@@ -813,6 +813,8 @@ static int asr_run_streaming(gasr_asr *a, const float *x_dev, const float *x_hos
         GASR_TRY(launch_xproj_stream(ctx, a->xs_maps, prep, 0, gemm_st));
     }
     GASR_CUDA(cudaMemsetAsync(a->flags, 0, a->flags_bytes, main_st));
+    GASR_TRY(ctc_decode_upload_vocab(ctx, ca, main_st));       // before the input copy occupies the copy engine
+    ca.vocab_resident = true;
     if (x_host == nullptr) {
         GASR_CUDA(cudaMemsetAsync(x_ready, 0xff, sizeof(unsigned) * nb, main_st));
         GASR_TRY(xproj_tc_split_rows(ctx, x_dev, c.in, rows, c.in, a->x_planes, main_st));

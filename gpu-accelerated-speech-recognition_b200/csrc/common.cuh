@@ -110,8 +110,10 @@ struct CtcArgs {
     int t0 = 0, t1 = 0;   // frames [t0, t1) only (t1 = 0: all T); the beam is parked in the ctx workspace between chunks
     // streaming pipeline: scores of frame t may be read once lp_ready[t / lp_fpb] >= lp_need (device counters)
     const unsigned *lp_ready = nullptr; int lp_need = 0, lp_fpb = 1; int *error = nullptr; volatile unsigned *abort = nullptr;
+    bool vocab_resident = false;   // the vocabulary was uploaded by ctc_decode_upload_vocab
 };
 int ctc_decode_reserve(gasr_ctx *ctx, const CtcArgs &a);                  // allocations only (device-synchronising)
+int ctc_decode_upload_vocab(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st);
 int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st);   // enqueue kernel + D2H into pinned staging
 int ctc_decode_finish(gasr_ctx *ctx, const CtcArgs &a);                    // after stream sync: unpack to caller buffers
 

@@ -113,6 +113,7 @@ struct CtcParams {
     int *parent;         // [N, cap]
     int *meta;           // [N, cap]  depth << 8 | vocab id of the node's last label
     int *child;          // [N, cap, Vp] 0 = absent
+    int *anc;            // [N, cap] skip pointer: the ancestor at the last multiple-of-32 depth below the node's own (cta2 kernel)
     char *out_paths;     // [N, nbest, max_len]
     int *out_lens;       // [N, nbest]
     float *out_scores;   // [N, nbest]
@@ -1492,13 +1493,14 @@ struct Cta2Beam {
     int sel_m[2];
     unsigned char rel[2][BMAX][BMAX];
     unsigned cand[BMAX][32];
-    unsigned ckey[128];
+    alignas(16) unsigned ckey[128];
     unsigned surv_key[128];
-    int surv_iv[128];
+    unsigned short surv_iv[128];
     float lpring[2][32];
     int order[2][32], rankof[2][32];
     unsigned theta;
     int ns, nodes;
+    int sanc[2][BMAX];                  // trie warp: skip pointer of each kept state's node
     unsigned char cellmap[BMAX * 32];   // (parent rank, score rank) -> probe cell, 255 = none (copied from the parameters)
 };
 
@@ -1521,6 +1523,7 @@ __global__ void __launch_bounds__(MW * 32 + 64) ctc_beam_cta2_kernel(const CtcPa
 
     int *parent = p.parent + (size_t)utt * p.cap;
     int *meta = p.meta + (size_t)utt * p.cap;
+    int *anc = p.anc + (size_t)utt * p.cap;
     int *child = p.child + (size_t)utt * p.cap * Vp;
     const float *S = p.scores + (size_t)utt * p.ld;
     const size_t frame_stride = (size_t)p.N * p.ld;
@@ -1531,12 +1534,13 @@ __global__ void __launch_bounds__(MW * 32 + 64) ctc_beam_cta2_kernel(const CtcPa
     if (tid < 128) cb.ckey[tid] = 0u;
     for (int i = tid; i < BMAX * 32; i += MT + 64) cb.cellmap[i] = p.cellmap[i];
     if (tid == 0) {
-        parent[0] = -1; meta[0] = 0xff;
+        parent[0] = -1; meta[0] = 0xff; anc[0] = 0;
         cb.sc[0][0] = DOMAIN ? 0.0f : 1.0f;
         cb.node[0][0] = 0; cb.depth[0][0] = 0; cb.pk[0][0] = 0xff | (1 << 8);
         cb.rel[0][0][0] = REL_EQ;
-        cb.nodes = 1; cb.theta = 0u; cb.ns = 0;
+        cb.nodes = 1; cb.theta = 0u; cb.ns = 0; cb.sanc[0][0] = 0;
     }
+
 
     if (w == MW) {
         // =============================== fetch warp: log-probabilities one frame ahead ===============================
@@ -1591,21 +1595,24 @@ __global__ void __launch_bounds__(MW * 32 + 64) ctc_beam_cta2_kernel(const CtcPa
         int cur = 0, kept = 1;
         for (int t = 0; t < T; t++) {
             cta2_bar_all<MW>();                              // frame t's selection is visible; my previous trie work is done
-            // ---- trie: the selected candidates become nodes (lookup, allocate on a miss) ----
+            // ---- trie: the selected candidates become nodes (child-table lookup, allocation on a miss); this warp has
+            // a whole frame for the global-memory round trip
             const int nxt = cur ^ 1, sb = t & 1;
             const int m = cb.sel_m[sb];
             bool need_new = false;
-            int nd = 0, pn = 0, dp = 0, v = 0;
+            int nd = 0, pn = 0, dp = 0, v = 0, an = 0;
             if (lane < m) {
                 const int i = cb.seli[sb][lane];
                 v = cb.selv[sb][lane];
                 const int pki = cb.pk[cur][i];
                 const int ebi = (pki >> 8) & 1, lasti = pki & 0xff;
-                if (v == blank || (ebi == 0 && v == lasti)) nd = cb.node[cur][i];
+                if (v == blank || (ebi == 0 && v == lasti)) { nd = cb.node[cur][i]; an = cb.sanc[cur][i]; }
                 else {
                     pn = cb.node[cur][i]; dp = cb.depth[cur][i] + 1;
                     nd = child[(size_t)pn * Vp + v];
                     need_new = nd == 0;
+                    an = ((dp - 1) & 31) == 0 ? pn : cb.sanc[cur][i];      // a parent at a multiple-of-32 depth starts a new block
+                    if (!need_new) an = anc[nd];                            // re-created prefix (rare): its own record
                 }
             }
             const unsigned nb = __ballot_sync(FULL, need_new);
@@ -1614,13 +1621,14 @@ __global__ void __launch_bounds__(MW * 32 + 64) ctc_beam_cta2_kernel(const CtcPa
                 nd = nodes + __popc(nb & ((1u << lane) - 1u));
                 parent[nd] = pn;
                 meta[nd] = (dp << 8) | v;
+                anc[nd] = an;
                 child[(size_t)pn * Vp + v] = nd;
                 int4 *row = reinterpret_cast<int4 *>(child + (size_t)nd * Vp);
                 for (int q = 0; q < Vp / 4; q++) row[q] = make_int4(0, 0, 0, 0);
             }
-            if (lane < m) cb.node[nxt][lane] = nd;
-            __syncwarp();
+            if (lane < m) { cb.node[nxt][lane] = nd; cb.sanc[nxt][lane] = an; }
             if (lane == 0) cb.nodes = nodes + __popc(nb);
+            __syncwarp();
             kept = m;
             cur = nxt;
         }
@@ -1628,23 +1636,48 @@ __global__ void __launch_bounds__(MW * 32 + 64) ctc_beam_cta2_kernel(const CtcPa
         // ---- result (CTCBeamSearch.cu:290-298): the aux warp owns the trie, so it writes the paths ----
         cta2_bar_all<MW>();                                  // final scores / depths / pk are in place
         if (lane == 0 && p.out_counts) p.out_counts[utt] = kept;
-        for (int r = lane; r < p.nbest; r += 32) {
+        // the path of a kept state is read off the trie leaf-to-root; the skip pointers cut the chain of dependent loads
+        // from depth to depth / 32 + 32: lane 0 collects the 32-block end nodes, then every lane walks one block
+        int *ends = reinterpret_cast<int *>(&cb.cand[0][0]);          // the beam is final: the candidate matrix is free
+        constexpr int ENDS_CAP = BMAX * 32;
+        for (int r = 0; r < p.nbest; r++) {
             char *out = p.out_paths + ((size_t)utt * p.nbest + r) * p.max_len;
             int len = 0;
             float scv = 0.0f;
             if (r < kept) {
-                int nd = cb.node[cur][r];
+                const int nd0 = cb.node[cur][r];
                 const int dpt = cb.depth[cur][r];
                 len = dpt;
-                if (T == 1 && ((cb.pk[cur][r] >> 8) & 1)) { if (len < p.max_len) out[len] = vch[blank]; len += 1; }
-                for (int pos = dpt - 1; pos >= 0; pos--) {
-                    if (pos < p.max_len) out[pos] = vch[meta[nd] & 0xff];
-                    nd = parent[nd];
+                if (T == 1 && ((cb.pk[cur][r] >> 8) & 1)) { if (lane == 0 && len < p.max_len) out[len] = vch[blank]; len += 1; }
+                const int nblk = (dpt + 31) >> 5;
+                if (nblk <= ENDS_CAP) {
+                    if (lane == 0) {
+                        int nd = nd0;
+                        for (int j = nblk - 1; j >= 0; j--) { ends[j] = nd; nd = anc[nd]; }
+                    }
+                    __syncwarp();
+                    for (int j = lane; j < nblk; j += 32) {
+                        int nd = ends[j];
+                        const int top = min(dpt, 32 * (j + 1));
+                        for (int pos = top - 1; pos >= 32 * j; pos--) {
+                            if (pos < p.max_len) out[pos] = vch[meta[nd] & 0xff];
+                            nd = parent[nd];
+                        }
+                    }
+                    __syncwarp();
+                } else if (lane == 0) {
+                    int nd = nd0;
+                    for (int pos = dpt - 1; pos >= 0; pos--) {
+                        if (pos < p.max_len) out[pos] = vch[meta[nd] & 0xff];
+                        nd = parent[nd];
+                    }
                 }
                 scv = cb.sc[cur][r];
             }
-            p.out_lens[(size_t)utt * p.nbest + r] = len;
-            p.out_scores[(size_t)utt * p.nbest + r] = scv;
+            if (lane == 0) {
+                p.out_lens[(size_t)utt * p.nbest + r] = len;
+                p.out_scores[(size_t)utt * p.nbest + r] = scv;
+            }
         }
         return;
     }
@@ -1669,40 +1702,77 @@ __global__ void __launch_bounds__(MW * 32 + 64) ctc_beam_cta2_kernel(const CtcPa
 
         // ================= phase B: merged candidates (+ probe cells) =================
         if (!last_frame) {
+            // this warp's rows (parents w, w + MW, ...) are processed together, stage by stage and without divergent
+            // branches, so their dependent shared-memory loads and the two merges overlap
+            constexpr int RPWB = (BMAX + MW - 1) / MW;
             const int jr = cb.rankof[slot][lane];
-            for (int i = w; i < k; i += MW) {
-                const int pki = pk[i], twi = cb.tw[i];
-                const int ebi = (pki >> 8) & 1, lasti = pki & 0xff;
+            int ri[RPWB], pki[RPWB], twi[RPWB], m0[RPWB], m1[RPWB];
+            unsigned ab0[RPWB];
+            bool have[RPWB];
+#pragma unroll
+            for (int q = 0; q < RPWB; q++) {
+                const int i = w + MW * q;
+                have[q] = i < k;
+                ri[q] = have[q] ? i : 0;
+                pki[q] = pk[ri[q]]; twi[q] = cb.tw[ri[q]]; ab0[q] = cb.abs0[ri[q]];
+                m0[q] = cb.p0[ri[q]]; m1[q] = cb.p1[ri[q]];
+            }
+            int pm0[RPWB];
+#pragma unroll
+            for (int q = 0; q < RPWB; q++) pm0[q] = pk[m0[q] >= 0 ? m0[q] : 0];
+            int a0[RPWB], a1[RPWB], a2[RPWB];
+            bool keep[RPWB];
+#pragma unroll
+            for (int q = 0; q < RPWB; q++) {
+                const int i = ri[q];
+                const int ebi = (pki[q] >> 8) & 1, lasti = pki[q] & 0xff;
                 const bool is_stay = (ebi == 0 && lane == lasti);
                 const bool is_blank = (lane == blank);
-                const bool member = twi >= 0 && (is_blank || ebi == 0 || lane != lasti);
-                const bool dead = (member && twi < i) || (!is_blank && ((cb.abs0[i] >> lane) & 1u));
-                // addends in canonical (parent rank) order; missing ones contribute the neutral element
-                int a0 = i, a1 = kNone, a2 = kNone;
-                if (is_stay) {
-                    int m0 = cb.p0[i], m1 = cb.p1[i], m2 = i, tmp;
-                    if (m0 >= 0 && (pk[m0] & 0xff) == lasti) m0 = kNone;
-                    if (m0 > m1) { tmp = m0; m0 = m1; m1 = tmp; }
-                    if (m1 > m2) { tmp = m1; m1 = m2; m2 = tmp; }
-                    if (m0 > m1) { tmp = m0; m0 = m1; m1 = tmp; }
-                    // (kNone = -1 sorts first) -> pack the valid ones to the front
-                    if (m0 >= 0) { a0 = m0; a1 = m1; a2 = m2; }
-                    else if (m1 >= 0) { a0 = m1; a1 = m2; }
-                    else a0 = m2;
-                } else if (member && twi > i) a1 = twi;
-                float acc = comb<DOMAIN>(sc[a0], lp);
-                if (__any_sync(FULL, a1 >= 0)) {
-                    const float s1 = a1 >= 0 ? comb<DOMAIN>(sc[a1], lp) : NEUTRAL;
-                    acc = mrg_bf<DOMAIN>(acc, s1);
-                    if (__any_sync(FULL, a2 >= 0)) {
-                        const float s2 = a2 >= 0 ? comb<DOMAIN>(sc[a2], lp) : NEUTRAL;
-                        acc = mrg_bf<DOMAIN>(acc, s2);
-                    }
+                const bool member = twi[q] >= 0 && (is_blank || ebi == 0 || lane != lasti);
+                const bool dead = (member && twi[q] < i) || (!is_blank && ((ab0[q] >> lane) & 1u));
+                // "stay": addends among {(P,0) if last(P) != last, (P,1), this state}, ascending rank; kNone = -1 sorts first
+                int s0 = (m0[q] >= 0 && (pm0[q] & 0xff) == lasti) ? kNone : m0[q], s1 = m1[q], s2 = i;
+                int lo = min(s0, s1), hi = max(s0, s1);
+                s0 = lo; s1 = hi;
+                lo = min(s1, s2); hi = max(s1, s2);
+                s1 = lo; s2 = hi;
+                lo = min(s0, s1); hi = max(s0, s1);
+                s0 = lo; s1 = hi;
+                const int t0 = s0 >= 0 ? s0 : (s1 >= 0 ? s1 : s2);
+                const int t1 = s0 >= 0 ? s1 : (s1 >= 0 ? s2 : kNone);
+                const int t2 = s0 >= 0 ? s2 : kNone;
+                const bool twin_owner = member && twi[q] > i;
+                a0[q] = is_stay ? t0 : i;
+                a1[q] = is_stay ? t1 : (twin_owner ? twi[q] : kNone);
+                a2[q] = is_stay ? t2 : kNone;
+                if (!have[q]) { a1[q] = kNone; a2[q] = kNone; }
+                keep[q] = have[q] && active && (is_stay || !dead);
+            }
+            float acc[RPWB], x1[RPWB], x2[RPWB];
+            bool need1 = false, need2 = false;
+#pragma unroll
+            for (int q = 0; q < RPWB; q++) {
+                acc[q] = comb<DOMAIN>(sc[a0[q]], lp);
+                x1[q] = a1[q] >= 0 ? comb<DOMAIN>(sc[a1[q] >= 0 ? a1[q] : 0], lp) : NEUTRAL;
+                x2[q] = a2[q] >= 0 ? comb<DOMAIN>(sc[a2[q] >= 0 ? a2[q] : 0], lp) : NEUTRAL;
+                need1 |= a1[q] >= 0; need2 |= a2[q] >= 0;
+            }
+            if (__any_sync(FULL, need1)) {                // merging the neutral element returns the other operand bit-exactly
+#pragma unroll
+                for (int q = 0; q < RPWB; q++) acc[q] = mrg_bf<DOMAIN>(acc[q], x1[q]);
+                if (__any_sync(FULL, need2)) {
+#pragma unroll
+                    for (int q = 0; q < RPWB; q++) acc[q] = mrg_bf<DOMAIN>(acc[q], x2[q]);
                 }
-                const unsigned key = (active && (is_stay || !dead)) ? f2ord(acc) : 0u;
-                cb.cand[i][lane] = key;
-                const int c = cb.cellmap[i * 32 + jr];
-                if (c != 255) cb.ckey[c] = key;
+            }
+#pragma unroll
+            for (int q = 0; q < RPWB; q++) {
+                if (have[q]) {
+                    const unsigned key = keep[q] ? f2ord(acc[q]) : 0u;
+                    cb.cand[ri[q]][lane] = key;
+                    const int c = cb.cellmap[ri[q] * 32 + jr];
+                    if (c != 255) cb.ckey[c] = key;
+                }
             }
         } else if (w == 0) {
             const float lpb = __shfl_sync(FULL, lp, blank);
@@ -1768,12 +1838,17 @@ __global__ void __launch_bounds__(MW * 32 + 64) ctc_beam_cta2_kernel(const CtcPa
         {
             const int c = tid / TPC;
             const unsigned mine = cb.ckey[c];
-            const int span = NC / TPC, ob = (tid % TPC) * span;
+            constexpr int span = NC / TPC;
+            const int ob = (tid % TPC) * span;
             int cnt = 0;
-#pragma unroll 8
-            for (int o = ob; o < ob + span; o++) {
-                const unsigned x = cb.ckey[o];
-                cnt += (x > mine || (x == mine && o < c)) ? 1 : 0;
+            static_assert(span % 4 == 0, "probe cells are scanned four at a time");
+#pragma unroll
+            for (int o = 0; o < span; o += 4) {
+                const uint4 x = *reinterpret_cast<const uint4 *>(&cb.ckey[ob + o]);
+                cnt += (x.x > mine || (x.x == mine && ob + o < c)) ? 1 : 0;
+                cnt += (x.y > mine || (x.y == mine && ob + o + 1 < c)) ? 1 : 0;
+                cnt += (x.z > mine || (x.z == mine && ob + o + 2 < c)) ? 1 : 0;
+                cnt += (x.w > mine || (x.w == mine && ob + o + 3 < c)) ? 1 : 0;
             }
 #pragma unroll
             for (int off = 1; off < TPC; off <<= 1) cnt += __shfl_xor_sync(FULL, cnt, off);
@@ -1808,7 +1883,7 @@ __global__ void __launch_bounds__(MW * 32 + 64) ctc_beam_cta2_kernel(const CtcPa
             for (int q = 0; q < RPW; q++) {
                 const int pos = base + __popc(masks4[q] & ((1u << lane) - 1u));
                 if (((masks4[q] >> lane) & 1u) && pos < 128) {
-                    cb.surv_key[pos] = keys4[q]; cb.surv_iv[pos] = ((w + MW * q) << 8) | lane;
+                    cb.surv_key[pos] = keys4[q]; cb.surv_iv[pos] = (unsigned short)(((w + MW * q) << 8) | lane);
                 }
                 base += __popc(masks4[q]);
             }
@@ -1824,23 +1899,27 @@ __global__ void __launch_bounds__(MW * 32 + 64) ctc_beam_cta2_kernel(const CtcPa
         if (ns <= 128) {
             m = ns < B ? ns : B;
             // TPS threads share a survivor (fewer when the bound was loose and survivors are many)
-            const int tps = ns <= 64 ? TPS : TPS / 2;
-            const int sidx = tid / tps, half = tid % tps;
+            // threads per survivor: as many as fit (a power of two, at most 16, at least MT / 128)
+            constexpr int TS_MIN = MT == 128 ? 0 : MT == 256 ? 1 : 2;
+            int tshift = TS_MIN;
+            for (int cap = 64; cap >= ns && tshift < 4; cap >>= 1) tshift++;
+            const int tps = 1 << tshift;
+            const int sidx = tid >> tshift, half = tid & (tps - 1);
             int rank = 0;
             unsigned key = 0u;
             int iv = 0;
             if (sidx < ns) {
                 key = cb.surv_key[sidx];
                 iv = cb.surv_iv[sidx];
-                const int mi = iv >> 8, mv = iv & 0xff;
-                const int ms = cand_suffix_id(mv, blank, pk[mi]);
                 for (int o = half; o < ns; o += tps) {
                     const unsigned ok = cb.surv_key[o];
-                    if (ok > key) rank++;
-                    else if (ok == key && o != sidx) {
+                    rank += ok > key ? 1 : 0;
+                    if (ok == key && o != sidx) {             // exact tie: raw-string order (rare)
                         const int oiv = cb.surv_iv[o];
                         if (t == 0) rank += oiv < iv;
                         else {
+                            const int mi = iv >> 8, mv = iv & 0xff;
+                            const int ms = cand_suffix_id(mv, blank, pk[mi]);
                             const int oi = oiv >> 8, ov = oiv & 0xff;
                             rank += cand_less_rel(rel[oi][mi], cand_suffix_id(ov, blank, pk[oi]), ms, vch) ? 1 : 0;
                         }
@@ -1848,7 +1927,7 @@ __global__ void __launch_bounds__(MW * 32 + 64) ctc_beam_cta2_kernel(const CtcPa
                 }
             }
 #pragma unroll
-            for (int off = 1; off < TPS; off <<= 1) {
+            for (int off = 1; off < 16; off <<= 1) {
                 const int other = __shfl_xor_sync(FULL, rank, off);
                 if (off < tps) rank += other;
             }
@@ -1962,7 +2041,7 @@ static size_t ctc_smem_bytes(int B, int V, int Vp, int n_pad) {
 
 struct CtcLayout {
     int Vp, n_pad, cap, threads;
-    size_t smem, off_vocab, off_parent, off_meta, off_child, off_state, state_stride, off_paths, off_lens, off_scores,
+    size_t smem, off_vocab, off_parent, off_meta, off_anc, off_child, off_state, state_stride, off_paths, off_lens, off_scores,
         off_counts, off_stats, total;
     size_t out_bytes;
 };
@@ -1980,6 +2059,7 @@ static int ctc_layout(const CtcArgs &a, CtcLayout &L) {
     L.off_vocab = o; o = align_up(o + a.V, 256);
     L.off_parent = o; o = align_up(o + sizeof(int) * (size_t)a.N * L.cap, 256);
     L.off_meta = o; o = align_up(o + sizeof(int) * (size_t)a.N * L.cap, 256);
+    L.off_anc = o; o = align_up(o + sizeof(int) * (size_t)a.N * L.cap, 256);
     L.off_child = o; o = align_up(o + sizeof(int) * (size_t)a.N * L.cap * L.Vp, 256);
     L.state_stride = align_up((sizeof(CtaBeam<32>) > sizeof(WarpBeam<32>) ? sizeof(CtaBeam<32>) : sizeof(WarpBeam<32>)) + sizeof(int4), 256);
     L.off_state = o; o = align_up(o + L.state_stride * (size_t)a.N, 256);
@@ -2003,6 +2083,16 @@ int ctc_decode_reserve(gasr_ctx *ctx, const CtcArgs &a) {
     GASR_TRY(ws_reserve(ctx, ctx->ws_ctc, L.total));
     GASR_TRY(ws_reserve(ctx, ctx->ws_out, L.out_bytes));
     GASR_TRY(pinned_reserve(ctx, L.out_bytes));
+    return GASR_OK;
+}
+
+// Upload the vocabulary ahead of the launch (CtcArgs::vocab_resident then skips it): a small pageable copy issued at
+// launch time would queue behind whatever the copy engine is busy with.
+int ctc_decode_upload_vocab(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
+    if (a.N == 0) return GASR_OK;
+    CtcLayout L;
+    ctc_layout(a, L);
+    GASR_CUDA(cudaMemcpyAsync(static_cast<unsigned char *>(ctx->ws_ctc.ptr) + L.off_vocab, a.vocab_host, a.V, cudaMemcpyHostToDevice, st));
     return GASR_OK;
 }
 
@@ -2036,7 +2126,7 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
     const bool fast = a.beam <= 32 && a.V <= 32;
     GASR_CHECK(t0 >= 0 && t0 < t1 && t1 <= a.T, "ctc_decode: bad frame range [%d, %d)", t0, t1);
     GASR_CHECK(fast || (t0 == 0 && t1 == a.T), "ctc_decode: time-chunked decoding needs beam <= 32 and vocab <= 32");
-    if (t0 == 0) GASR_CUDA(cudaMemcpyAsync(ws + L.off_vocab, a.vocab_host, a.V, cudaMemcpyHostToDevice, st));
+    if (t0 == 0 && !a.vocab_resident) GASR_CUDA(cudaMemcpyAsync(ws + L.off_vocab, a.vocab_host, a.V, cudaMemcpyHostToDevice, st));
 
     CtcParams p;
     p.scores = a.scores; p.T = a.T; p.N = a.N; p.V = a.V; p.ld = a.ld; p.beam = a.beam; p.blank = a.blank;
@@ -2044,6 +2134,7 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
     p.vocab = reinterpret_cast<const char *>(ws + L.off_vocab);
     p.parent = reinterpret_cast<int *>(ws + L.off_parent);
     p.meta = reinterpret_cast<int *>(ws + L.off_meta);
+    p.anc = reinterpret_cast<int *>(ws + L.off_anc);
     p.child = reinterpret_cast<int *>(ws + L.off_child);
     p.out_paths = reinterpret_cast<char *>(wo + L.off_paths);
     p.out_lens = reinterpret_cast<int *>(wo + L.off_lens);

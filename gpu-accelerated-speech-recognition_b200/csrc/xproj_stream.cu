@@ -22,7 +22,7 @@
 
 namespace gasr {
 
-constexpr int XS_SMEM_BYTES = TC_SMEM_BYTES + 4 * 32 * 36 * 4;   // + the epilogue's staging tiles
+constexpr int XS_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/ + 4 * 32 * 36 * 4 /*epilogue staging*/;
 constexpr unsigned long long XS_TIMEOUT_NS = 2000000000ull;
 
 __device__ __forceinline__ bool xs_mbar_try(uint32_t bar, uint32_t parity) {
@@ -89,7 +89,7 @@ xproj_stream_kernel(const __grid_constant__ XsMaps maps, const XsParams p) {
     unsigned char *gen_tiles = smem_raw + (tiles - raw);
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen_tiles + TC_STAGES * TC_STAGE_BYTES + 16 * TC_STAGES + 32);
     volatile int *abort_flag = &abort_s;
-    float *epi_stage = reinterpret_cast<float *>(gen_tiles + TC_STAGES * TC_STAGE_BYTES + 256);     // [4 warps][32][36] floats
+    float *epi_stage = reinterpret_cast<float *>(gen_tiles + TC_STAGES * TC_STAGE_BYTES + 128);     // [4 warps][32][36] floats
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
