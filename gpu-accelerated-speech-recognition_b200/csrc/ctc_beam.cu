@@ -1702,76 +1702,88 @@ __global__ void __launch_bounds__(MW * 32 + 64) ctc_beam_cta2_kernel(const CtcPa
 
         // ================= phase B: merged candidates (+ probe cells) =================
         if (!last_frame) {
-            // this warp's rows (parents w, w + MW, ...) are processed together, stage by stage and without divergent
-            // branches, so their dependent shared-memory loads and the two merges overlap
-            constexpr int RPWB = (BMAX + MW - 1) / MW;
             const int jr = cb.rankof[slot][lane];
-            int ri[RPWB], pki[RPWB], twi[RPWB], m0[RPWB], m1[RPWB];
-            unsigned ab0[RPWB];
-            bool have[RPWB];
+            if (w < MW - 1) {
+                // ---- row warps: parent rows w, w + (MW-1), ... processed together, stage by stage, branch-free.  A plain
+                // candidate is one add; only rows that own a twin pair run the merge.  The "stay" cell of a row is left to
+                // the stay warp below.
+                constexpr int RW = MW - 1;
+                constexpr int RPWB = (BMAX + RW - 1) / RW;
+                int ri[RPWB], pki[RPWB], twi[RPWB];
+                unsigned ab0[RPWB];
+                bool have[RPWB];
 #pragma unroll
-            for (int q = 0; q < RPWB; q++) {
-                const int i = w + MW * q;
-                have[q] = i < k;
-                ri[q] = have[q] ? i : 0;
-                pki[q] = pk[ri[q]]; twi[q] = cb.tw[ri[q]]; ab0[q] = cb.abs0[ri[q]];
-                m0[q] = cb.p0[ri[q]]; m1[q] = cb.p1[ri[q]];
-            }
-            int pm0[RPWB];
-#pragma unroll
-            for (int q = 0; q < RPWB; q++) pm0[q] = pk[m0[q] >= 0 ? m0[q] : 0];
-            int a0[RPWB], a1[RPWB], a2[RPWB];
-            bool keep[RPWB];
-#pragma unroll
-            for (int q = 0; q < RPWB; q++) {
-                const int i = ri[q];
-                const int ebi = (pki[q] >> 8) & 1, lasti = pki[q] & 0xff;
-                const bool is_stay = (ebi == 0 && lane == lasti);
-                const bool is_blank = (lane == blank);
-                const bool member = twi[q] >= 0 && (is_blank || ebi == 0 || lane != lasti);
-                const bool dead = (member && twi[q] < i) || (!is_blank && ((ab0[q] >> lane) & 1u));
-                // "stay": addends among {(P,0) if last(P) != last, (P,1), this state}, ascending rank; kNone = -1 sorts first
-                int s0 = (m0[q] >= 0 && (pm0[q] & 0xff) == lasti) ? kNone : m0[q], s1 = m1[q], s2 = i;
-                int lo = min(s0, s1), hi = max(s0, s1);
-                s0 = lo; s1 = hi;
-                lo = min(s1, s2); hi = max(s1, s2);
-                s1 = lo; s2 = hi;
-                lo = min(s0, s1); hi = max(s0, s1);
-                s0 = lo; s1 = hi;
-                const int t0 = s0 >= 0 ? s0 : (s1 >= 0 ? s1 : s2);
-                const int t1 = s0 >= 0 ? s1 : (s1 >= 0 ? s2 : kNone);
-                const int t2 = s0 >= 0 ? s2 : kNone;
-                const bool twin_owner = member && twi[q] > i;
-                a0[q] = is_stay ? t0 : i;
-                a1[q] = is_stay ? t1 : (twin_owner ? twi[q] : kNone);
-                a2[q] = is_stay ? t2 : kNone;
-                if (!have[q]) { a1[q] = kNone; a2[q] = kNone; }
-                keep[q] = have[q] && active && (is_stay || !dead);
-            }
-            float acc[RPWB], x1[RPWB], x2[RPWB];
-            bool need1 = false, need2 = false;
-#pragma unroll
-            for (int q = 0; q < RPWB; q++) {
-                acc[q] = comb<DOMAIN>(sc[a0[q]], lp);
-                x1[q] = a1[q] >= 0 ? comb<DOMAIN>(sc[a1[q] >= 0 ? a1[q] : 0], lp) : NEUTRAL;
-                x2[q] = a2[q] >= 0 ? comb<DOMAIN>(sc[a2[q] >= 0 ? a2[q] : 0], lp) : NEUTRAL;
-                need1 |= a1[q] >= 0; need2 |= a2[q] >= 0;
-            }
-            if (__any_sync(FULL, need1)) {                // merging the neutral element returns the other operand bit-exactly
-#pragma unroll
-                for (int q = 0; q < RPWB; q++) acc[q] = mrg_bf<DOMAIN>(acc[q], x1[q]);
-                if (__any_sync(FULL, need2)) {
-#pragma unroll
-                    for (int q = 0; q < RPWB; q++) acc[q] = mrg_bf<DOMAIN>(acc[q], x2[q]);
+                for (int q = 0; q < RPWB; q++) {
+                    const int i = w + RW * q;
+                    have[q] = i < k;
+                    ri[q] = have[q] ? i : 0;
+                    pki[q] = pk[ri[q]]; twi[q] = cb.tw[ri[q]]; ab0[q] = cb.abs0[ri[q]];
                 }
-            }
+                float acc[RPWB], x1[RPWB];
+                bool keep[RPWB], stay[RPWB];
+                bool need1 = false;
 #pragma unroll
-            for (int q = 0; q < RPWB; q++) {
-                if (have[q]) {
-                    const unsigned key = keep[q] ? f2ord(acc[q]) : 0u;
-                    cb.cand[ri[q]][lane] = key;
-                    const int c = cb.cellmap[ri[q] * 32 + jr];
-                    if (c != 255) cb.ckey[c] = key;
+                for (int q = 0; q < RPWB; q++) {
+                    const int i = ri[q];
+                    const int ebi = (pki[q] >> 8) & 1, lasti = pki[q] & 0xff;
+                    stay[q] = (ebi == 0 && lane == lasti);
+                    const bool is_blank = (lane == blank);
+                    const bool member = twi[q] >= 0 && (is_blank || ebi == 0 || lane != lasti);
+                    const bool dead = (member && twi[q] < i) || (!is_blank && ((ab0[q] >> lane) & 1u));
+                    const bool twin_owner = have[q] && member && twi[q] > i && !stay[q];
+                    acc[q] = comb<DOMAIN>(sc[i], lp);
+                    x1[q] = twin_owner ? comb<DOMAIN>(sc[twin_owner ? twi[q] : 0], lp) : NEUTRAL;
+                    need1 |= twin_owner;
+                    keep[q] = have[q] && active && !dead;
+                }
+                if (__any_sync(FULL, need1)) {            // merging the neutral element returns the other operand bit-exactly
+#pragma unroll
+                    for (int q = 0; q < RPWB; q++) acc[q] = mrg_bf<DOMAIN>(acc[q], x1[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < RPWB; q++) {
+                    if (have[q] && !stay[q]) {
+                        const unsigned key = keep[q] ? f2ord(acc[q]) : 0u;
+                        cb.cand[ri[q]][lane] = key;
+                        const int c = cb.cellmap[ri[q] * 32 + jr];
+                        if (c != 255) cb.ckey[c] = key;
+                    }
+                }
+            } else {
+                // ---- stay warp: lane = kept state (X, 0); its "stay" candidate sums up to three addends -- (P,0)+last if
+                // last(P) != last, (P,1)+last, (X,0)+last -- in ascending parent rank (kNone = -1 sorts first)
+                for (int i0 = 0; i0 < k; i0 += 32) {
+                    const int i = i0 + lane;
+                    const bool on = i < k;
+                    const int ii = on ? i : 0;
+                    const int pkI = pk[ii];
+                    const int lasti = pkI & 0xff;
+                    const bool is_state0 = on && ((pkI >> 8) & 1) == 0 && lasti < 32;
+                    const int q0 = cb.p0[ii], q1 = cb.p1[ii];
+                    const int pq0 = pk[q0 >= 0 ? q0 : 0];
+                    int s0 = (q0 >= 0 && (pq0 & 0xff) == lasti) ? kNone : q0, s1 = q1, s2 = ii;
+                    int lo = min(s0, s1), hi = max(s0, s1);
+                    s0 = lo; s1 = hi;
+                    lo = min(s1, s2); hi = max(s1, s2);
+                    s1 = lo; s2 = hi;
+                    lo = min(s0, s1); hi = max(s0, s1);
+                    s0 = lo; s1 = hi;
+                    const int t0 = s0 >= 0 ? s0 : (s1 >= 0 ? s1 : s2);
+                    const int t1 = s0 >= 0 ? s1 : (s1 >= 0 ? s2 : kNone);
+                    const int t2 = s0 >= 0 ? s2 : kNone;
+                    const float lpv = cb.lpring[slot][is_state0 ? lasti : 0];
+                    float acc = comb<DOMAIN>(sc[t0], lpv);
+                    const bool n1 = is_state0 && t1 >= 0, n2 = is_state0 && t2 >= 0;
+                    if (__any_sync(FULL, n1)) {
+                        acc = mrg_bf<DOMAIN>(acc, n1 ? comb<DOMAIN>(sc[t1 >= 0 ? t1 : 0], lpv) : NEUTRAL);
+                        if (__any_sync(FULL, n2)) acc = mrg_bf<DOMAIN>(acc, n2 ? comb<DOMAIN>(sc[t2 >= 0 ? t2 : 0], lpv) : NEUTRAL);
+                    }
+                    if (is_state0) {
+                        const unsigned key = lasti < V ? f2ord(acc) : 0u;
+                        cb.cand[ii][lasti] = key;
+                        const int c = cb.cellmap[ii * 32 + cb.rankof[slot][lasti]];
+                        if (c != 255) cb.ckey[c] = key;
+                    }
                 }
             }
         } else if (w == 0) {
