@@ -234,13 +234,33 @@ def main():
         hbm_peak, tc_peak, peak_kind = measured_peaks()
         stage_ms = stage_acc / args.steps                      # proj, recurrence, linear, decode (per step)
         rows = c["T"] * c["N"]
-        rec_bytes = rows * c["H"] * 4 * 2                      # per launch: read xproj + write h
+        rec_bytes = rows * c["H"] * 4 * 2                      # per layer: read xproj (fp32) + write h (4 B/element)
         launches_per_stage, chunk_frames = pipe.stage_launches()
+        streaming = chunk_frames < 0
         n_rec = max(launches_per_stage[1], 1)
-        rec_bytes = rec_bytes * c["L"] // n_rec                # algorithmic bytes of ONE launch (a time chunk of a layer)
+        rec_bytes = rec_bytes * c["L"] // n_rec                # algorithmic bytes of ONE launch
         rec_ms_per_launch = stage_ms[1] / n_rec
         achieved = rec_bytes / (rec_ms_per_launch * 1e-3) / 1e9
+        if streaming:
+            rec_kernel = ("rnn_stream_kernel<512> (persistent recurrence of all 3 layers, ONE launch per step; its duration "
+                          "includes waiting for the projection GEMM that runs concurrently)")
+            mode = {"mode": "streaming", "note": "three persistent kernels (recurrence of all layers / tcgen05 projection + "
+                    "output-layer GEMM / decoder) run concurrently for the whole sequence and hand 128-row blocks to each "
+                    "other through counters in HBM; stage times are whole-kernel durations and overlap; Linear + "
+                    "log-softmax is a target of the GEMM kernel", "launches_per_stage": launches_per_stage}
+        else:
+            rec_kernel = "rnn_tanh_mma_kernel (recurrence, one launch per layer and time chunk)"
+            mode = {"mode": "chunked" if chunk_frames > 0 else "sequential", "chunk_frames": chunk_frames,
+                    "launches_per_stage": launches_per_stage,
+                    "note": "chunk_frames > 0: stages overlap on separate streams; stage times are sums of per-launch "
+                            "durations and may exceed ms_per_step"}
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "rnn_stream_traffic.json")
+        if streaming and os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")   # ncu --set full capture of the same kernel and shape
         proj_flop = 2.0 * rows * (c["D"] * c["H"] + (c["L"] - 1) * c["H"] * c["H"])
+        if streaming:
+            proj_flop += 2.0 * rows * c["H"] * c["V"]          # the output layer is a target of the same GEMM kernel
         lin_bytes = rows * (c["H"] * 4 + c["V"] * 4)
         dec_bytes = rows * c["V"] * 4
         value = world * audio_per_step * args.steps / (ms_dev * 1e-3)
@@ -257,35 +277,39 @@ def main():
                     "h2d_bytes_per_step": int(x.nbytes), "d2h_bytes_per_step": int(c["N"] * (c["T"] + 1 + 8))},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "rnn_tanh_cluster_kernel (recurrence, one launch per layer and time chunk)", "bound": "hbm",
+            "roofline": {"kernel": rec_kernel, "bound": "hbm",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_kind,
+                         "traffic": traffic, "peak_source": peak_kind,
                          "algorithmic_bytes_per_launch": rec_bytes, "ms_per_launch": rec_ms_per_launch,
                          "launches_per_step": n_rec},
             "decode_prune": dict(zip(("fallback_utt_frames", "survivors_total"), ctx.ctc_last_stats())),
-            "pipeline": {"chunk_frames": chunk_frames, "launches_per_stage": launches_per_stage,
-                         "note": "chunk_frames > 0: stages overlap on separate streams; stage times are sums of "
-                                 "per-launch durations and may exceed ms_per_step"},
+            "pipeline": mode,
             "stages_ms_per_step": {"projection_gemm": stage_ms[0], "recurrence": stage_ms[1],
                                    "linear_logsoftmax": stage_ms[2], "ctc_decode": stage_ms[3]},
             "stage_rooflines": {
                 "projection_gemm": {"bound": "tensor", "achieved": proj_flop / (stage_ms[0] * 1e-3) / 1e12,
                                     "peak": tc_peak, "unit": "TFLOP/s",
                                     "frac": proj_flop / (stage_ms[0] * 1e-3) / 1e12 / tc_peak},
-                "linear_logsoftmax": {"bound": "hbm", "achieved": lin_bytes / (stage_ms[2] * 1e-3) / 1e9,
-                                      "peak": hbm_peak, "unit": "GB/s",
-                                      "frac": lin_bytes / (stage_ms[2] * 1e-3) / 1e9 / hbm_peak},
+                "linear_logsoftmax": (None if stage_ms[2] <= 0 else
+                                      {"bound": "hbm", "achieved": lin_bytes / (stage_ms[2] * 1e-3) / 1e9,
+                                       "peak": hbm_peak, "unit": "GB/s",
+                                       "frac": lin_bytes / (stage_ms[2] * 1e-3) / 1e9 / hbm_peak}),
                 "ctc_decode": {"bound": "hbm", "achieved": dec_bytes / (stage_ms[3] * 1e-3) / 1e9, "peak": hbm_peak,
                                "unit": "GB/s", "frac": dec_bytes / (stage_ms[3] * 1e-3) / 1e9 / hbm_peak},
             },
         }
         if world == 1 and not args.no_cpu_baseline:
+            # bounded sample: whole cfg2 batches (64 utterances) on all host threads until ~10 s of CPU work are spent
             cores = host_cores()
-            n_utt = max(2 * cores, 16)
-            v, dt = cpu_port_rtfx(n_utt, cores)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt,
-                                    "sample": f"{n_utt} utterances x T={c['T']} of the cfg2 workload (of 64), "
-                                              f"{cores} host threads"}
+            n_utt, total_s, reps = c["N"], 0.0, 0
+            while total_s < 10.0 and reps < 12:
+                _, dt = cpu_port_rtfx(n_utt, cores)
+                total_s += dt
+                reps += 1
+            v = reps * n_utt * c["T"] * FRAME_SEC / total_s
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "seconds": total_s,
+                                    "sample": f"{reps} x the full cfg2 batch ({n_utt} utterances x T={c['T']}), "
+                                              f"{cores} host threads, oracle port (forward + CTC-REF decode)"}
         print(json.dumps(line), flush=True)
 
     pipe.close()

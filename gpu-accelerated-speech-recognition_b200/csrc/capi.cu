@@ -1026,7 +1026,7 @@ int gasr_asr_stage_times(gasr_asr *a, float *ms4) {
 int gasr_asr_stage_launches(gasr_asr *a, int *n4, int *chunk_frames) {
     GASR_CHECK(a && n4, "gasr_asr_stage_launches: null argument");
     for (int i = 0; i < 4; i++) n4[i] = a->stage_launches[i];
-    if (chunk_frames) *chunk_frames = a->chunk;
+    if (chunk_frames) *chunk_frames = a->stream_ok ? -1 : a->chunk;
     return GASR_OK;
 }
 

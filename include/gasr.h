@@ -155,9 +155,13 @@ int gasr_asr_run_device(gasr_asr *asr, const float *x_dev, char *out_paths, int 
 int gasr_asr_logprobs(gasr_asr *asr, const float **logp_dev, int *ldp);
 /* Per-stage device times (ms) of the last run: projection, recurrence, linear+log-softmax, decode.  */
 int gasr_asr_stage_times(gasr_asr *asr, float *ms4);
-/* Kernel launches per stage in the last run (same order) and the pipeline chunk length in frames (0: the stages
- * ran back to back on one stream; otherwise time chunks flowed through the stages on concurrent streams and a
- * stage time is the sum of its launches' durations).                                                        */
+/* Kernel launches per stage in the last run (same order) and the execution mode in *chunk_frames:
+ *   0   the stages ran back to back on one stream;
+ *   >0  time chunks of that many frames flowed through the stages on concurrent streams (a stage time is the sum of
+ *       its launches' durations);
+ *   -1  streaming: one persistent kernel per stage (recurrence of all layers / projection + output-layer GEMM / decoder)
+ *       ran concurrently for the whole sequence, coupled by progress counters in HBM; a stage time is the duration of
+ *       its kernel and the Linear + log-softmax stage is part of the GEMM kernel (reported as 0).                  */
 int gasr_asr_stage_launches(gasr_asr *asr, int *n4, int *chunk_frames);
 
 #ifdef __cplusplus

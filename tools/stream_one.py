@@ -9,6 +9,14 @@ fc_w, fc_b = synth.fc_weights(99, H, V)
 ctx = gasr.Context(0)
 pipe = gasr.AsrPipeline(ctx, gasr.CELL_TANH, False, T, N, D, H, L, V, beam, 0, synth.VOCAB29)
 pipe.set_weights(w_ih, w_hh, b_ih, b_hh, fc_w, fc_b)
+if os.environ.get("GASR_STREAM_DEBUG") == "3":
+    # "alone" mode (tools/capture_profiles.sh): the library runs the persistent kernels one at a time with their
+    # dependencies preset and then reports an error on purpose -- there is no result to return
+    try:
+        pipe.run_host(x)
+    except gasr.GasrError:
+        pass
+    sys.exit(0)
 paths, scores = pipe.run_host(x)
 print("ok", paths[0][:40], scores[0], pipe.stage_times())
 if len(sys.argv) > 7:
