@@ -797,7 +797,9 @@ static int asr_run_streaming(gasr_asr *a, const float *x_dev, const float *x_hos
     cudaStream_t main_st = ctx->stream, rec_st = ctx->side[0], gemm_st = ctx->side[1], dec_st = ctx->side[3];
     unsigned *h_done = a->flags, *xp_ready = a->flags + (size_t)L * nb, *lp_ready = a->flags + (size_t)2 * L * nb;
     unsigned *x_ready = lp_ready + nb, *misc = x_ready + nb;
-    const int rec_ctas_per_layer = ceil_div(N, 16) * (H / 64);
+    const int rec_nsub = rnn_stream_default_nsub(N);
+    const int rec_groups = rec_nsub == 4 ? ceil_div(N, 32) : ceil_div(N, 16);
+    const int rec_ctas_per_layer = rec_groups * (H / 64);
     a->epoch += 1;
     a->host_words[1] = 0;
     // everything that may synchronise the device (allocations, function attributes) happens before the first persistent
@@ -841,7 +843,7 @@ static int asr_run_streaming(gasr_asr *a, const float *x_dev, const float *x_hos
 
     // ---- recurrence: all layers, one launch ------------------------------------------------------------------------
     RnnStreamParams rp = {};
-    rp.T = T; rp.N = N; rp.L = L; rp.groups = ceil_div(N, 16); rp.frames_per_block = a->stream_fpb;
+    rp.T = T; rp.N = N; rp.L = L; rp.groups = rec_groups; rp.nsub = rec_nsub; rp.frames_per_block = a->stream_fpb;
     rp.xp_need = XS_EPI_WARPS * (H / TC_BN);
     rp.error = a->host_words_dev + 1; rp.abort = misc + 1; rp.started = misc; rp.host_go = a->host_words_dev; rp.epoch = a->epoch;
     for (int l = 0; l < L; l++) {

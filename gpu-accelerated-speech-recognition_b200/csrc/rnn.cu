@@ -415,7 +415,9 @@ int launch_rnn_recurrence(gasr_ctx *ctx, const RnnLayerArgs &a, cudaStream_t st)
         if (!(force && (force[0] == 'f' || force[0] == 'm')) && !a.reverse && p.s0 == 0 && p.s1 == a.T &&
             rnn_stream_supported(ctx, a.H, a.N, 1) && a.col0 == 0) {
             RnnStreamParams sp = {};
-            sp.T = a.T; sp.N = a.N; sp.L = 1; sp.groups = groups; sp.frames_per_block = 1; sp.xp_need = 0; sp.error = nullptr;
+            sp.T = a.T; sp.N = a.N; sp.L = 1; sp.frames_per_block = 1; sp.xp_need = 0; sp.error = nullptr;
+            sp.nsub = rnn_stream_default_nsub(a.N);
+            sp.groups = sp.nsub == 4 ? ceil_div(a.N, 32) : groups;
             sp.layer[0].xproj = a.xproj; sp.layer[0].ldxp = a.ldxp; sp.layer[0].w_hh = a.w_hh;
             sp.layer[0].out = a.out; sp.layer[0].ldo = a.ldo;
             return launch_rnn_stream(ctx, sp, a.H, st);

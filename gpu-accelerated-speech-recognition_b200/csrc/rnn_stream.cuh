@@ -20,7 +20,8 @@ struct RnnStreamLayer {
 };
 
 struct RnnStreamParams {
-    int T, N, L, groups;              // groups = ceil(N / 16)
+    int T, N, L, groups;              // groups = ceil(N / (8 * sub-batches per cluster))
+    int nsub;                         // 0: first-generation kernel (2 sub-batches); 2 or 4: software-pipelined kernel
     int frames_per_block;             // frames covered by one progress counter
     int xp_need;                      // arrivals that complete an xproj block
     int *error;                       // set to 1 if a watchdog fired
@@ -31,6 +32,7 @@ struct RnnStreamParams {
 };
 
 bool rnn_stream_supported(const gasr_ctx *ctx, int H, int N, int L);
+int rnn_stream_default_nsub(int N);
 int launch_rnn_stream(gasr_ctx *ctx, const RnnStreamParams &p, int H, cudaStream_t st);
 
 }  // namespace gasr

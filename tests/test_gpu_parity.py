@@ -371,6 +371,44 @@ def test_gru_bidirectional_vs_oracle(gasr, ctx, O):
     assert np.abs(out[-1] - ref[-1]).max() < AM_TOL
 
 
+def test_gru_bidirectional_cfg3_width(gasr, ctx, O):
+    """BASELINE cfg3's layer shape (bidirectional GRU, H = 800, 161-bin input) at a short T / small batch."""
+    import synth
+    T, N, D, H, L = 6, 4, 161, 800, 2
+    x = synth.spectrogram_batch(31, T, N, D)
+    w_ih, w_hh, b_ih, b_hh = synth.rnn_weights(32, D, H, L, cell_gates=3, bidir=True)
+    out = _run_rnn(gasr, ctx, gasr.CELL_GRU, True, T, N, D, H, L, x, w_ih, w_hh, b_ih, b_hh)
+    ref = O.gru_forward(x, T, N, H, L, True, w_ih, w_hh, b_ih, b_hh)
+    for l in range(L):
+        assert np.abs(out[l] - ref[l]).max() < AM_TOL, f"layer {l}"
+
+
+def test_pipeline_cfg3_style_gru_bf16_projection(gasr, ctx, O):
+    """cfg3 in miniature through the fused entry point: bidirectional GRU stack, beam 32, bf16 input projection.
+    Stated tolerance of the bf16 mode: 2e-2 on the log-probabilities; transcripts of the utterances whose fp32 / bf16
+    log-probabilities decode identically on the oracle must be unchanged (decode parity itself stays bit-exact)."""
+    import synth
+    T, N, D, H, L, V, beam = 30, 6, 161, 96, 3, 29, 32
+    x = synth.spectrogram_batch(41, T, N, D)
+    w_ih, w_hh, b_ih, b_hh = synth.rnn_weights(42, D, H, L, cell_gates=3, bidir=True)
+    fc_w, fc_b = synth.fc_weights(43, 2 * H, V)
+    ref_h = O.gru_forward(x, T, N, H, L, True, w_ih, w_hh, b_ih, b_hh)[-1]
+    ref_logp = O.linear(ref_h, fc_w, fc_b, act="logsoftmax")
+    got = {}
+    for prec, tol in ((gasr.PREC_FP32, AM_TOL), (gasr.PREC_BF16, 2e-2)):
+        pipe = gasr.AsrPipeline(ctx, gasr.CELL_GRU, True, T, N, D, H, L, V, beam, 0, synth.VOCAB29, precision=prec)
+        pipe.set_weights(w_ih, w_hh, b_ih, b_hh, fc_w, fc_b)
+        paths, scores = pipe.run_host(x)
+        logp = pipe.logprobs()
+        assert np.abs(logp - ref_logp).max() < tol, f"precision {prec}"
+        op, os_ = O.ctc_decode(logp.reshape(T, N, V), synth.VOCAB29, 0, beam, domain="log", nthreads=4)
+        _assert_same(paths, scores, op, os_)
+        got[prec] = paths
+        pipe.close()
+    same = sum(a == b for a, b in zip(got[gasr.PREC_FP32], got[gasr.PREC_BF16]))
+    assert same >= N - 1, f"bf16 projection changed {N - same} of {N} transcripts"
+
+
 # ---------------------------------------------------------------- end-to-end pipeline ----------------------
 # the last three shapes sit inside the streaming envelope (persistent kernels coupled by progress counters)
 @pytest.mark.parametrize("T,N,D,H,L,beam", [(60, 10, 161, 512, 3, 16), (33, 3, 20, 64, 1, 4), (230, 20, 40, 128, 3, 8),
