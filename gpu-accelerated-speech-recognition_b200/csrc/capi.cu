@@ -956,7 +956,8 @@ static int asr_run_streaming(gasr_asr *a, const float *x_dev, const float *x_hos
     }
     GASR_CUDA(cudaStreamWaitEvent(gemm_st, a->ev_go, 0));
     GASR_CUDA(cudaEventRecord(a->ev_g0, gemm_st));
-    GASR_TRY(launch_xproj_stream(ctx, a->xs_maps, xp, gemm_ctas, gemm_st));
+    if (!getenv("GASR_STREAM_INJECT_LOST_PRODUCER"))     // (test hook: the GEMM kernel never starts -> watchdogs -> fallback)
+        GASR_TRY(launch_xproj_stream(ctx, a->xs_maps, xp, gemm_ctas, gemm_st));
     GASR_CUDA(cudaEventRecord(a->ev_g1, gemm_st));
     if (dbg) {
         cudaError_t q = cudaStreamSynchronize(gemm_st);
@@ -987,13 +988,27 @@ static int asr_run_streaming(gasr_asr *a, const float *x_dev, const float *x_hos
     return ctc_decode_finish(ctx, ca);
 }
 
+// The streaming mode needs every CTA of its three kernels resident at once (a whole, otherwise idle B200).  If its
+// residency handshake or a watchdog failed without a CUDA fault (e.g. the GPU is shared), the pipeline object drops to
+// the time-chunked mode -- still the same kernels' siblings on the GPU, never a CPU path -- and says so once.
+static bool asr_stream_recover(gasr_asr *a, int rc) {
+    if (rc != GASR_ERR_CUDA || cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) return false;
+    fprintf(stderr, "libgasr: streaming pipeline unavailable (%s); falling back to the time-chunked pipeline\n", gasr_last_error());
+    a->stream_ok = false;
+    return true;
+}
+
 int gasr_asr_run_device(gasr_asr *a, const float *x_dev, char *out_paths, int *out_lens, float *out_scores) {
     GASR_CHECK(a != nullptr, "null gasr_asr");
     gasr_ctx *ctx = a->ctx;
     GASR_ENTER(ctx);
     GASR_CHECK(a->have_weights, "gasr_asr_run: weights not set");
     GASR_CHECK(x_dev && out_paths && out_lens && out_scores, "gasr_asr_run: null argument");
-    if (a->stream_ok) return asr_run_streaming(a, x_dev, nullptr, out_paths, out_lens, out_scores);
+    if (a->stream_ok) {
+        const int rc = asr_run_streaming(a, x_dev, nullptr, out_paths, out_lens, out_scores);
+        if (rc == GASR_OK || getenv("GASR_STREAM_DEBUG")) return rc;
+        if (!asr_stream_recover(a, rc)) return rc;
+    }
     if (a->chunk > 0) return asr_run_pipelined(a, x_dev, out_paths, out_lens, out_scores);
     return asr_run_sequential(a, x_dev, out_paths, out_lens, out_scores);
 }
@@ -1006,7 +1021,11 @@ int gasr_asr_run_host(gasr_asr *a, const float *x_host, char *out_paths, int *ou
     const gasr_asr_config &c = a->cfg;
     GASR_CHECK(a->have_weights, "gasr_asr_run: weights not set");
     GASR_CHECK(out_paths && out_lens && out_scores, "gasr_asr_run: null argument");
-    if (a->stream_ok) return asr_run_streaming(a, a->x_dev, x_host, out_paths, out_lens, out_scores);
+    if (a->stream_ok) {
+        const int rc = asr_run_streaming(a, a->x_dev, x_host, out_paths, out_lens, out_scores);
+        if (rc == GASR_OK || getenv("GASR_STREAM_DEBUG")) return rc;
+        if (!asr_stream_recover(a, rc)) return rc;
+    }
     GASR_CUDA(cudaMemcpyAsync(a->x_dev, x_host, sizeof(float) * (size_t)c.T * c.N * c.in, cudaMemcpyHostToDevice,
                               ctx->stream));
     return gasr_asr_run_device(a, a->x_dev, out_paths, out_lens, out_scores);

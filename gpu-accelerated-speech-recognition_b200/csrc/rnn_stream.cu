@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_stream_kernel(const RnnStre
     // CTA-uniform bases + 32-bit element offsets that advance by one frame per step (T*N*ld < 2^31 is checked on the host)
     const float *const xp_base = L.xproj;
     float *const out_base = L.out;
+    unsigned *const hdone = L.h_done;
     const int xstep = N * L.ldxp, ostep = N * L.ldo, pstep = N * L.ldp;
     const int nA0 = n0 + 2 * tg, nA1 = n0 + RS_SUB + 2 * tg;             // first utterance of this thread in sub-batch 0 / 1
     const unsigned vmask = (nA0 < N ? 1u : 0u) | (nA0 + 1 < N ? 2u : 0u) | (nA1 < N ? 4u : 0u) | (nA1 + 1 < N ? 8u : 0u);
@@ -192,13 +193,14 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_stream_kernel(const RnnStre
     // volatile load one step before it is needed (flag_next); a miss falls back to spinning on fresh loads.
     const volatile unsigned *xr = L.xp_ready;
     const int nblocks = (T + fpb - 1) / fpb;
+    const int fsh = (fpb & (fpb - 1)) == 0 ? __ffs(fpb) - 1 : -1;        // frames per block is a power of two in the pipeline
     int ready_blocks = xr == nullptr ? nblocks : 0;
     unsigned flag_next = 0;
     auto sample_flag = [&]() { if (lane == 0) flag_next = xr[ready_blocks]; };
     auto advance_blocks = [&](int t) {                   // make sure the xproj rows of frame t are complete
         // opportunistic: last step's sample of the next block's counter
         if (__shfl_sync(0xffffffffu, flag_next, 0) >= (unsigned)p.xp_need) ready_blocks++;
-        const int need = t / fpb + 1;
+        const int need = (fsh >= 0 ? (t >> fsh) : t / fpb) + 1;
         while (ready_blocks < need) {                    // slow path: spin on fresh loads
             const unsigned long long t0 = rs_now_ns();
             unsigned v;
@@ -228,6 +230,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_stream_kernel(const RnnStre
     const int r0 = (lane >> 4) * (CS / 2);               // lanes 0-15 serve the first half of the cluster, 16-31 the second
     uint32_t phase_bits = 0;                             // bit (sub*2+par): parity of the next phase to wait for
     int pend_hi = -1;                                    // lane 0: highest block whose completion this warp still has to publish
+    int fcnt = 0, blk = 0;                               // frames finished in the current block, current block
 
     cluster.sync();
     if (p.started != nullptr && tid == 0) {
@@ -290,7 +293,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_stream_kernel(const RnnStre
             const float v0 = tanhf((sub ? xc10 : xc00) + a0), v1 = tanhf((sub ? xc11 : xc01) + a1);
             if (sub == 0 && pend_hi >= 0) {        // (lane 0 of one warp per CTA, once per RS_SIGNAL_BLOCKS blocks)
                 __threadfence();
-                for (int b2 = pend_hi - (RS_SIGNAL_BLOCKS - 1); b2 <= pend_hi; b2++) atomicAdd(L.h_done + b2, 1u);
+                for (int b2 = pend_hi - (RS_SIGNAL_BLOCKS - 1); b2 <= pend_hi; b2++) atomicAdd(hdone + b2, 1u);
                 pend_hi = -1;
             }
             // ---- publish: fp32 output, bf16 planes, DSMEM all-gather ------------------------------------------------
@@ -321,21 +324,24 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_stream_kernel(const RnnStre
         // progress: the warp that completes a block last owes the consumers a fence + count for it.  The fence waits for
         // the CTA's outstanding stores, so it is DEFERRED to the middle of the next step (pend_hi), when those stores have
         // long been acknowledged, and issued once per RS_SIGNAL_BLOCKS blocks.
-        if (L.h_done != nullptr && ((s + 1) % fpb == 0 || !more)) {
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                const int blk = s / fpb;
-                const int last = (atomicAdd(const_cast<int *>(ctl + (blk & 1)), 1) & (RS_MATH_WARPS - 1)) == RS_MATH_WARPS - 1;
-                if (last && ((blk + 1) % RS_SIGNAL_BLOCKS == 0 || !more)) {
-                    pend_hi = blk;
-                    if (!more) {
-                        __threadfence();
-                        for (int b2 = blk - blk % RS_SIGNAL_BLOCKS; b2 <= blk; b2++) atomicAdd(L.h_done + b2, 1u);
-                        pend_hi = -1;
+        if (++fcnt == fpb || !more) {
+            if (hdone != nullptr) {
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();
+                    const int last = (atomicAdd(const_cast<int *>(ctl + (blk & 1)), 1) & (RS_MATH_WARPS - 1)) == RS_MATH_WARPS - 1;
+                    if (last && ((blk + 1) % RS_SIGNAL_BLOCKS == 0 || !more)) {
+                        pend_hi = blk;
+                        if (!more) {
+                            __threadfence();
+                            for (int b2 = blk - blk % RS_SIGNAL_BLOCKS; b2 <= blk; b2++) atomicAdd(hdone + b2, 1u);
+                            pend_hi = -1;
+                        }
                     }
                 }
             }
+            fcnt = 0;
+            blk++;
         }
     }
     cluster.sync();
@@ -431,11 +437,12 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_stream2_kernel(const RnnStr
     // projection progress (see rnn_stream_kernel)
     const volatile unsigned *xr = L.xp_ready;
     const int nblocks = (T + fpb - 1) / fpb;
+    const int fsh = (fpb & (fpb - 1)) == 0 ? __ffs(fpb) - 1 : -1;        // frames per block is a power of two in the pipeline
     int ready_blocks = xr == nullptr ? nblocks : 0;
     unsigned flag_next = 0;
     auto advance_blocks = [&](int t) {
         if (__shfl_sync(0xffffffffu, flag_next, 0) >= (unsigned)p.xp_need) ready_blocks++;
-        const int need = t / fpb + 1;
+        const int need = (fsh >= 0 ? (t >> fsh) : t / fpb) + 1;
         while (ready_blocks < need) {
             const unsigned long long t0 = rs_now_ns();
             unsigned v;

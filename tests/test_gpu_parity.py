@@ -436,6 +436,30 @@ def test_pipeline_end_to_end(gasr, ctx, O, T, N, D, H, L, beam):
     pipe.close()
 
 
+def test_streaming_falls_back_to_chunked_when_a_producer_is_lost(gasr, ctx, O, monkeypatch):
+    """The streaming mode waits inside kernels for other kernels.  If one of them never runs (injected here), the in-kernel
+    watchdogs end the step with an error word instead of a hang and the pipeline object drops to the time-chunked mode,
+    which must give the same transcripts and scores."""
+    import synth
+    T, N, D, H, L, V, beam = 104, 16, 40, 128, 2, 29, 8
+    x = synth.spectrogram_batch(5, T, N, D)
+    w_ih, w_hh, b_ih, b_hh = synth.rnn_weights(6, D, H, L)
+    fc_w, fc_b = synth.fc_weights(7, H, V)
+    pipe = gasr.AsrPipeline(ctx, gasr.CELL_TANH, False, T, N, D, H, L, V, beam, 0, synth.VOCAB29)
+    pipe.set_weights(w_ih, w_hh, b_ih, b_hh, fc_w, fc_b)
+    good = pipe.run_host(x)
+    assert pipe.stage_launches()[1] == -1                      # streaming
+    monkeypatch.setenv("GASR_STREAM_INJECT_LOST_PRODUCER", "1")
+    again = pipe.run_host(x)                                   # watchdog (2 s) -> fallback -> chunked run
+    monkeypatch.delenv("GASR_STREAM_INJECT_LOST_PRODUCER")
+    assert pipe.stage_launches()[1] > 0                        # chunked from now on
+    # the two modes run different recurrence kernels (different fp32 summation order): same transcripts, scores equal to
+    # fp32 rounding of the acoustic model (the decoders themselves are bit-identical on identical log-probabilities)
+    assert again[0] == good[0]
+    assert np.allclose(again[1], good[1], rtol=1e-5, atol=0)
+    pipe.close()
+
+
 def test_cpp_module_mirror(tmp_path):
     """include/*.h (cuMatrix, Linear, RNN_Cell, RNN, CTCBeamSearch, MemoryMonitor) compiled with plain g++ and linked
     to libgasr.so: the reference's own drivers (nn_test.cpp, main.cpp) as assertions."""
