@@ -348,11 +348,11 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_stream_kernel(const RnnStre
 }
 
 // =====================================================================================================================
-// Second generation: NSUB (2 or 4) sub-batches of 8 utterances per cluster, SOFTWARE PIPELINED inside every warp: the
-// MMAs of sub-step q are issued interleaved with the epilogue (K-half exchange, tanh, bf16 split, stores, DSMEM send) of
-// sub-step q-1, so the tensor pipe keeps working while the long epilogue dependency chain and the DSMEM transfer of the
-// previous sub-steps are in flight.  With 4 sub-batches a cluster serves 32 utterances: cfg2's layer stack needs 48 SMs
-// instead of 96 -- the SMs the decoder needs to run one CTA per SM.
+// Second generation: NSUB (2 or 4) sub-batches of 8 utterances per cluster and a LEADER / FOLLOWER schedule of the two
+// K-half warps that share an SM sub-partition (see the comment at the main loop): their MMA bursts alternate on the
+// tensor pipe and each warp's epilogue (K-half exchange, tanh, bf16 split, stores, DSMEM send) hides under the partner's
+// burst.  With 4 sub-batches a cluster serves 32 utterances: cfg2's layer stack needs 48 SMs instead of 96 -- the SMs the
+// decoder needs to run one CTA per SM.
 // =====================================================================================================================
 __device__ __forceinline__ void rs_mma_nv(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
@@ -369,8 +369,8 @@ struct Rs2Layout {
     static constexpr int OFF_XCH = OFF_H + NSUB * 2 * HBUF;          // [sub NSUB][ch 4][kh 2][32] float2
     static constexpr int OFF_STG = OFF_XCH + NSUB * 2048;            // [warp 8][plane 2][utt 8][16 B]
     static constexpr int OFF_BAR = OFF_STG + RS_MATH_WARPS * 256;    // mbar[sub NSUB][parity 2]
-    static constexpr int OFF_CTL = OFF_BAR + NSUB * 2 * 8;           // int: [0], [1] warp arrivals by block parity, [2] abort
-    static constexpr int BYTES = OFF_CTL + 16;
+    static constexpr int OFF_CTL = OFF_BAR + NSUB * 2 * 8;           // int: [0], [1] warp arrivals by block parity, [2] abort, [4..11] per-warp sequence numbers
+    static constexpr int BYTES = OFF_CTL + 48;
     static constexpr uint32_t TX = 2u * RS_SUB * H * 2u;
 };
 
@@ -380,7 +380,6 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_stream2_kernel(const RnnStr
     constexpr int CS = H / RS_HC;
     constexpr int KSW = H / 32;                          // k-steps (of 16) per warp: half of K
     constexpr int KP = KSW / 2;                          // ldmatrix.x4 pairs per sub-step
-    constexpr int NPARTS = 6;                            // pieces of the epilogue, interleaved with the MMA groups
     extern __shared__ __align__(128) unsigned char smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -400,6 +399,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_stream2_kernel(const RnnStr
         for (int b = 0; b < NSUB * 2; b++) rs_mbar_init(sbase + LT::OFF_BAR + 8 * b, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         ctl[0] = 0; ctl[1] = 0; ctl[2] = 0;
+        for (int i = 4; i < 12; i++) ctl[i] = 0;
     }
     __syncthreads();
     if (tid == 0)
@@ -488,136 +488,143 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_stream2_kernel(const RnnStr
 
     const int Q = T * NSUB;
     int s = 0, sub = 0;
-    // One slot = issue the MMAs of sub-step q (DO_M) interleaved with the epilogue of sub-step q - 1 (DO_E).  The first and
-    // the last slot are peeled so that the steady-state body has no conditionals around the two instruction streams.
-    auto slot = [&](auto DM, auto DE) {
-        constexpr bool do_m = decltype(DM)::value, do_e = decltype(DE)::value;
+    // Leader / follower schedule.  The two warps of an SM sub-partition are the K-half partners (ch, 0) and (ch, 1).  Each
+    // slot is an MMA BURST (48 back-to-back MMAs at H = 512) followed by a long epilogue.  The follower (kh = 1) runs half
+    // a slot behind the leader, so their bursts alternate on the sub-partition's tensor pipe instead of colliding, and
+    // each warp's epilogue hides under the partner's burst.  The leader finalises sub-step q - 1 after its burst of q (its
+    // partner's partial of q - 1 was published half a slot earlier); the follower finalises q right after its own burst.
+    // Partials are handed over through shared memory with per-warp sequence numbers (no barrier: a barrier would
+    // re-align the two warps).
+    volatile int *seq = reinterpret_cast<volatile int *>(smem + LT::OFF_CTL) + 4;    // [8] sub-steps published by each warp
+    const int partner = warp ^ 4;
+    if (kh) {                                            // initial half-slot offset of the followers
+        const long long t0 = clock64();
+        while (clock64() - t0 < 700) { }
+    }
+    auto burst = [&](float &c0, float &c1, float &c2, float &c3, float &xn0, float &xn1) {
         const int par = s & 1;
-        float xn0 = 0.f, xn1 = 0.f;
-        uint32_t hb = 0;
-        if (do_m) {
-            if (sub == 0 && ready_blocks < nblocks) advance_blocks(s);
-            const int n = nA + RS_SUB * sub;
-            if (n < N) xn0 = __ldcg(xp_base + xoff + sub * ldxp8);
-            if (n + 1 < N) xn1 = __ldcg(xp_base + xoff + sub * ldxp8 + ldxp1);
-            const int bi = sub * 2 + par;
-            const uint32_t bar = bar0 + 8 * bi;
-            if (s > 0) {
-                const uint32_t ph = (phase_bits >> bi) & 1u;
-                if (!rs_mbar_try(bar, ph)) {
-                    const unsigned long long t0 = rs_now_ns();
-                    int spins = 0;
-                    while (!rs_mbar_try(bar, ph))
-                        if (ctl[2] || ((++spins & 255) == 0 && ((p.abort && *p.abort) || rs_now_ns() - t0 > RS_TIMEOUT_NS))) {
-                            ctl[2] = 1; if (p.abort) *p.abort = 1u; break;
-                        }
-                }
-                phase_bits ^= 1u << bi;
-                if (tid == 0) rs_mbar_expect_tx(bar, LT::TX);
+        if (sub == 0 && ready_blocks < nblocks) advance_blocks(s);
+        const int n = nA + RS_SUB * sub;
+        xn0 = 0.f; xn1 = 0.f;
+        if (n < N) xn0 = __ldcg(xp_base + xoff + sub * ldxp8);
+        if (n + 1 < N) xn1 = __ldcg(xp_base + xoff + sub * ldxp8 + ldxp1);
+        const int bi = sub * 2 + par;
+        const uint32_t bar = bar0 + 8 * bi;
+        if (s > 0) {
+            const uint32_t ph = (phase_bits >> bi) & 1u;
+            if (!rs_mbar_try(bar, ph)) {
+                const unsigned long long t0 = rs_now_ns();
+                int spins = 0;
+                while (!rs_mbar_try(bar, ph))
+                    if (ctl[2] || ((++spins & 255) == 0 && ((p.abort && *p.abort) || rs_now_ns() - t0 > RS_TIMEOUT_NS))) {
+                        ctl[2] = 1; if (p.abort) *p.abort = 1u; break;
+                    }
             }
-            hb = sbase + LT::OFF_H + bi * LT::HBUF + lm_off;
+            phase_bits ^= 1u << bi;
+            if (tid == 0) rs_mbar_expect_tx(bar, LT::TX);
         }
+        const uint32_t hb = sbase + LT::OFF_H + bi * LT::HBUF + lm_off;
         float cm0[4] = {0.f, 0.f, 0.f, 0.f}, cm1[4] = {0.f, 0.f, 0.f, 0.f};
         float cs0[4] = {0.f, 0.f, 0.f, 0.f}, cs1[4] = {0.f, 0.f, 0.f, 0.f};
-        float v0 = 0.f, v1 = 0.f;
-        const bool more_e = ps + 1 < T;                  // the pending sub-step's h feeds another step
-        uint4 chunk = make_uint4(0, 0, 0, 0);
-        auto epilogue_part = [&](int part) {             // straight-line pieces (predicated, no loops): they interleave with the MMAs
-            if (part == 0) {
-                const float2 o = xch_peer[psub * 256];
-                v0 = px0 + (kh == 0 ? pc0 + o.x : o.x + pc2);
-                v1 = px1 + (kh == 0 ? pc1 + o.y : o.y + pc3);
-            } else if (part == 1) {
-                v0 = tanhf(v0);
-            } else if (part == 2) {
-                v1 = tanhf(v1);
-            } else if (part == 3) {
-                const int n = nA + RS_SUB * psub;
-                if (out_base != nullptr) {
-                    if (n < N) out_base[ooff + psub * ldo8] = v0;
-                    if (n + 1 < N) out_base[ooff + psub * ldo8 + ldo1] = v1;
-                }
-                __nv_bfloat16 h0, l0, h1, l1;
-                rs_split(v0, h0, l0);
-                rs_split(v1, h1, l1);
-                __syncwarp();
-                sg[0] = h0; sg[8] = h1; sg[64] = l0; sg[72] = l1;
-                __syncwarp();
-            } else if (part == 4) {
-                chunk = *chunk_src;
-                if (plane_lane && n0 + RS_SUB * psub + cu < N) *reinterpret_cast<uint4 *>(plane_base + poff + psub * ldp8) = chunk;
-            } else {
-                if (more_e) {
-                    const uint32_t nb_off = (uint32_t)(psub * 2 + ((ps & 1) ^ 1));
-                    const uint32_t dst_local = dst_local0 + nb_off * LT::HBUF, bar_local = bar0 + 8 * nb_off;
-#pragma unroll
-                    for (int r = 0; r < CS / 2; r++)
-                        rs_st_async_v4(rs_mapa(dst_local, r0 + r), chunk, rs_mapa(bar_local, r0 + r));
-                }
-            }
-        };
+        uint32_t bh[2][4], bl[2][4];
+        rs_ldmatrix_x4(bh[0], hb);
+        rs_ldmatrix_x4(bl[0], hb + LT::PLANE);
 #pragma unroll
         for (int kp = 0; kp < KP; kp++) {
-            if (do_m) {
-                uint32_t bh[4], bl[4];
-                rs_ldmatrix_x4(bh, hb + kp * 64);
-                rs_ldmatrix_x4(bl, hb + LT::PLANE + kp * 64);
-                rs_mma_nv(cm0, ahi[2 * kp], bh[0], bh[1]);
-                rs_mma_nv(cm1, ahi[2 * kp + 1], bh[2], bh[3]);
-                rs_mma_nv(cs0, ahi[2 * kp], bl[0], bl[1]);
-                rs_mma_nv(cs1, ahi[2 * kp + 1], bl[2], bl[3]);
-                rs_mma_nv(cs0, alo[2 * kp], bh[0], bh[1]);
-                rs_mma_nv(cs1, alo[2 * kp + 1], bh[2], bh[3]);
+            const int cb = kp & 1, nb = cb ^ 1;
+            if (kp + 1 < KP) {                           // operands of the next k-pair are in flight while this one multiplies
+                rs_ldmatrix_x4(bh[nb], hb + (kp + 1) * 64);
+                rs_ldmatrix_x4(bl[nb], hb + LT::PLANE + (kp + 1) * 64);
             }
-            if (do_e && kp < NPARTS) epilogue_part(kp);
+            rs_mma_nv(cm0, ahi[2 * kp], bh[cb][0], bh[cb][1]);
+            rs_mma_nv(cm1, ahi[2 * kp + 1], bh[cb][2], bh[cb][3]);
+            rs_mma_nv(cs0, ahi[2 * kp], bl[cb][0], bl[cb][1]);
+            rs_mma_nv(cs1, ahi[2 * kp + 1], bl[cb][2], bl[cb][3]);
+            rs_mma_nv(cs0, alo[2 * kp], bh[cb][0], bh[cb][1]);
+            rs_mma_nv(cs1, alo[2 * kp + 1], bh[cb][2], bh[cb][3]);
         }
-        if (do_e) {
+        c0 = (cm0[0] + cm1[0]) + (cs0[0] + cs1[0]); c1 = (cm0[1] + cm1[1]) + (cs0[1] + cs1[1]);
+        c2 = (cm0[2] + cm1[2]) + (cs0[2] + cs1[2]); c3 = (cm0[3] + cm1[3]) + (cs0[3] + cs1[3]);
+        xch_mine[sub * 256] = kh == 0 ? make_float2(c2, c3) : make_float2(c0, c1);
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); seq[warp] = s * NSUB + sub + 1; }      // partial of this sub-step is published
+    };
+    // epilogue of sub-step (es, esub): combine with the partner's partial, tanh, publish
+    auto epilogue = [&](int es, int esub, float c0, float c1, float c2, float c3, float x0, float x1) {
+        const int need = es * NSUB + esub + 1;
+        if (seq[partner] < need) {
+            const unsigned long long t0 = rs_now_ns();
+            int spins = 0;
+            while (seq[partner] < need)
+                if (ctl[2] || ((++spins & 1023) == 0 && ((p.abort && *p.abort) || rs_now_ns() - t0 > RS_TIMEOUT_NS))) {
+                    ctl[2] = 1; if (p.abort) *p.abort = 1u; break;
+                }
+        }
+        const bool more_e = es + 1 < T;
+        const float2 o = xch_peer[esub * 256];
+        const float v0 = tanhf(x0 + (kh == 0 ? c0 + o.x : o.x + c2));
+        const float v1 = tanhf(x1 + (kh == 0 ? c1 + o.y : o.y + c3));
+        if (esub == 0 && pend_hi >= 0) {                 // deferred progress fence (lane 0 of one warp, once per RS_SIGNAL_BLOCKS)
+            __threadfence();
+            for (int b2 = pend_hi - (RS_SIGNAL_BLOCKS - 1); b2 <= pend_hi; b2++) atomicAdd(hdone + b2, 1u);
+            pend_hi = -1;
+        }
+        const int n = nA + RS_SUB * esub;
+        if (out_base != nullptr) {
+            if (n < N) out_base[ooff + esub * ldo8] = v0;
+            if (n + 1 < N) out_base[ooff + esub * ldo8 + ldo1] = v1;
+        }
+        __nv_bfloat16 h0, l0, h1, l1;
+        rs_split(v0, h0, l0);
+        rs_split(v1, h1, l1);
+        __syncwarp();
+        sg[0] = h0; sg[8] = h1; sg[64] = l0; sg[72] = l1;
+        __syncwarp();
+        const uint4 chunk = *chunk_src;
+        if (plane_lane && n0 + RS_SUB * esub + cu < N) *reinterpret_cast<uint4 *>(plane_base + poff + esub * ldp8) = chunk;
+        if (more_e) {
+            const uint32_t nb_off = (uint32_t)(esub * 2 + ((es & 1) ^ 1));
+            const uint32_t dst_local = dst_local0 + nb_off * LT::HBUF, bar_local = bar0 + 8 * nb_off;
 #pragma unroll
-            for (int part = KP; part < NPARTS; part++) epilogue_part(part);
-            // ---- bookkeeping of the pending sub-step (rare branches, after the interleaved region) ----
-            if (psub == 0 && pend_hi >= 0) {              // deferred progress fence (lane 0 of one warp, once per RS_SIGNAL_BLOCKS)
-                __threadfence();
-                for (int b2 = pend_hi - (RS_SIGNAL_BLOCKS - 1); b2 <= pend_hi; b2++) atomicAdd(hdone + b2, 1u);
-                pend_hi = -1;
-            }
-            if (psub == NSUB - 1) {                      // the pending sub-step closes frame ps
-                ooff += ostep;
-                poff += pstep;
-                fcnt++;
-                if (fcnt == fpb || !more_e) {
-                    if (hdone != nullptr) {
-                        __syncwarp();
-                        if (lane == 0) {
-                            __threadfence_block();
-                            const int last = (atomicAdd(const_cast<int *>(ctl + (blk & 1)), 1) & (RS_MATH_WARPS - 1)) == RS_MATH_WARPS - 1;
-                            if (last && ((blk + 1) % RS_SIGNAL_BLOCKS == 0 || !more_e)) {
-                                if (more_e) pend_hi = blk;
-                                else {
-                                    __threadfence();
-                                    for (int b2 = blk - blk % RS_SIGNAL_BLOCKS; b2 <= blk; b2++) atomicAdd(hdone + b2, 1u);
-                                }
+            for (int r = 0; r < CS / 2; r++)
+                rs_st_async_v4(rs_mapa(dst_local, r0 + r), chunk, rs_mapa(bar_local, r0 + r));
+        }
+        if (esub == NSUB - 1) {                          // this sub-step closes frame es
+            ooff += ostep;
+            poff += pstep;
+            fcnt++;
+            if (fcnt == fpb || !more_e) {
+                if (hdone != nullptr) {
+                    __syncwarp();
+                    if (lane == 0) {
+                        __threadfence_block();
+                        const int last = (atomicAdd(const_cast<int *>(ctl + (blk & 1)), 1) & (RS_MATH_WARPS - 1)) == RS_MATH_WARPS - 1;
+                        if (last && ((blk + 1) % RS_SIGNAL_BLOCKS == 0 || !more_e)) {
+                            if (more_e) pend_hi = blk;
+                            else {
+                                __threadfence();
+                                for (int b2 = blk - blk % RS_SIGNAL_BLOCKS; b2 <= blk; b2++) atomicAdd(hdone + b2, 1u);
                             }
                         }
                     }
-                    fcnt = 0;
-                    blk++;
                 }
+                fcnt = 0;
+                blk++;
             }
         }
-        if (do_m) {
-            const float c0 = (cm0[0] + cm1[0]) + (cs0[0] + cs1[0]), c1 = (cm0[1] + cm1[1]) + (cs0[1] + cs1[1]);
-            const float c2 = (cm0[2] + cm1[2]) + (cs0[2] + cs1[2]), c3 = (cm0[3] + cm1[3]) + (cs0[3] + cs1[3]);
-            xch_mine[sub * 256] = kh == 0 ? make_float2(c2, c3) : make_float2(c0, c1);
-            rs_bar_sync(RS_BAR_PAIR0 + ch, 64);
-            pc0 = c0; pc1 = c1; pc2 = c2; pc3 = c3;
-            px0 = xn0; px1 = xn1;
-            psub = sub; ps = s;
-            if (++sub == NSUB) { sub = 0; s++; xoff += xstep; }
-        }
     };
-    slot(std::true_type{}, std::false_type{});
-    for (int q = 1; q < Q; q++) slot(std::true_type{}, std::true_type{});
-    slot(std::false_type{}, std::true_type{});
+    for (int q = 0; q < Q; q++) {
+        float c0, c1, c2, c3, xn0, xn1;
+        burst(c0, c1, c2, c3, xn0, xn1);
+        if (kh) {
+            epilogue(s, sub, c0, c1, c2, c3, xn0, xn1);                      // follower: its own sub-step
+        } else {
+            if (q > 0) epilogue(ps, psub, pc0, pc1, pc2, pc3, px0, px1);     // leader: the previous sub-step
+            pc0 = c0; pc1 = c1; pc2 = c2; pc3 = c3; px0 = xn0; px1 = xn1; psub = sub; ps = s;
+        }
+        if (++sub == NSUB) { sub = 0; s++; xoff += xstep; }
+    }
+    if (kh == 0) epilogue(ps, psub, pc0, pc1, pc2, pc3, px0, px1);
     cluster.sync();
 }
 
