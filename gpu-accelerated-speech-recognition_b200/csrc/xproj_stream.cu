@@ -44,6 +44,7 @@ __device__ __forceinline__ bool xs_wait(uint32_t bar, uint32_t parity, volatile 
     while (!xs_mbar_try(bar, parity)) {
         if (*abort_flag) return false;
         if ((++spins & 1023) == 0 && (*gabort || xs_now_ns() - t0 > XS_TIMEOUT_NS)) { *abort_flag = 1; *gabort = 1u; return false; }
+        __nanosleep(40);        // these CTAs share their SM with decoder CTAs: do not burn issue slots while waiting
     }
     return true;
 }
