@@ -122,6 +122,7 @@ struct CtcParams {
     unsigned char cell_i[128], cell_j[128]; // prune lower-bound probe cells (parent rank, score rank), by rising (i+1)(j+1)
     unsigned char cellmap[32 * 32];          // (parent rank, score rank) -> probe cell index, 255 = not probed
     int n_cells;         // 32 (one per lane) or 64
+    int use_rel;         // general kernel: prefix-relation matrix in shared memory (O(1) tie-breaks)
     int t0, t1;          // frames [t0, t1) are decoded by this launch (time chunking; warp kernel only)
     unsigned char *state;   // [N, state_stride] saved beam state between chunk launches
     size_t state_stride;
@@ -178,6 +179,56 @@ __device__ __noinline__ bool raw_less(const int *__restrict__ parent, const int 
     return lena == end && lenb > end;
 }
 
+// ---- prefix relations for the general kernel (vocabulary up to 255) -----------------------------------------------
+// rel[a][b] of two kept states' label prefixes: 0 equal, 1 X_a < X_b with the first difference inside both, 2 the
+// reverse, 3 + y: X_a is a proper prefix of X_b and y is X_b's next label, 3 + 256 + y: the mirror image.  Updated in
+// O(1) per pair and frame (children append one label); makes the raw-string tie-break O(1) instead of a trie walk.
+constexpr int RW_EQ = 0, RW_LT = 1, RW_GT = 2, RW_PFX = 3, RW_RPFX = 3 + 256;
+__device__ int trie_char_at(const int *__restrict__ parent, const int *__restrict__ meta, int nd, int pos);   // below
+__device__ __forceinline__ bool chw_less(const char *vch, int a, int b) { return (signed char)vch[a] < (signed char)vch[b]; }
+// raw-string order of candidates (a, suffix sa) and (b, suffix sb); suffix < 0 = none ("stay")
+__device__ __forceinline__ bool candw_less(int R, int sa, int sb, const char *vch) {
+    if (R == RW_EQ) {
+        if (sa < 0) return sb >= 0;
+        if (sb < 0 || sa == sb) return false;
+        return chw_less(vch, sa, sb);
+    }
+    if (R == RW_LT) return true;
+    if (R == RW_GT) return false;
+    if (R < RW_RPFX) {
+        const int y = R - RW_PFX;
+        if (sa < 0 || sa == y) return true;
+        return chw_less(vch, sa, y);
+    }
+    const int y = R - RW_RPFX;
+    if (sb < 0 || sb == y) return false;
+    return chw_less(vch, y, sb);
+}
+// relation of the children (A + er, B + eq2; e < 0 = nothing appended) from the relation R of A and B
+__device__ __forceinline__ int relw_child(int R, int er, int eq2, int dA, int dB, int nodeA, int nodeB, const char *vch,
+                                          const int *parent, const int *meta) {
+    if (R == RW_EQ) {
+        if (er < 0 && eq2 < 0) return RW_EQ;
+        if (er < 0) return RW_PFX + eq2;
+        if (eq2 < 0) return RW_RPFX + er;
+        if (er == eq2) return RW_EQ;
+        return chw_less(vch, er, eq2) ? RW_LT : RW_GT;
+    }
+    if (R == RW_LT || R == RW_GT) return R;
+    if (R < RW_RPFX) {
+        const int y = R - RW_PFX;
+        if (er < 0) return R;
+        if (er != y) return chw_less(vch, er, y) ? RW_LT : RW_GT;
+        if (dB == dA + 1) return eq2 < 0 ? RW_EQ : RW_PFX + eq2;
+        return RW_PFX + trie_char_at(parent, meta, nodeB, dA + 1);
+    }
+    const int y = R - RW_RPFX;
+    if (eq2 < 0) return R;
+    if (eq2 != y) return chw_less(vch, y, eq2) ? RW_LT : RW_GT;
+    if (dA == dB + 1) return er < 0 ? RW_EQ : RW_RPFX + er;
+    return RW_RPFX + trie_char_at(parent, meta, nodeA, dB + 1);
+}
+
 template <int DOMAIN, int MAXT>
 __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -201,6 +252,12 @@ __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
     uint16_t *redir1 = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * B * V;
     char *vch = reinterpret_cast<char *>(sp); sp += (V + 3) / 4 * 4;
     unsigned char *eb2 = sp; sp += 2 * B;
+    sp = smem_raw + (((size_t)(sp - smem_raw) + 7) & ~(size_t)7);
+    int *depth2 = reinterpret_cast<int *>(sp); sp += sizeof(int) * 2 * B;
+    int *sel_i = reinterpret_cast<int *>(sp); sp += sizeof(int) * B;
+    int *sel_v = reinterpret_cast<int *>(sp); sp += sizeof(int) * B;
+    unsigned short *relw = reinterpret_cast<unsigned short *>(sp);      // [2][B][B], only when p.use_rel
+    const bool use_rel = p.use_rel != 0;
     // the two beam buffers (current / next) are halves of the arrays above; no dynamically indexed struct array
     auto beam_view = [&](int w) {
         BeamView v;
@@ -224,6 +281,8 @@ __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
         parent[0] = -1; meta[0] = 0 | 0xff;
         sc2[0] = DOMAIN ? 0.0f : 1.0f;
         node2[0] = 0; pnode2[0] = kNone; last2[0] = -1; eb2[0] = 1;
+        depth2[0] = 0;
+        if (use_rel) relw[0] = RW_EQ;
         s_kept = 1; s_nodes = 1;
     }
     float next_lp = 0.0f;
@@ -373,7 +432,13 @@ __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
                                 const int iy = cy / V, vy = cy - iy * V;
                                 const int sufy = (vy == blank) ? vch[blank]
                                                  : ((st.eb[iy] == 0 && vy == st.last[iy]) ? 0 : vch[vy]);
-                                if (!raw_less(parent, meta, vch, st.node[ix], sufx, st.node[iy], sufy)) break;
+                                bool less;
+                                if (use_rel) {
+                                    const int sx = (vx == blank) ? blank : ((st.eb[ix] == 0 && vx == st.last[ix]) ? -1 : vx);
+                                    const int sy = (vy == blank) ? blank : ((st.eb[iy] == 0 && vy == st.last[iy]) ? -1 : vy);
+                                    less = candw_less(relw[((size_t)cur * B + ix) * B + iy], sx, sy, vch);
+                                } else less = raw_less(parent, meta, vch, st.node[ix], sufx, st.node[iy], sufy);
+                                if (!less) break;
                                 keys[y + 1] = keys[y];
                                 y--;
                             }
@@ -408,8 +473,29 @@ __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
                 }
             }
             newflag[tid] = my_new;
+            sel_i[tid] = valid ? my_i : -1;
+            sel_v[tid] = my_v;
+            if (valid) {
+                const bool stay2 = (my_v == blank) || (st.eb[my_i] == 0 && my_v == st.last[my_i]);
+                depth2[(cur ^ 1) * B + tid] = depth2[cur * B + my_i] + (stay2 ? 0 : 1);
+            }
         }
         __syncthreads();
+        if (use_rel) {
+            // prefix relations of the new beam from the current one and this frame's choices (old node ids still in st)
+            const unsigned short *rc = relw + (size_t)cur * B * B;
+            unsigned short *rn = relw + (size_t)(cur ^ 1) * B * B;
+            for (int e = tid; e < B * B; e += NT) {
+                const int r = e / B, q = e - r * B;
+                const int ar = sel_i[r], aq = sel_i[q];
+                if (ar < 0 || aq < 0) continue;
+                const int vr = sel_v[r], vq = sel_v[q];
+                const int er = (vr == blank || (st.eb[ar] == 0 && vr == st.last[ar])) ? -1 : vr;
+                const int eq2 = (vq == blank || (st.eb[aq] == 0 && vq == st.last[aq])) ? -1 : vq;
+                rn[e] = (unsigned short)relw_child(rc[(size_t)ar * B + aq], er, eq2, depth2[cur * B + ar], depth2[cur * B + aq],
+                                                   st.node[ar], st.node[aq], vch, parent, meta);
+            }
+        }
         if (tid < B && valid) {
             if (my_new) {
                 int off = 0;
@@ -2048,8 +2134,11 @@ static size_t ctc_smem_bytes(int B, int V, int Vp, int n_pad) {
     s += 2 * sizeof(uint16_t) * (size_t)B * V;        // redir0/1
     s += (V + 3) / 4 * 4;                             // vocab chars
     s += 2 * B;                                       // eb (x2)
+    s = (s + 7) / 8 * 8;
+    s += sizeof(int) * 4 * B;                         // depth (x2), selected parent / label
     return s + 16;
 }
+static size_t ctc_rel_bytes(int B) { return sizeof(unsigned short) * 2 * (size_t)B * B; }
 
 struct CtcLayout {
     int Vp, n_pad, cap, threads;
@@ -2124,6 +2213,11 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
     if (a.N == 0) return GASR_OK;
     CtcLayout L;
     ctc_layout(a, L);
+    bool general_rel = false;
+    if (!(a.beam <= 32 && a.V <= 32) && L.smem + ctc_rel_bytes(a.beam) <= (size_t)ctx->max_smem_optin) {
+        general_rel = true;                           // the prefix-relation matrix fits: O(1) raw-string tie-breaks
+        L.smem += ctc_rel_bytes(a.beam);
+    }
     if (!(a.beam <= 32 && a.V <= 32) && L.smem > (size_t)ctx->max_smem_optin) {
         set_error("ctc_decode: beam %d x vocab %d needs %zu B of shared memory (> %d)", a.beam, a.V, L.smem,
                   ctx->max_smem_optin);
@@ -2154,7 +2248,7 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
     p.out_counts = reinterpret_cast<int *>(wo + L.off_counts);
     p.out_stats = reinterpret_cast<int *>(wo + L.off_stats);
     if (!fast) GASR_CUDA(cudaMemsetAsync(p.out_stats, 0, 2 * sizeof(int) * (size_t)a.N, st));
-    p.t0 = t0; p.t1 = t1;
+    p.t0 = t0; p.t1 = t1; p.use_rel = general_rel ? 1 : 0;
     p.state = ws + L.off_state; p.state_stride = L.state_stride;
     p.lp_ready = a.lp_ready; p.lp_need = a.lp_need; p.lp_fpb = a.lp_fpb > 0 ? a.lp_fpb : 1; p.error = a.error; p.abort = a.abort;
     const char *force_k = getenv("GASR_CTC_KERNEL");

@@ -128,6 +128,7 @@ xproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                 const float *bsrc = p.bias ? p.bias + n0 + c * 32 : nullptr;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
+                    if (n0 + c * 32 + j >= p.N) break;           // last column tile of an N that is not a multiple of 128 (N % 4 == 0)
                     float4 o;
                     o.x = __uint_as_float(v[j + 0]) + (bsrc ? bsrc[j + 0] : 0.0f);
                     o.y = __uint_as_float(v[j + 1]) + (bsrc ? bsrc[j + 1] : 0.0f);
@@ -204,7 +205,7 @@ int tc_make_map(CUtensorMap *map, const void *base, int rows, int Kp, int box_ro
     return GASR_OK;
 }
 
-bool xproj_tc_supported(int M, int K, int N) { return M >= 1 && K >= 1 && N >= TC_BN && N % TC_BN == 0; }
+bool xproj_tc_supported(int M, int K, int N) { return M >= 1 && K >= 1 && N >= TC_BN && N % 4 == 0; }
 
 size_t xproj_tc_a_bytes(int M, int K) { return 2 * align_up((size_t)M * (size_t)ceil_div(K, TC_BK) * TC_BK * 2, 1024); }
 size_t xproj_tc_w_bytes(int K, int N) { return 2 * align_up((size_t)N * (size_t)ceil_div(K, TC_BK) * TC_BK * 2, 1024); }
@@ -278,7 +279,7 @@ int launch_xproj_tc(gasr_ctx *ctx, const float *A, int lda, int M, int K, int N,
     p.M = M; p.N = N; p.kblocks = Kp / TC_BK; p.terms = precision == GASR_PREC_BF16 ? 1 : 3;
     p.C = C; p.ldc = ldc; p.bias = bias;
     GASR_CUDA(cudaFuncSetAttribute(xproj_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    dim3 grid(N / TC_BN, ceil_div(M, TC_BM));
+    dim3 grid(ceil_div(N, TC_BN), ceil_div(M, TC_BM));   // TMA zero-fills the rows of W^T beyond N
     xproj_tcgen05_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
     GASR_CUDA(cudaGetLastError());
     ctx->launches += 1;

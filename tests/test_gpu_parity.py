@@ -266,7 +266,7 @@ def test_matmul_variants_and_matadd(gasr, ctx, O):
 
 
 @pytest.mark.parametrize("rows,in_,out", [(1, 1, 128), (130, 161, 512), (1000, 512, 512), (257, 70, 256), (64, 2048, 128),
-                                         (50, 33, 96)])
+                                         (50, 33, 96), (130, 96, 224), (96, 161, 2400)])   # 2400 = cfg3's 3 x 800 gates
 def test_xproj_gemm_tensor_core_vs_oracle(gasr, ctx, O, rows, in_, out):
     """tcgen05 projection GEMM: fp32-grade mode within 1e-4 of the fp32 oracle, bf16 mode within its 2e-2 budget."""
     rng = np.random.default_rng(rows * 7 + in_)
