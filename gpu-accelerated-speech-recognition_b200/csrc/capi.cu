@@ -130,7 +130,7 @@ int gasr_ctx_destroy(gasr_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->dev_blocks) cudaFree(kv.first);
     for (auto &kv : ctx->host_blocks) cudaFreeHost(kv.first);
-    Workspace *wss[] = {&ctx->ws_ctc, &ctx->ws_rnn, &ctx->ws_misc, &ctx->ws_out};
+    Workspace *wss[] = {&ctx->ws_ctc, &ctx->ws_rnn, &ctx->ws_misc, &ctx->ws_out, &ctx->ws_gru};
     for (Workspace *w : wss) if (w->ptr) cudaFree(w->ptr);
     if (ctx->pinned_out) cudaFreeHost(ctx->pinned_out);
     for (int i = 0; i < 6; i++) if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);

@@ -1,5 +1,6 @@
 // common.cuh -- context, error plumbing and launch helpers shared by the kernels of libgasr.so.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -55,7 +56,7 @@ struct gasr_ctx {
     long long launches = 0;
     size_t device_bytes = 0, host_bytes = 0;
     std::map<void *, size_t> dev_blocks, host_blocks;
-    gasr::Workspace ws_ctc, ws_rnn, ws_misc, ws_out;
+    gasr::Workspace ws_ctc, ws_rnn, ws_misc, ws_out, ws_gru;
     void *pinned_out = nullptr;          // pinned staging for decode results
     size_t pinned_out_bytes = 0;
     long long ctc_fallback_frames = 0, ctc_survivors = 0;   // diagnostics of the last decode
@@ -87,6 +88,10 @@ size_t xproj_tc_a_bytes(int M, int K);      // scratch for the bf16 hi/lo planes
 size_t xproj_tc_w_bytes(int K, int N);      // prepared (transposed, split) weights
 int xproj_tc_prepare_weights(gasr_ctx *ctx, const float *W, int K, int N, void *wbuf, cudaStream_t st);
 int xproj_tc_split_rows(gasr_ctx *ctx, const float *A, int lda, int M, int K, void *abuf, cudaStream_t st);
+struct XprojTcPlan { CUtensorMap maps[4]; int M, K, N; void *abuf; };
+int xproj_tc_plan(XprojTcPlan &pl, int M, int K, int N, const void *wbuf, void *abuf);
+int xproj_tc_run(gasr_ctx *ctx, const XprojTcPlan &pl, const float *A, int lda, const float *bias, float *C, int ldc,
+                 int precision, cudaStream_t st);
 int xproj_tc_split_rows_range(gasr_ctx *ctx, const float *A, int lda, int M_total, int row0, int nrows, int K, void *abuf,
                               cudaStream_t st);
 int launch_xproj_tc(gasr_ctx *ctx, const float *A, int lda, int M, int K, int N, const void *wbuf, void *abuf,

@@ -93,6 +93,26 @@ __global__ void gru_step_kernel(const float *__restrict__ xp, int ldxp, const fl
     out[(size_t)n * ldo + j] = (1.0f - z) * nn + z * hj;
 }
 
+// GRU gates once the hidden-side products hh = h_{t-1} * W_hh + b_hh are known (one GEMM per timestep): torch.nn.GRU,
+// gate order r, z, n; xp already holds x * W_ih + b_ih.  hh == nullptr: first step, h_0 = 0, so hh is just b_hh.
+__global__ void gru_gate_kernel(const float *__restrict__ xp, int ldxp, const float *__restrict__ hh, const float *__restrict__ b_hh,
+                                const float *__restrict__ hprev, int ldh, float *__restrict__ out, int ldo, int N, int H) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = blockIdx.y;
+    if (j >= H) return;
+    const float *xr = xp + (size_t)n * ldxp;
+    float gr, gz, gn, hj = 0.0f;
+    if (hh != nullptr) {
+        const float *hr = hh + (size_t)n * 3 * H;
+        gr = hr[j]; gz = hr[H + j]; gn = hr[2 * H + j];
+        hj = hprev[(size_t)n * ldh + j];
+    } else { gr = b_hh[j]; gz = b_hh[H + j]; gn = b_hh[2 * H + j]; }
+    const float r = sigmoid_f(xr[j] + gr);
+    const float z = sigmoid_f(xr[H + j] + gz);
+    const float nn = tanhf(xr[2 * H + j] + r * gn);
+    out[(size_t)n * ldo + j] = (1.0f - z) * nn + z * hj;
+}
+
 // ---- persistent cluster kernel (tanh) ------------------------------------------------------------------------
 constexpr int RC_NB = 16;     // utterances per cluster
 constexpr int RC_HC = 64;     // hidden columns per CTA
@@ -446,8 +466,37 @@ int launch_rnn_recurrence(gasr_ctx *ctx, const RnnLayerArgs &a, cudaStream_t st)
         ctx->launches += 1;
         return GASR_OK;
     }
-    // fallback: one kernel per timestep
     GASR_CHECK(a.N <= 65535, "rnn_recurrence: batch too large for the per-step path");
+    const char *force_g = getenv("GASR_GRU");
+    if (a.cell == GASR_CELL_GRU && !(force_g && force_g[0] == 's') && a.N >= 32 && xproj_tc_supported(a.N, a.H, 3 * a.H) &&
+        a.s0 == 0 && (a.s1 == 0 || a.s1 == a.T)) {
+        // GRU with a real batch: per timestep ONE tcgen05 GEMM hh = h_{t-1} * W_hh + b_hh (fp32-grade 3 x bf16 split,
+        // W_hh^T prepared once, TMA descriptors reused) + one gate kernel, instead of a kernel that streams W_hh from L2
+        // for every (utterance, column) thread
+        const int H = a.H, G3 = 3 * a.H;
+        const size_t wb = align_up(xproj_tc_w_bytes(H, G3), 1024), ab = align_up(xproj_tc_a_bytes(a.N, H), 1024);
+        const size_t hb = align_up(sizeof(float) * (size_t)a.N * G3, 1024);
+        GASR_TRY(ws_reserve(ctx, ctx->ws_gru, wb + ab + hb + 1024));
+        unsigned char *base = static_cast<unsigned char *>(ctx->ws_gru.ptr);
+        float *hh = reinterpret_cast<float *>(base + wb + ab);
+        GASR_TRY(xproj_tc_prepare_weights(ctx, a.w_hh, H, G3, base, st));
+        XprojTcPlan pl;
+        GASR_TRY(xproj_tc_plan(pl, a.N, H, G3, base, base + wb));
+        dim3 ggrid(ceil_div(H, 128), a.N);
+        for (int s = 0; s < a.T; s++) {
+            const int t = a.reverse ? a.T - 1 - s : s;
+            const int tp = a.reverse ? t + 1 : t - 1;
+            const float *xp = a.xproj + (size_t)t * a.N * a.ldxp;
+            float *o = a.out + (size_t)t * a.N * a.ldo + a.col0;
+            const float *hp = s == 0 ? nullptr : a.out + (size_t)tp * a.N * a.ldo + a.col0;
+            if (s > 0) GASR_TRY(xproj_tc_run(ctx, pl, hp, a.ldo, a.b_hh, hh, G3, GASR_PREC_FP32, st));
+            gru_gate_kernel<<<ggrid, 128, 0, st>>>(xp, a.ldxp, s > 0 ? hh : nullptr, a.b_hh, hp, a.ldo, o, a.ldo, a.N, H);
+            ctx->launches += 1;
+        }
+        GASR_CUDA(cudaGetLastError());
+        return GASR_OK;
+    }
+    // fallback: one kernel per timestep
     dim3 grid(ceil_div(a.H, 128), a.N);
     for (int s = a.s0; s < (a.s1 > 0 ? a.s1 : a.T); s++) {
         const int t = a.reverse ? a.T - 1 - s : s;

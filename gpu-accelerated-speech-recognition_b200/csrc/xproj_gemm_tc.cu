@@ -252,38 +252,46 @@ int xproj_tc_split_rows_range(gasr_ctx *ctx, const float *A, int lda, int M_tota
     return GASR_OK;
 }
 
-// C[M, N] = A[M, K] * W + bias with W prepared by xproj_tc_prepare_weights; abuf is scratch of xproj_tc_a_bytes(M, K).
-int launch_xproj_tc(gasr_ctx *ctx, const float *A, int lda, int M, int K, int N, const void *wbuf, void *abuf,
-                    const float *bias, float *C, int ldc, int precision, cudaStream_t st) {
+// A reusable launch plan: the four TMA descriptors of a fixed (A scratch, prepared W) pair.  Building descriptors costs
+// microseconds of host time per call, which matters when the same GEMM runs once per timestep (GRU recurrence).
+int xproj_tc_plan(XprojTcPlan &pl, int M, int K, int N, const void *wbuf, void *abuf) {
     GASR_CHECK(xproj_tc_supported(M, K, N), "xproj_tc: unsupported shape M=%d K=%d N=%d", M, K, N);
-    GASR_CHECK(ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0, "xproj_tc: output must be 16-byte aligned");
     const int Kp = ceil_div(K, TC_BK) * TC_BK;
-    __nv_bfloat16 *a_hi = static_cast<__nv_bfloat16 *>(abuf);
-    __nv_bfloat16 *a_lo = reinterpret_cast<__nv_bfloat16 *>(static_cast<unsigned char *>(abuf) + xproj_tc_a_bytes(M, K) / 2);
-    const __nv_bfloat16 *w_hi = static_cast<const __nv_bfloat16 *>(wbuf);
-    const __nv_bfloat16 *w_lo = reinterpret_cast<const __nv_bfloat16 *>(static_cast<const unsigned char *>(wbuf) + xproj_tc_w_bytes(K, N) / 2);
-    {
-        const size_t total = (size_t)M * (Kp / 2);
-        int blocks = (int)((total + 255) / 256);
-        if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
-        split_rows_kernel<<<blocks, 256, 0, st>>>(A, lda, M, K, Kp, a_hi, a_lo);
-        GASR_CUDA(cudaGetLastError());
-        ctx->launches += 1;
-    }
-    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-    GASR_TRY(tc_make_map(&ma_hi, a_hi, M, Kp, TC_BM));
-    GASR_TRY(tc_make_map(&ma_lo, a_lo, M, Kp, TC_BM));
-    GASR_TRY(tc_make_map(&mb_hi, w_hi, N, Kp, TC_BM));
-    GASR_TRY(tc_make_map(&mb_lo, w_lo, N, Kp, TC_BM));
+    pl.M = M; pl.K = K; pl.N = N; pl.abuf = abuf;
+    unsigned char *ab = static_cast<unsigned char *>(abuf);
+    const unsigned char *wb = static_cast<const unsigned char *>(wbuf);
+    GASR_TRY(tc_make_map(&pl.maps[0], ab, M, Kp, TC_BM));
+    GASR_TRY(tc_make_map(&pl.maps[1], ab + xproj_tc_a_bytes(M, K) / 2, M, Kp, TC_BM));
+    GASR_TRY(tc_make_map(&pl.maps[2], wb, N, Kp, TC_BM));
+    GASR_TRY(tc_make_map(&pl.maps[3], wb + xproj_tc_w_bytes(K, N) / 2, N, Kp, TC_BM));
+    return GASR_OK;
+}
+
+// C[M, N] = A[M, K] * W + bias through a plan: split A into the plan's bf16 planes, then the tcgen05 GEMM
+int xproj_tc_run(gasr_ctx *ctx, const XprojTcPlan &pl, const float *A, int lda, const float *bias, float *C, int ldc,
+                 int precision, cudaStream_t st) {
+    GASR_CHECK(ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0, "xproj_tc: output must be 16-byte aligned");
+    GASR_TRY(xproj_tc_split_rows(ctx, A, lda, pl.M, pl.K, pl.abuf, st));
     TcParams p;
-    p.M = M; p.N = N; p.kblocks = Kp / TC_BK; p.terms = precision == GASR_PREC_BF16 ? 1 : 3;
+    p.M = pl.M; p.N = pl.N; p.kblocks = ceil_div(pl.K, TC_BK); p.terms = precision == GASR_PREC_BF16 ? 1 : 3;
     p.C = C; p.ldc = ldc; p.bias = bias;
-    GASR_CUDA(cudaFuncSetAttribute(xproj_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    dim3 grid(ceil_div(N, TC_BN), ceil_div(M, TC_BM));   // TMA zero-fills the rows of W^T beyond N
-    xproj_tcgen05_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+    if (!(ctx->attr_mask & 1024u)) {
+        GASR_CUDA(cudaFuncSetAttribute(xproj_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        ctx->attr_mask |= 1024u;
+    }
+    dim3 grid(ceil_div(pl.N, TC_BN), ceil_div(pl.M, TC_BM));   // TMA zero-fills the rows of W^T beyond N
+    xproj_tcgen05_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(pl.maps[0], pl.maps[1], pl.maps[2], pl.maps[3], p);
     GASR_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return GASR_OK;
+}
+
+// C[M, N] = A[M, K] * W + bias with W prepared by xproj_tc_prepare_weights; abuf is scratch of xproj_tc_a_bytes(M, K).
+int launch_xproj_tc(gasr_ctx *ctx, const float *A, int lda, int M, int K, int N, const void *wbuf, void *abuf,
+                    const float *bias, float *C, int ldc, int precision, cudaStream_t st) {
+    XprojTcPlan pl;
+    GASR_TRY(xproj_tc_plan(pl, M, K, N, wbuf, abuf));
+    return xproj_tc_run(ctx, pl, A, lda, bias, C, ldc, precision, st);
 }
 
 }  // namespace gasr

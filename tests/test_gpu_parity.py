@@ -383,6 +383,18 @@ def test_gru_bidirectional_cfg3_width(gasr, ctx, O):
         assert np.abs(out[l] - ref[l]).max() < AM_TOL, f"layer {l}"
 
 
+@pytest.mark.parametrize("T,N,D,H,L", [(9, 32, 40, 64, 2), (5, 48, 161, 800, 1)])
+def test_gru_batched_recurrence_gemm_path(gasr, ctx, O, T, N, D, H, L):
+    """Batches of >= 32 utterances take the GRU path that runs h * W_hh as one tcgen05 GEMM per timestep."""
+    import synth
+    x = synth.spectrogram_batch(51, T, N, D)
+    w_ih, w_hh, b_ih, b_hh = synth.rnn_weights(52, D, H, L, cell_gates=3, bidir=True)
+    out = _run_rnn(gasr, ctx, gasr.CELL_GRU, True, T, N, D, H, L, x, w_ih, w_hh, b_ih, b_hh)
+    ref = O.gru_forward(x, T, N, H, L, True, w_ih, w_hh, b_ih, b_hh)
+    for l in range(L):
+        assert np.abs(out[l] - ref[l]).max() < AM_TOL, f"layer {l}"
+
+
 def test_pipeline_cfg3_style_gru_bf16_projection(gasr, ctx, O):
     """cfg3 in miniature through the fused entry point: bidirectional GRU stack, beam 32, bf16 input projection.
     Stated tolerance of the bf16 mode: 2e-2 on the log-probabilities; transcripts of the utterances whose fp32 / bf16
