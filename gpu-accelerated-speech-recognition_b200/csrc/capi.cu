@@ -130,7 +130,9 @@ int gasr_ctx_destroy(gasr_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->dev_blocks) cudaFree(kv.first);
     for (auto &kv : ctx->host_blocks) cudaFreeHost(kv.first);
-    Workspace *wss[] = {&ctx->ws_ctc, &ctx->ws_rnn, &ctx->ws_misc, &ctx->ws_out, &ctx->ws_gru};
+    Workspace *wss[] = {&ctx->ws_ctc, &ctx->ws_rnn, &ctx->ws_misc, &ctx->ws_out, &ctx->ws_gru, &ctx->ws_rnn_b, &ctx->ws_misc_b, &ctx->ws_gru_b};
+    for (cudaEvent_t e : ctx->ev_bi) if (e) cudaEventDestroy(e);
+    for (auto &g : ctx->step_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (Workspace *w : wss) if (w->ptr) cudaFree(w->ptr);
     if (ctx->pinned_out) cudaFreeHost(ctx->pinned_out);
     for (int i = 0; i < 6; i++) if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
@@ -378,8 +380,9 @@ static int rnn_layer_direction(gasr_ctx *ctx, int cell, int T, int N, int in_l, 
     if (use_tc) {
         // tensor-core path: W^T and A are split into bf16 hi/lo planes in the misc workspace
         const size_t wb = xproj_tc_w_bytes(in_l, G * H), ab = xproj_tc_a_bytes(T * N, in_l);
-        GASR_TRY(ws_reserve(ctx, ctx->ws_misc, wb + ab + 2048));
-        unsigned char *base = static_cast<unsigned char *>(ctx->ws_misc.ptr);
+        Workspace &wsm = ctx->ws_sel ? ctx->ws_misc_b : ctx->ws_misc;
+        GASR_TRY(ws_reserve(ctx, wsm, wb + ab + 2048));
+        unsigned char *base = static_cast<unsigned char *>(wsm.ptr);
         GASR_TRY(xproj_tc_prepare_weights(ctx, w_ih, in_l, G * H, base, st));
         GASR_TRY(launch_xproj_tc(ctx, src, ld_src, T * N, in_l, G * H, base, base + align_up(wb, 1024), bias, xproj, G * H,
                                  precision, st));
@@ -406,19 +409,41 @@ int rnn_forward_impl(gasr_ctx *ctx, int cell, int bidir, int T, int N, int in, i
     if (T == 0 || N == 0) return GASR_OK;
     const size_t xp_bytes = align_up(sizeof(float) * (size_t)T * N * G * H, 256);
     GASR_TRY(ws_reserve(ctx, ctx->ws_rnn, xp_bytes + align_up(sizeof(float) * G * H, 256)));
-    float *xproj = static_cast<float *>(ctx->ws_rnn.ptr);
-    float *bias = reinterpret_cast<float *>(static_cast<unsigned char *>(ctx->ws_rnn.ptr) + xp_bytes);
-    for (int l = 0; l < L; l++) {
+    // the two directions of a bidirectional layer are independent (same input, disjoint output columns): the backward one
+    // runs on a side stream with its own workspaces
+    const bool fork = D == 2 && st == ctx->stream && !getenv("GASR_BIDIR_SERIAL");
+    if (fork) {
+        GASR_TRY(ws_reserve(ctx, ctx->ws_rnn_b, xp_bytes + align_up(sizeof(float) * G * H, 256)));
+        for (cudaEvent_t &e : ctx->ev_bi)
+            if (e == nullptr) GASR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    cudaStream_t st_b = fork ? ctx->side[5] : st;
+    int rc = GASR_OK;
+    for (int l = 0; l < L && rc == GASR_OK; l++) {
         const int in_l = l == 0 ? in : D * H;
         const float *src = l == 0 ? x : hiddens[l - 1];
-        for (int d = 0; d < D; d++) {
+        if (fork) {
+            GASR_CUDA(cudaEventRecord(ctx->ev_bi[0], st));
+            GASR_CUDA(cudaStreamWaitEvent(st_b, ctx->ev_bi[0], 0));
+        }
+        for (int d = 0; d < D && rc == GASR_OK; d++) {
             const int i = l * D + d;
             GASR_CHECK(w_ih[i] && w_hh[i] && b_ih[i] && b_hh[i] && hiddens[l], "rnn_forward: null layer parameter");
-            GASR_TRY(rnn_layer_direction(ctx, cell, T, N, in_l, H, src, in_l, w_ih[i], w_hh[i], b_ih[i], b_hh[i], d,
-                                         hiddens[l], D * H, d * H, precision, xproj, bias, st, prof));
+            const bool side = fork && d == 1;
+            Workspace &wr = side ? ctx->ws_rnn_b : ctx->ws_rnn;
+            float *xproj = static_cast<float *>(wr.ptr);
+            float *bias = reinterpret_cast<float *>(static_cast<unsigned char *>(wr.ptr) + xp_bytes);
+            ctx->ws_sel = side ? 1 : 0;
+            rc = rnn_layer_direction(ctx, cell, T, N, in_l, H, src, in_l, w_ih[i], w_hh[i], b_ih[i], b_hh[i], d,
+                                     hiddens[l], D * H, d * H, precision, xproj, bias, side ? st_b : st, side ? nullptr : prof);
+            ctx->ws_sel = 0;
+        }
+        if (fork) {
+            GASR_CUDA(cudaEventRecord(ctx->ev_bi[1], st_b));
+            GASR_CUDA(cudaStreamWaitEvent(st, ctx->ev_bi[1], 0));
         }
     }
-    return GASR_OK;
+    return rc;
 }
 
 }  // namespace gasr

@@ -7,6 +7,7 @@
 
 #include <map>
 #include <string>
+#include <vector>
 
 #include "gasr.h"
 
@@ -57,6 +58,12 @@ struct gasr_ctx {
     size_t device_bytes = 0, host_bytes = 0;
     std::map<void *, size_t> dev_blocks, host_blocks;
     gasr::Workspace ws_ctc, ws_rnn, ws_misc, ws_out, ws_gru;
+    gasr::Workspace ws_rnn_b, ws_misc_b, ws_gru_b;   // second set: the backward direction of a bidirectional layer runs concurrently
+    int ws_sel = 0;                      // which set the recurrent-layer helpers use (0 / 1)
+    // instantiated CUDA graphs of launch-bound per-timestep loops (GRU recurrence), keyed by their operands
+    struct StepGraph { const void *k[5]; int dims[8]; cudaGraphExec_t exec; };
+    std::vector<StepGraph> step_graphs;
+    cudaEvent_t ev_bi[2] = {nullptr, nullptr};
     void *pinned_out = nullptr;          // pinned staging for decode results
     size_t pinned_out_bytes = 0;
     long long ctc_fallback_frames = 0, ctc_survivors = 0;   // diagnostics of the last decode

@@ -18,6 +18,7 @@
 #include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "rnn_stream.cuh"
@@ -476,23 +477,67 @@ int launch_rnn_recurrence(gasr_ctx *ctx, const RnnLayerArgs &a, cudaStream_t st)
         const int H = a.H, G3 = 3 * a.H;
         const size_t wb = align_up(xproj_tc_w_bytes(H, G3), 1024), ab = align_up(xproj_tc_a_bytes(a.N, H), 1024);
         const size_t hb = align_up(sizeof(float) * (size_t)a.N * G3, 1024);
-        GASR_TRY(ws_reserve(ctx, ctx->ws_gru, wb + ab + hb + 1024));
-        unsigned char *base = static_cast<unsigned char *>(ctx->ws_gru.ptr);
+        Workspace &wsg = ctx->ws_sel ? ctx->ws_gru_b : ctx->ws_gru;
+        GASR_TRY(ws_reserve(ctx, wsg, wb + ab + hb + 1024));
+        unsigned char *base = static_cast<unsigned char *>(wsg.ptr);
         float *hh = reinterpret_cast<float *>(base + wb + ab);
         GASR_TRY(xproj_tc_prepare_weights(ctx, a.w_hh, H, G3, base, st));
         XprojTcPlan pl;
         GASR_TRY(xproj_tc_plan(pl, a.N, H, G3, base, base + wb));
         dim3 ggrid(ceil_div(H, 128), a.N);
-        for (int s = 0; s < a.T; s++) {
-            const int t = a.reverse ? a.T - 1 - s : s;
-            const int tp = a.reverse ? t + 1 : t - 1;
-            const float *xp = a.xproj + (size_t)t * a.N * a.ldxp;
-            float *o = a.out + (size_t)t * a.N * a.ldo + a.col0;
-            const float *hp = s == 0 ? nullptr : a.out + (size_t)tp * a.N * a.ldo + a.col0;
-            if (s > 0) GASR_TRY(xproj_tc_run(ctx, pl, hp, a.ldo, a.b_hh, hh, G3, GASR_PREC_FP32, st));
-            gru_gate_kernel<<<ggrid, 128, 0, st>>>(xp, a.ldxp, s > 0 ? hh : nullptr, a.b_hh, hp, a.ldo, o, a.ldo, a.N, H);
-            ctx->launches += 1;
+        auto issue_steps = [&]() -> int {
+            for (int s = 0; s < a.T; s++) {
+                const int t = a.reverse ? a.T - 1 - s : s;
+                const int tp = a.reverse ? t + 1 : t - 1;
+                const float *xp = a.xproj + (size_t)t * a.N * a.ldxp;
+                float *o = a.out + (size_t)t * a.N * a.ldo + a.col0;
+                const float *hp = s == 0 ? nullptr : a.out + (size_t)tp * a.N * a.ldo + a.col0;
+                if (s > 0) GASR_TRY(xproj_tc_run(ctx, pl, hp, a.ldo, a.b_hh, hh, G3, GASR_PREC_FP32, st));
+                gru_gate_kernel<<<ggrid, 128, 0, st>>>(xp, a.ldxp, s > 0 ? hh : nullptr, a.b_hh, hp, a.ldo, o, a.ldo, a.N, H);
+                ctx->launches += 1;
+            }
+            return GASR_OK;
+        };
+        // 3 launches per timestep: the loop is launch-bound from the host.  The whole T-step sequence is captured once
+        // into a CUDA graph (operands are stable across calls: workspaces, weights, layer buffers) and replayed.
+        if (a.T >= 64 && !getenv("GASR_NO_GRAPH")) {
+            gasr_ctx::StepGraph key = {};
+            key.k[0] = a.xproj; key.k[1] = a.out; key.k[2] = a.w_hh; key.k[3] = base; key.k[4] = a.b_hh;
+            const int dims[8] = {a.T, a.N, H, a.reverse, a.col0, a.ldo, a.ldxp, 0};
+            memcpy(key.dims, dims, sizeof(dims));
+            for (auto &g : ctx->step_graphs)
+                if (memcmp(g.k, key.k, sizeof(key.k)) == 0 && memcmp(g.dims, key.dims, sizeof(key.dims)) == 0) {
+                    GASR_CUDA(cudaGraphLaunch(g.exec, st));
+                    ctx->launches += 3LL * a.T - 2;
+                    return GASR_OK;
+                }
+            if (!(ctx->attr_mask & 1024u)) {          // function attributes cannot be set while capturing: warm the GEMM up
+                GASR_TRY(xproj_tc_run(ctx, pl, a.out + a.col0, a.ldo, a.b_hh, hh, G3, GASR_PREC_FP32, st));
+            }
+            cudaGraph_t graph = nullptr;
+            const long long launches0 = ctx->launches;
+            GASR_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const int rc = issue_steps();
+            const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc != GASR_OK || ce != cudaSuccess || graph == nullptr) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                ctx->launches = launches0;
+                GASR_TRY(issue_steps());              // capture unavailable: plain launches
+                GASR_CUDA(cudaGetLastError());
+                return GASR_OK;
+            }
+            GASR_CUDA(cudaGraphInstantiate(&key.exec, graph, 0));
+            cudaGraphDestroy(graph);
+            if (ctx->step_graphs.size() >= 64) {      // bounded cache
+                cudaGraphExecDestroy(ctx->step_graphs.front().exec);
+                ctx->step_graphs.erase(ctx->step_graphs.begin());
+            }
+            ctx->step_graphs.push_back(key);
+            GASR_CUDA(cudaGraphLaunch(key.exec, st));
+            return GASR_OK;
         }
+        GASR_TRY(issue_steps());
         GASR_CUDA(cudaGetLastError());
         return GASR_OK;
     }

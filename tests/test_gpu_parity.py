@@ -383,7 +383,7 @@ def test_gru_bidirectional_cfg3_width(gasr, ctx, O):
         assert np.abs(out[l] - ref[l]).max() < AM_TOL, f"layer {l}"
 
 
-@pytest.mark.parametrize("T,N,D,H,L", [(9, 32, 40, 64, 2), (5, 48, 161, 800, 1)])
+@pytest.mark.parametrize("T,N,D,H,L", [(9, 32, 40, 64, 2), (5, 48, 161, 800, 1), (70, 32, 40, 64, 1)])   # T >= 64: CUDA-graph replay
 def test_gru_batched_recurrence_gemm_path(gasr, ctx, O, T, N, D, H, L):
     """Batches of >= 32 utterances take the GRU path that runs h * W_hh as one tcgen05 GEMM per timestep."""
     import synth
@@ -393,6 +393,9 @@ def test_gru_batched_recurrence_gemm_path(gasr, ctx, O, T, N, D, H, L):
     ref = O.gru_forward(x, T, N, H, L, True, w_ih, w_hh, b_ih, b_hh)
     for l in range(L):
         assert np.abs(out[l] - ref[l]).max() < AM_TOL, f"layer {l}"
+    if T >= 64:   # second call with fresh buffers: a cached graph must not be replayed onto stale operands
+        out2 = _run_rnn(gasr, ctx, gasr.CELL_GRU, True, T, N, D, H, L, x, w_ih, w_hh, b_ih, b_hh)
+        assert all(np.array_equal(a, b) for a, b in zip(out, out2))
 
 
 def test_pipeline_cfg3_style_gru_bf16_projection(gasr, ctx, O):
