@@ -37,7 +37,7 @@ constexpr int RS_NB = 16;                  // utterances per cluster
 constexpr int RS_SUB = 8;                  // utterances per sub-batch (MMA N)
 constexpr int RS_HC = 64;                  // hidden columns per CTA
 constexpr int RS_MATH_WARPS = 8;
-constexpr int RS_SIGNAL_BLOCKS = 2;        // progress is published once per this many blocks
+constexpr int RS_SIGNAL_BLOCKS = 4;        // progress is published (and the warps are counted) once per this many blocks
 constexpr int RS_THREADS = 32 * RS_MATH_WARPS;
 constexpr unsigned long long RS_TIMEOUT_NS = 2000000000ull;   // watchdog for every spin on a flag
 
@@ -83,6 +83,14 @@ __device__ __forceinline__ unsigned long long rs_now_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
+}
+// tanh(x) = 1 - 2 / (2^(2x log2 e) + 1) on the SFU (ex2.approx, rcp.approx): absolute error ~1e-7 over the whole range
+// (the fp32 libm tanhf costs 32 instructions per value on the step's critical path; the parity bar is 1e-4 absolute)
+__device__ __forceinline__ float rs_tanh(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
 }
 __device__ __forceinline__ void rs_split(float x, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
     hi = __float2bfloat16_rn(x);
@@ -289,7 +297,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_stream_kernel(const RnnStre
             const float2 o = xch_peer[sub * 256];
             const float a0 = kh == 0 ? c[0] + o.x : o.x + c[2];
             const float a1 = kh == 0 ? c[1] + o.y : o.y + c[3];
-            const float v0 = tanhf((sub ? xc10 : xc00) + a0), v1 = tanhf((sub ? xc11 : xc01) + a1);
+            const float v0 = rs_tanh((sub ? xc10 : xc00) + a0), v1 = rs_tanh((sub ? xc11 : xc01) + a1);
             if (sub == 0 && pend_hi >= 0) {        // (lane 0 of one warp per CTA, once per RS_SIGNAL_BLOCKS blocks)
                 __threadfence();
                 for (int b2 = pend_hi - (RS_SIGNAL_BLOCKS - 1); b2 <= pend_hi; b2++) atomicAdd(hdone + b2, 1u);
@@ -324,12 +332,13 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_stream_kernel(const RnnStre
         // the CTA's outstanding stores, so it is DEFERRED to the middle of the next step (pend_hi), when those stores have
         // long been acknowledged, and issued once per RS_SIGNAL_BLOCKS blocks.
         if (++fcnt == fpb || !more) {
-            if (hdone != nullptr) {
+            if (hdone != nullptr && ((blk + 1) % RS_SIGNAL_BLOCKS == 0 || !more)) {
                 __syncwarp();
                 if (lane == 0) {
                     __threadfence_block();
-                    const int last = (atomicAdd(const_cast<int *>(ctl + (blk & 1)), 1) & (RS_MATH_WARPS - 1)) == RS_MATH_WARPS - 1;
-                    if (last && ((blk + 1) % RS_SIGNAL_BLOCKS == 0 || !more)) {
+                    const int grp_par = (blk / RS_SIGNAL_BLOCKS) & 1;
+                    const int last = (atomicAdd(const_cast<int *>(ctl + grp_par), 1) & (RS_MATH_WARPS - 1)) == RS_MATH_WARPS - 1;
+                    if (last) {
                         pend_hi = blk;
                         if (!more) {
                             __threadfence();
@@ -347,11 +356,10 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_stream_kernel(const RnnStre
 }
 
 // =====================================================================================================================
-// Second generation: NSUB (2 or 4) sub-batches of 8 utterances per cluster and a LEADER / FOLLOWER schedule of the two
-// K-half warps that share an SM sub-partition (see the comment at the main loop): their MMA bursts alternate on the
-// tensor pipe and each warp's epilogue (K-half exchange, tanh, bf16 split, stores, DSMEM send) hides under the partner's
-// burst.  With 4 sub-batches a cluster serves 32 utterances: cfg2's layer stack needs 48 SMs instead of 96 -- the SMs the
-// decoder needs to run one CTA per SM.
+// Second generation: NSUB (2 or 4) sub-batches of 8 utterances per cluster, processed in GROUPS of two: the MMAs of both
+// sub-batches of a group are issued back to back, then one joint epilogue runs their two independent dependency chains
+// interleaved (see the comment at the main loop).  With 4 sub-batches a cluster serves 32 utterances: cfg2's layer stack
+// needs 48 SMs instead of 96 -- the SMs the decoder needs to run one CTA per SM.
 // =====================================================================================================================
 __device__ __forceinline__ void rs_mma_nv(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
@@ -367,7 +375,7 @@ struct Rs2Layout {
     static constexpr int OFF_H = 0;                                  // [sub NSUB][parity 2][plane 2][8][HSB]
     static constexpr int OFF_XCH = OFF_H + NSUB * 2 * HBUF;          // [sub NSUB][ch 4][kh 2][32] float2
     static constexpr int OFF_STG = OFF_XCH + NSUB * 2048;            // [warp 8][plane 2][utt 8][16 B]
-    static constexpr int OFF_BAR = OFF_STG + RS_MATH_WARPS * 256;    // mbar[sub NSUB][parity 2]
+    static constexpr int OFF_BAR = OFF_STG + 2 * RS_MATH_WARPS * 256;  // (two staging tiles per warp) mbar[sub NSUB][parity 2]
     static constexpr int OFF_CTL = OFF_BAR + NSUB * 2 * 8;           // int: [0], [1] warp arrivals by block parity, [2] abort, [4..11] per-warp sequence numbers
     static constexpr int BYTES = OFF_CTL + 48;
     static constexpr uint32_t TX = 2u * RS_SUB * H * 2u;
@@ -480,150 +488,131 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_stream2_kernel(const RnnStr
         if (atomicAdd(p.started, 1u) == gridDim.x - 1) { *p.host_go = p.epoch; __threadfence_system(); }
     }
 
-    // pipeline registers: the sub-step whose epilogue is pending
-    float pc0 = 0.f, pc1 = 0.f, pc2 = 0.f, pc3 = 0.f;    // its summed accumulators
-    float px0 = 0.f, px1 = 0.f;                          // its xproj values
-    int psub = 0, ps = 0;
-
-    const int Q = T * NSUB;
-    int s = 0, sub = 0;
-    // Leader / follower schedule.  The two warps of an SM sub-partition are the K-half partners (ch, 0) and (ch, 1).  Each
-    // slot is an MMA BURST (48 back-to-back MMAs at H = 512) followed by a long epilogue.  The follower (kh = 1) runs half
-    // a slot behind the leader, so their bursts alternate on the sub-partition's tensor pipe instead of colliding, and
-    // each warp's epilogue hides under the partner's burst.  The leader finalises sub-step q - 1 after its burst of q (its
-    // partner's partial of q - 1 was published half a slot earlier); the follower finalises q right after its own burst.
-    // Partials are handed over through shared memory with per-warp sequence numbers (no barrier: a barrier would
-    // re-align the two warps).
-    volatile int *seq = reinterpret_cast<volatile int *>(smem + LT::OFF_CTL) + 4;    // [8] sub-steps published by each warp
-    const int partner = warp ^ 4;
-    if (kh) {                                            // initial half-slot offset of the followers
-        const long long t0 = clock64();
-        while (clock64() - t0 < 700) { }
-    }
-    auto burst = [&](float &c0, float &c1, float &c2, float &c3, float &xn0, float &xn1) {
+    // Grouped schedule: the sub-batches of a step are processed in groups of GP = 2.  A group first issues the MMAs of both
+    // of its sub-batches back to back (the tensor pipe stays busy for 2 x 48 MMAs per warp), then runs ONE joint epilogue
+    // whose two independent dependency chains (K-half exchange, tanh, bf16 split, staging, stores, DSMEM send) interleave.
+    // With NSUB = 4 a step is two such groups, and the h a group sends has a whole other group's time to cross DSMEM.
+    constexpr int GP = 2, NG = NSUB / GP;
+    unsigned char *const stg2[GP] = {stg, smem + LT::OFF_STG + RS_MATH_WARPS * 256 + warp * 256};
+    for (int s = 0; s < T; s++) {
         const int par = s & 1;
-        if (sub == 0 && ready_blocks < nblocks) advance_blocks(s);
-        const int n = nA + RS_SUB * sub;
-        xn0 = 0.f; xn1 = 0.f;
-        if (n < N) xn0 = __ldcg(xp_base + xoff + sub * ldxp8);
-        if (n + 1 < N) xn1 = __ldcg(xp_base + xoff + sub * ldxp8 + ldxp1);
-        const int bi = sub * 2 + par;
-        const uint32_t bar = bar0 + 8 * bi;
-        if (s > 0) {
-            const uint32_t ph = (phase_bits >> bi) & 1u;
-            if (!rs_mbar_try(bar, ph)) {
-                const unsigned long long t0 = rs_now_ns();
-                int spins = 0;
-                while (!rs_mbar_try(bar, ph))
-                    if (ctl[2] || ((++spins & 255) == 0 && ((p.abort && *p.abort) || rs_now_ns() - t0 > RS_TIMEOUT_NS))) {
-                        ctl[2] = 1; if (p.abort) *p.abort = 1u; break;
-                    }
-            }
-            phase_bits ^= 1u << bi;
-            if (tid == 0) rs_mbar_expect_tx(bar, LT::TX);
-        }
-        const uint32_t hb = sbase + LT::OFF_H + bi * LT::HBUF + lm_off;
-        float cm0[4] = {0.f, 0.f, 0.f, 0.f}, cm1[4] = {0.f, 0.f, 0.f, 0.f};
-        float cs0[4] = {0.f, 0.f, 0.f, 0.f}, cs1[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t bh[2][4], bl[2][4];
-        rs_ldmatrix_x4(bh[0], hb);
-        rs_ldmatrix_x4(bl[0], hb + LT::PLANE);
+        const bool more = s + 1 < T;
+        if (ready_blocks < nblocks) advance_blocks(s);
 #pragma unroll
-        for (int kp = 0; kp < KP; kp++) {
-            const int cb = kp & 1, nb = cb ^ 1;
-            if (kp + 1 < KP) {                           // operands of the next k-pair are in flight while this one multiplies
-                rs_ldmatrix_x4(bh[nb], hb + (kp + 1) * 64);
-                rs_ldmatrix_x4(bl[nb], hb + LT::PLANE + (kp + 1) * 64);
-            }
-            rs_mma_nv(cm0, ahi[2 * kp], bh[cb][0], bh[cb][1]);
-            rs_mma_nv(cm1, ahi[2 * kp + 1], bh[cb][2], bh[cb][3]);
-            rs_mma_nv(cs0, ahi[2 * kp], bl[cb][0], bl[cb][1]);
-            rs_mma_nv(cs1, ahi[2 * kp + 1], bl[cb][2], bl[cb][3]);
-            rs_mma_nv(cs0, alo[2 * kp], bh[cb][0], bh[cb][1]);
-            rs_mma_nv(cs1, alo[2 * kp + 1], bh[cb][2], bh[cb][3]);
-        }
-        c0 = (cm0[0] + cm1[0]) + (cs0[0] + cs1[0]); c1 = (cm0[1] + cm1[1]) + (cs0[1] + cs1[1]);
-        c2 = (cm0[2] + cm1[2]) + (cs0[2] + cs1[2]); c3 = (cm0[3] + cm1[3]) + (cs0[3] + cs1[3]);
-        xch_mine[sub * 256] = kh == 0 ? make_float2(c2, c3) : make_float2(c0, c1);
-        __syncwarp();
-        if (lane == 0) { __threadfence_block(); seq[warp] = s * NSUB + sub + 1; }      // partial of this sub-step is published
-    };
-    // epilogue of sub-step (es, esub): combine with the partner's partial, tanh, publish
-    auto epilogue = [&](int es, int esub, float c0, float c1, float c2, float c3, float x0, float x1) {
-        const int need = es * NSUB + esub + 1;
-        if (seq[partner] < need) {
-            const unsigned long long t0 = rs_now_ns();
-            int spins = 0;
-            while (seq[partner] < need)
-                if (ctl[2] || ((++spins & 1023) == 0 && ((p.abort && *p.abort) || rs_now_ns() - t0 > RS_TIMEOUT_NS))) {
-                    ctl[2] = 1; if (p.abort) *p.abort = 1u; break;
-                }
-        }
-        const bool more_e = es + 1 < T;
-        const float2 o = xch_peer[esub * 256];
-        const float v0 = tanhf(x0 + (kh == 0 ? c0 + o.x : o.x + c2));
-        const float v1 = tanhf(x1 + (kh == 0 ? c1 + o.y : o.y + c3));
-        if (esub == 0 && pend_hi >= 0) {                 // deferred progress fence (lane 0 of one warp, once per RS_SIGNAL_BLOCKS)
-            __threadfence();
-            for (int b2 = pend_hi - (RS_SIGNAL_BLOCKS - 1); b2 <= pend_hi; b2++) atomicAdd(hdone + b2, 1u);
-            pend_hi = -1;
-        }
-        const int n = nA + RS_SUB * esub;
-        if (out_base != nullptr) {
-            if (n < N) out_base[ooff + esub * ldo8] = v0;
-            if (n + 1 < N) out_base[ooff + esub * ldo8 + ldo1] = v1;
-        }
-        __nv_bfloat16 h0, l0, h1, l1;
-        rs_split(v0, h0, l0);
-        rs_split(v1, h1, l1);
-        __syncwarp();
-        sg[0] = h0; sg[8] = h1; sg[64] = l0; sg[72] = l1;
-        __syncwarp();
-        const uint4 chunk = *chunk_src;
-        if (plane_lane && n0 + RS_SUB * esub + cu < N) *reinterpret_cast<uint4 *>(plane_base + poff + esub * ldp8) = chunk;
-        if (more_e) {
-            const uint32_t nb_off = (uint32_t)(esub * 2 + ((es & 1) ^ 1));
-            const uint32_t dst_local = dst_local0 + nb_off * LT::HBUF, bar_local = bar0 + 8 * nb_off;
+        for (int grp = 0; grp < NG; grp++) {
+            float c[GP][4], xn[GP][2];
+            // ---- MMA phase of the group ----
 #pragma unroll
-            for (int r = 0; r < CS / 2; r++)
-                rs_st_async_v4(rs_mapa(dst_local, r0 + r), chunk, rs_mapa(bar_local, r0 + r));
-        }
-        if (esub == NSUB - 1) {                          // this sub-step closes frame es
-            ooff += ostep;
-            poff += pstep;
-            fcnt++;
-            if (fcnt == fpb || !more_e) {
-                if (hdone != nullptr) {
-                    __syncwarp();
-                    if (lane == 0) {
-                        __threadfence_block();
-                        const int last = (atomicAdd(const_cast<int *>(ctl + (blk & 1)), 1) & (RS_MATH_WARPS - 1)) == RS_MATH_WARPS - 1;
-                        if (last && ((blk + 1) % RS_SIGNAL_BLOCKS == 0 || !more_e)) {
-                            if (more_e) pend_hi = blk;
-                            else {
-                                __threadfence();
-                                for (int b2 = blk - blk % RS_SIGNAL_BLOCKS; b2 <= blk; b2++) atomicAdd(hdone + b2, 1u);
+            for (int u = 0; u < GP; u++) {
+                const int sub = grp * GP + u;
+                const int n = nA + RS_SUB * sub;
+                xn[u][0] = 0.f; xn[u][1] = 0.f;
+                if (n < N) xn[u][0] = __ldcg(xp_base + xoff + sub * ldxp8);
+                if (n + 1 < N) xn[u][1] = __ldcg(xp_base + xoff + sub * ldxp8 + ldxp1);
+                const int bi = sub * 2 + par;
+                const uint32_t bar = bar0 + 8 * bi;
+                if (s > 0) {
+                    const uint32_t ph = (phase_bits >> bi) & 1u;
+                    if (!rs_mbar_try(bar, ph)) {
+                        const unsigned long long t0 = rs_now_ns();
+                        int spins = 0;
+                        while (!rs_mbar_try(bar, ph))
+                            if (ctl[2] || ((++spins & 255) == 0 && ((p.abort && *p.abort) || rs_now_ns() - t0 > RS_TIMEOUT_NS))) {
+                                ctl[2] = 1; if (p.abort) *p.abort = 1u; break;
                             }
+                    }
+                    phase_bits ^= 1u << bi;
+                    if (tid == 0) rs_mbar_expect_tx(bar, LT::TX);
+                }
+                const uint32_t hb = sbase + LT::OFF_H + bi * LT::HBUF + lm_off;
+                float cm0[4] = {0.f, 0.f, 0.f, 0.f}, cm1[4] = {0.f, 0.f, 0.f, 0.f};
+                float cs0[4] = {0.f, 0.f, 0.f, 0.f}, cs1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int kp = 0; kp < KP; kp++) {
+                    uint32_t bh[4], bl[4];
+                    rs_ldmatrix_x4(bh, hb + kp * 64);
+                    rs_ldmatrix_x4(bl, hb + LT::PLANE + kp * 64);
+                    rs_mma_nv(cm0, ahi[2 * kp], bh[0], bh[1]);
+                    rs_mma_nv(cm1, ahi[2 * kp + 1], bh[2], bh[3]);
+                    rs_mma_nv(cs0, ahi[2 * kp], bl[0], bl[1]);
+                    rs_mma_nv(cs1, ahi[2 * kp + 1], bl[2], bl[3]);
+                    rs_mma_nv(cs0, alo[2 * kp], bh[0], bh[1]);
+                    rs_mma_nv(cs1, alo[2 * kp + 1], bh[2], bh[3]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) c[u][i] = (cm0[i] + cm1[i]) + (cs0[i] + cs1[i]);
+                xch_mine[sub * 256] = kh == 0 ? make_float2(c[u][2], c[u][3]) : make_float2(c[u][0], c[u][1]);
+            }
+            rs_bar_sync(RS_BAR_PAIR0 + ch, 64);
+            // ---- joint epilogue of the group: two independent chains ----
+            float v[GP][2];
+#pragma unroll
+            for (int u = 0; u < GP; u++) {
+                const float2 o = xch_peer[(grp * GP + u) * 256];
+                v[u][0] = xn[u][0] + (kh == 0 ? c[u][0] + o.x : o.x + c[u][2]);
+                v[u][1] = xn[u][1] + (kh == 0 ? c[u][1] + o.y : o.y + c[u][3]);
+            }
+#pragma unroll
+            for (int u = 0; u < GP; u++) { v[u][0] = rs_tanh(v[u][0]); v[u][1] = rs_tanh(v[u][1]); }
+            if (grp == 0 && pend_hi >= 0) {               // deferred progress fence (lane 0 of one warp, once per RS_SIGNAL_BLOCKS)
+                __threadfence();
+                for (int b2 = pend_hi - (RS_SIGNAL_BLOCKS - 1); b2 <= pend_hi; b2++) atomicAdd(hdone + b2, 1u);
+                pend_hi = -1;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < GP; u++) {
+                const int sub = grp * GP + u;
+                const int n = nA + RS_SUB * sub;
+                if (out_base != nullptr) {
+                    if (n < N) out_base[ooff + sub * ldo8] = v[u][0];
+                    if (n + 1 < N) out_base[ooff + sub * ldo8 + ldo1] = v[u][1];
+                }
+                __nv_bfloat16 h0, l0, h1, l1;
+                rs_split(v[u][0], h0, l0);
+                rs_split(v[u][1], h1, l1);
+                __nv_bfloat16 *sgu = reinterpret_cast<__nv_bfloat16 *>(stg2[u]) + (2 * tg) * 8 + g;
+                sgu[0] = h0; sgu[8] = h1; sgu[64] = l0; sgu[72] = l1;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < GP; u++) {
+                const int sub = grp * GP + u;
+                const uint4 chunk = *reinterpret_cast<const uint4 *>(stg2[u] + (lane & 15) * 16);
+                if (plane_lane && n0 + RS_SUB * sub + cu < N) *reinterpret_cast<uint4 *>(plane_base + poff + sub * ldp8) = chunk;
+                if (more) {
+                    const uint32_t nb_off = (uint32_t)(sub * 2 + (par ^ 1));
+                    const uint32_t dst_local = dst_local0 + nb_off * LT::HBUF, bar_local = bar0 + 8 * nb_off;
+#pragma unroll
+                    for (int r = 0; r < CS / 2; r++)
+                        rs_st_async_v4(rs_mapa(dst_local, r0 + r), chunk, rs_mapa(bar_local, r0 + r));
+                }
+            }
+        }
+        // ---- frame s is finished ----
+        xoff += xstep;
+        ooff += ostep;
+        poff += pstep;
+        if (++fcnt == fpb || !more) {
+            if (hdone != nullptr && ((blk + 1) % RS_SIGNAL_BLOCKS == 0 || !more)) {
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();
+                    const int grp_par = (blk / RS_SIGNAL_BLOCKS) & 1;
+                    const int last = (atomicAdd(const_cast<int *>(ctl + grp_par), 1) & (RS_MATH_WARPS - 1)) == RS_MATH_WARPS - 1;
+                    if (last) {
+                        if (more) pend_hi = blk;
+                        else {
+                            __threadfence();
+                            for (int b2 = blk - blk % RS_SIGNAL_BLOCKS; b2 <= blk; b2++) atomicAdd(hdone + b2, 1u);
                         }
                     }
                 }
-                fcnt = 0;
-                blk++;
             }
+            fcnt = 0;
+            blk++;
         }
-    };
-    for (int q = 0; q < Q; q++) {
-        float c0, c1, c2, c3, xn0, xn1;
-        burst(c0, c1, c2, c3, xn0, xn1);
-        if (kh) {
-            epilogue(s, sub, c0, c1, c2, c3, xn0, xn1);                      // follower: its own sub-step
-        } else {
-            if (q > 0) epilogue(ps, psub, pc0, pc1, pc2, pc3, px0, px1);     // leader: the previous sub-step
-            pc0 = c0; pc1 = c1; pc2 = c2; pc3 = c3; px0 = xn0; px1 = xn1; psub = sub; ps = s;
-        }
-        if (++sub == NSUB) { sub = 0; s++; xoff += xstep; }
     }
-    if (kh == 0) epilogue(ps, psub, pc0, pc1, pc2, pc3, px0, px1);
     cluster.sync();
 }
 
