@@ -265,7 +265,9 @@ __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
         v.eb = eb2 + w * B;
         return v;
     };
-    __shared__ int s_kept, s_nodes, s_tie;
+    __shared__ int s_kept, s_nodes, s_m;
+    __shared__ unsigned s_hist[256], s_prefix, s_need, s_lo, s_hi, s_nv;
+    const int lane = tid & 31, warp = tid >> 5;
 
     int *parent = p.parent + (size_t)utt * p.cap;
     int *meta = p.meta + (size_t)utt * p.cap;
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
             if (t + 1 < p.T) next_lp = S[(size_t)(t + 1) * frame_stride + tid];
         }
         for (int c = tid; c < ncand; c += NT) { redir0[c] = kNoRedir; redir1[c] = kNoRedir; }
-        if (tid == 0) s_tie = 0;
+        if (tid == 0) { s_m = 0; s_lo = 0xffffffffu; s_hi = 0u; s_nv = 0u; }
         if (tid < k) {
             const int nd = st.node[tid], pn = st.pnode[tid];
             int tw = kNone, p0 = kNone, p1 = kNone;
@@ -393,57 +395,177 @@ __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
             keys[c] = key;
         }
         __syncthreads();
-        // ---- D: bitonic sort, descending ------------------------------------------------------------------
-        for (int size = 2; size <= n_pad; size <<= 1) {
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                for (int idx = tid; idx < (n_pad >> 1); idx += NT) {
-                    const int pos = 2 * idx - (idx & (stride - 1));
-                    const unsigned long long a = keys[pos], b = keys[pos + stride];
-                    const bool desc = (pos & size) == 0;
-                    if ((a < b) == desc) { keys[pos] = b; keys[pos + stride] = a; }
+        // ---- D: prune.  Only the kept window matters, so instead of sorting all n_pad keys: radix-select the beam-th
+        //      largest score (four 8-bit passes over the order-preserving score bits, warp-aggregated shared-memory
+        //      histogram), move every candidate not below it to the front of keys[], and order that short list.
+        uint32_t thr = 0;
+        {
+            // the candidates' scores span a narrow band (a few thousand fp32 steps): select on (score - minimum), whose
+            // leading zero bytes need no pass -- usually 2 passes instead of 4, and the digits are spread over the bins
+            uint32_t lo = 0xffffffffu, hi = 0u;
+            unsigned nv = 0u;
+            for (int c = tid; c < ncand; c += NT) {
+                const unsigned long long key = keys[c];
+                if (key != 0ull) { const uint32_t o = (uint32_t)(key >> 32); lo = o < lo ? o : lo; hi = o > hi ? o : hi; nv++; }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const uint32_t l2 = __shfl_xor_sync(0xffffffffu, lo, off), h2 = __shfl_xor_sync(0xffffffffu, hi, off);
+                lo = l2 < lo ? l2 : lo; hi = h2 > hi ? h2 : hi;
+                nv += __shfl_xor_sync(0xffffffffu, nv, off);
+            }
+            if (lane == 0 && nv) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); atomicAdd(&s_nv, nv); }
+            __syncthreads();
+            lo = s_lo; hi = s_hi;
+            const uint32_t span = hi - lo;
+            const int passes = ((int)s_nv <= B) ? 0 : (39 - __clz(span | 1u)) >> 3;      // ceil(bits(span) / 8); span 0 -> 1
+            uint32_t prefix = 0;
+            unsigned need = (unsigned)B;
+            for (int shift = 8 * (passes - 1); shift >= 0; shift -= 8) {
+                for (int i = tid; i < 256; i += NT) s_hist[i] = 0u;
+                __syncthreads();
+                const bool top = shift == 8 * (passes - 1);
+                for (int base = 0; base < ncand; base += NT) {           // uniform trip count (warp votes below)
+                    const int c = base + tid;
+                    unsigned digit = 256u;
+                    if (c < ncand) {
+                        const unsigned long long key = keys[c];
+                        const uint32_t o = (uint32_t)(key >> 32) - lo;
+                        if (key != 0ull && (top || (o >> (shift + 8)) == (prefix >> (shift + 8)))) digit = (o >> shift) & 255u;
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, digit < 256u);
+                    if (bal == 0u) continue;
+                    const int first = __ffs(bal) - 1;
+                    const unsigned d0 = __shfl_sync(0xffffffffu, digit, first);
+                    if (__all_sync(0xffffffffu, digit >= 256u || digit == d0)) {       // one bin for the whole warp
+                        if (lane == first) atomicAdd(&s_hist[d0], (unsigned)__popc(bal));
+                    } else if (digit < 256u) atomicAdd(&s_hist[digit], 1u);
                 }
                 __syncthreads();
+                if (warp == 0) {
+                    unsigned cnt[8], sum = 0u;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) { cnt[j] = s_hist[lane * 8 + j]; sum += cnt[j]; }
+                    unsigned suf = sum;                                   // inclusive suffix sum over lanes (lane .. 31)
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const unsigned o = __shfl_down_sync(0xffffffffu, suf, off);
+                        if (lane + off < 32) suf += o;
+                    }
+                    const unsigned above = suf - sum;
+                    if (above < need && suf >= need) {                    // the beam-th largest has its digit in my 8 bins
+                        unsigned acc = above;
+#pragma unroll
+                        for (int j = 7; j >= 0; j--) {
+                            if (acc < need && acc + cnt[j] >= need) { s_prefix = prefix | ((uint32_t)(lane * 8 + j) << shift); s_need = need - acc; }
+                            acc += cnt[j];
+                        }
+                    }
+                }
+                __syncthreads();
+                prefix = s_prefix; need = s_need;
             }
+            thr = passes == 0 ? 0u : lo + prefix;                        // no more candidates than the beam: keep all
         }
-        // ---- E: exact score ties inside the kept window -> raw-string order (rare slow path) ---------------
-        if (t > 0) {
-            for (int r = tid; r < B && r + 1 < n_pad; r += NT) {
-                const unsigned long long a = keys[r], b = keys[r + 1];
-                if (a != 0ull && b != 0ull && (uint32_t)(a >> 32) == (uint32_t)(b >> 32)) s_tie = 1;
+        // compaction in place, NT keys per round: a round's keys are all read before its survivors are written, and
+        // the survivors land below the end of that round's range
+        for (int base = 0; base < ncand; base += NT) {
+            const int c = base + tid;
+            unsigned long long key = 0ull;
+            if (c < ncand) key = keys[c];
+            const bool keep = key != 0ull && (uint32_t)(key >> 32) >= thr;
+            __syncthreads();
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            int wbase = 0;
+            if (lane == 0 && bal) wbase = atomicAdd(&s_m, __popc(bal));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (keep) keys[wbase + __popc(bal & ((1u << lane) - 1u))] = key;
+        }
+        __syncthreads();
+        const int M = s_m;                       // >= min(beam, #candidates); larger only by ties at the threshold
+        // raw-string order of two merged candidates (exact score ties, t > 0): O(1) through the relation matrix
+        auto cand_before = [&](unsigned long long ka, unsigned long long kb) -> bool {
+            const int ca = (int)(0xffffffffu - (uint32_t)ka), cb = (int)(0xffffffffu - (uint32_t)kb);
+            if (t == 0) return ca < cb;
+            const int ia = ca / V, va = ca - ia * V, ib = cb / V, vb = cb - ib * V;
+            const bool staya = (va != blank) && (st.eb[ia] == 0 && va == st.last[ia]);
+            const bool stayb = (vb != blank) && (st.eb[ib] == 0 && vb == st.last[ib]);
+            if (use_rel)
+                return candw_less(relw[((size_t)cur * B + ia) * B + ib], staya ? -1 : va, stayb ? -1 : vb, vch);
+            return raw_less(parent, meta, vch, st.node[ia], staya ? 0 : vch[va], st.node[ib], stayb ? 0 : vch[vb]);
+        };
+        if (M <= NT) {
+            // rank sort of the survivors, TPE threads per survivor (each scans a slice of the list, shuffle-reduced);
+            // equal scores rank by raw string (CTC-REF step 4: ties keep the ascending string order of step 3; t = 0:
+            // label order).  The survivors' (parent state, suffix label) are decoded once into the redirect tables,
+            // which are dead after phase C.
+            int tpe = 1;
+            while (tpe < 32 && 2 * tpe * M <= NT) tpe <<= 1;
+            if (tid < M) {
+                const int c = (int)(0xffffffffu - (uint32_t)keys[tid]);
+                const int i = c / V, v = c - i * V;
+                const bool stay = (v != blank) && (st.eb[i] == 0 && v == st.last[i]);
+                redir0[tid] = (uint16_t)i;
+                redir1[tid] = (uint16_t)(stay ? 0 : v + 1);               // suffix label + 1, 0 = none
             }
             __syncthreads();
-            if (s_tie && tid == 0) {
+            const int x = tid / tpe, sub = tid & (tpe - 1);
+            unsigned long long mykey = 0ull;
+            int rank = 0;
+            if (x < M) {
+                mykey = keys[x];
+                const uint32_t ms = (uint32_t)(mykey >> 32);
+                const int ix = redir0[x], sx = (int)redir1[x] - 1;
+                for (int y = sub; y < M; y += tpe) {
+                    const unsigned long long ky = keys[y];
+                    const uint32_t ys = (uint32_t)(ky >> 32);
+                    if (ys > ms) rank++;
+                    else if (ys == ms && y != x) {
+                        bool before;
+                        if (t == 0) before = ky > mykey;                 // smaller candidate index first
+                        else {
+                            const int iy = redir0[y], sy = (int)redir1[y] - 1;
+                            if (use_rel) before = candw_less(relw[((size_t)cur * B + iy) * B + ix], sy, sx, vch);
+                            else before = raw_less(parent, meta, vch, st.node[iy], sy < 0 ? 0 : vch[sy], st.node[ix], sx < 0 ? 0 : vch[sx]);
+                        }
+                        rank += before ? 1 : 0;
+                    }
+                }
+            }
+            for (int off = 1; off < tpe; off <<= 1) rank += __shfl_xor_sync(0xffffffffu, rank, off);
+            __syncthreads();
+            if (x < M && sub == 0) keys[rank] = mykey;
+            for (int c = M + tid; c < B; c += NT) keys[c] = 0ull;
+            __syncthreads();
+        } else {
+            // (more survivors than threads: massive ties) bitonic sort of the survivors, descending, then the tied runs
+            // that reach into the kept window are put into raw-string order by one thread
+            int n_sort = 32;
+            while (n_sort < M) n_sort <<= 1;
+            for (int c = M + tid; c < n_sort || c < B; c += NT) keys[c] = 0ull;
+            __syncthreads();
+            for (int size = 2; size <= n_sort; size <<= 1) {
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (int idx = tid; idx < (n_sort >> 1); idx += NT) {
+                        const int pos = 2 * idx - (idx & (stride - 1));
+                        const unsigned long long a = keys[pos], b = keys[pos + stride];
+                        const bool desc = (pos & size) == 0;
+                        if ((a < b) == desc) { keys[pos] = b; keys[pos + stride] = a; }
+                    }
+                    __syncthreads();
+                }
+            }
+            if (t > 0 && tid == 0) {
                 int r = 0;
-                while (r < B && keys[r] != 0ull) {
+                while (r < B && r < M) {
                     const uint32_t sc = (uint32_t)(keys[r] >> 32);
                     int e = r + 1;
-                    while (e < n_pad && keys[e] != 0ull && (uint32_t)(keys[e] >> 32) == sc) e++;
-                    if (e - r > 1) {
-                        // insertion sort of keys[r:e) by raw string, ascending
-                        for (int x = r + 1; x < e; x++) {
-                            const unsigned long long kx = keys[x];
-                            const int cx = (int)(0xffffffffu - (uint32_t)kx);
-                            const int ix = cx / V, vx = cx - ix * V;
-                            const int sufx = (vx == blank) ? vch[blank]
-                                             : ((st.eb[ix] == 0 && vx == st.last[ix]) ? 0 : vch[vx]);
-                            int y = x - 1;
-                            while (y >= r) {
-                                const int cy = (int)(0xffffffffu - (uint32_t)keys[y]);
-                                const int iy = cy / V, vy = cy - iy * V;
-                                const int sufy = (vy == blank) ? vch[blank]
-                                                 : ((st.eb[iy] == 0 && vy == st.last[iy]) ? 0 : vch[vy]);
-                                bool less;
-                                if (use_rel) {
-                                    const int sx = (vx == blank) ? blank : ((st.eb[ix] == 0 && vx == st.last[ix]) ? -1 : vx);
-                                    const int sy = (vy == blank) ? blank : ((st.eb[iy] == 0 && vy == st.last[iy]) ? -1 : vy);
-                                    less = candw_less(relw[((size_t)cur * B + ix) * B + iy], sx, sy, vch);
-                                } else less = raw_less(parent, meta, vch, st.node[ix], sufx, st.node[iy], sufy);
-                                if (!less) break;
-                                keys[y + 1] = keys[y];
-                                y--;
-                            }
-                            keys[y + 1] = kx;
-                        }
+                    while (e < M && (uint32_t)(keys[e] >> 32) == sc) e++;
+                    for (int x = r + 1; x < e; x++) {                    // insertion sort of keys[r:e), ascending raw string
+                        const unsigned long long kx = keys[x];
+                        int y = x - 1;
+                        while (y >= r && cand_before(kx, keys[y])) { keys[y + 1] = keys[y]; y--; }
+                        keys[y + 1] = kx;
                     }
                     r = e;
                 }
@@ -474,7 +596,7 @@ __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
             }
             newflag[tid] = my_new;
             sel_i[tid] = valid ? my_i : -1;
-            sel_v[tid] = my_v;
+            sel_v[tid] = (valid && !((my_v == blank) || (st.eb[my_i] == 0 && my_v == st.last[my_i]))) ? my_v : -1;   // appended label
             if (valid) {
                 const bool stay2 = (my_v == blank) || (st.eb[my_i] == 0 && my_v == st.last[my_i]);
                 depth2[(cur ^ 1) * B + tid] = depth2[cur * B + my_i] + (stay2 ? 0 : 1);
@@ -485,15 +607,15 @@ __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
             // prefix relations of the new beam from the current one and this frame's choices (old node ids still in st)
             const unsigned short *rc = relw + (size_t)cur * B * B;
             unsigned short *rn = relw + (size_t)(cur ^ 1) * B * B;
+            int r = tid / B, q = tid - r * B;
+            const int dr = NT / B, dq = NT - dr * B;
             for (int e = tid; e < B * B; e += NT) {
-                const int r = e / B, q = e - r * B;
                 const int ar = sel_i[r], aq = sel_i[q];
-                if (ar < 0 || aq < 0) continue;
-                const int vr = sel_v[r], vq = sel_v[q];
-                const int er = (vr == blank || (st.eb[ar] == 0 && vr == st.last[ar])) ? -1 : vr;
-                const int eq2 = (vq == blank || (st.eb[aq] == 0 && vq == st.last[aq])) ? -1 : vq;
-                rn[e] = (unsigned short)relw_child(rc[(size_t)ar * B + aq], er, eq2, depth2[cur * B + ar], depth2[cur * B + aq],
-                                                   st.node[ar], st.node[aq], vch, parent, meta);
+                if (ar >= 0 && aq >= 0)
+                    rn[e] = (unsigned short)relw_child(rc[(size_t)ar * B + aq], sel_v[r], sel_v[q], depth2[cur * B + ar],
+                                                       depth2[cur * B + aq], st.node[ar], st.node[aq], vch, parent, meta);
+                r += dr; q += dq;
+                if (q >= B) { q -= B; r++; }
             }
         }
         if (tid < B && valid) {
@@ -510,13 +632,8 @@ __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
                 nx.node[tid] = nd;
             }
         }
-        __syncthreads();
-        if (tid == 0) {
-            int cnt = 0, kept = 0;
-            for (int j = 0; j < B; j++) { cnt += newflag[j]; kept += (keys[j] != 0ull); }
-            s_nodes += cnt;
-            s_kept = kept;
-        }
+        const int created = __syncthreads_count(my_new != 0);
+        if (tid == 0) { s_nodes += created; s_kept = M < B ? M : B; }
         cur ^= 1;
         __syncthreads();
     }

@@ -37,6 +37,19 @@ __device__ __forceinline__ unsigned long long xs_now_ns() {
     return t;
 }
 // bounded mbarrier wait: returns false (and raises the abort flag) if the watchdog fires
+// 32 lanes x 32 consecutive fp32 columns of the accumulator -> 32 registers per thread (asynchronous: tcgen05.wait::ld)
+__device__ __forceinline__ void xs_tmem_ld32(uint32_t (&v)[32], uint32_t taddr) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+
 __device__ __forceinline__ bool xs_wait(uint32_t bar, uint32_t parity, volatile int *abort_flag, volatile unsigned *gabort) {
     if (xs_mbar_try(bar, parity)) return true;
     const unsigned long long t0 = xs_now_ns();
@@ -190,28 +203,36 @@ xproj_stream_kernel(const __grid_constant__ XsMaps maps, const XsParams p) {
         const int qd = warp & 3;                                         // TMEM lane quadrant this warp may access
         int q = 0;
         XsIter wi;
+        // The "rows stored" signal of a tile (fence + count) is deferred into the next tile: issued right after that
+        // tile's first TMEM load, the fence finds this warp's stores already drained instead of waiting for them
+        // (it was 16% of the epilogue's samples).  If the next accumulator is not ready yet, publish at once.
+        unsigned *pend = nullptr;
         for (bool have = xs_iter_init(p, wi); have; have = xs_iter_next(wi), q++) {
             const int blk = wi.blk, tg = wi.tg, tile = wi.tile;
             const XsTarget &t = p.target[tg];
             const int acc = q & 1;
+            if (pend && !xs_mbar_try(tfull0 + 8 * acc, (q >> 1) & 1)) {
+                if (lane == 0) { __threadfence(); atomicAdd(pend, 1u); }
+                pend = nullptr;
+            }
             if (!xs_wait(tfull0 + 8 * acc, (q >> 1) & 1, abort_flag, p.abort)) break;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int row = blk * TC_BM + qd * 32 + lane;
             const int n0 = tile * t.bn;
-            for (int c = 0; c < t.bn / 32; c++) {
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * TC_BN + c * 32);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
+            const int nchunks = t.bn / 32;
+            uint32_t v[32];
+            xs_tmem_ld32(v, tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * TC_BN));
+            if (pend) {
+                if (lane == 0) { __threadfence(); atomicAdd(pend, 1u); }
+                pend = nullptr;
+            }
+            for (int c = 0; c < nchunks; c++) {
+                // bias of this lane's store columns: requested before the TMEM load is waited for
+                const float *bsrc = t.bias ? t.bias + n0 + c * 32 : nullptr;
+                float4 badd = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((t.kind & 15) == XS_KIND_XPROJ && bsrc) badd = __ldg(reinterpret_cast<const float4 *>(bsrc + 4 * (lane & 7)));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c == t.bn / 32 - 1) {
+                if (c == nchunks - 1) {
                     // accumulator fully read: hand it back to the MMA issuer before the (slow) stores
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
@@ -220,7 +241,6 @@ xproj_stream_kernel(const __grid_constant__ XsMaps maps, const XsParams p) {
                 // registers (thread = row) -> shared staging tile [32 rows][36 floats] -> coalesced 128-byte row segments:
                 // a scattered store (every lane its own row) costs 32 L2 transactions per instruction
                 float4 *stg4 = reinterpret_cast<float4 *>(epi_stage + (warp - 2) * (32 * 36));
-                const float *bsrc = t.bias ? t.bias + n0 + c * 32 : nullptr;
                 if ((t.kind & 15) == XS_KIND_XPROJ) {
 #pragma unroll
                     for (int j = 0; j < 8; j++)
@@ -244,11 +264,12 @@ xproj_stream_kernel(const __grid_constant__ XsMaps maps, const XsParams p) {
 #pragma unroll
                     for (int j = 0; j < 8; j++) stg4[lane * 9 + j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
                 }
+                // the registers are staged: fetch the next 32 columns while this chunk is being stored
+                if (c + 1 < nchunks)
+                    xs_tmem_ld32(v, tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * TC_BN + (c + 1) * 32));
                 __syncwarp();
                 if (!(t.kind & 16)) {
                     const int c4 = lane & 7, rsub = lane >> 3;                   // this lane: columns 4*c4..+3 of rows rsub + 4i
-                    float4 badd = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if ((t.kind & 15) == XS_KIND_XPROJ && bsrc) badd = *reinterpret_cast<const float4 *>(bsrc + 4 * c4);
                     const int row0 = blk * TC_BM + qd * 32;
                     const int ncols = (t.kind & 15) == XS_KIND_XPROJ ? 32 : (t.ldc < 32 ? t.ldc : 32);
 #pragma unroll
@@ -262,10 +283,11 @@ xproj_stream_kernel(const __grid_constant__ XsMaps maps, const XsParams p) {
                 }
                 __syncwarp();
             }
-            // this warp's 32 rows are stored: fence + count (the consumer waits for XS_EPI_WARPS counts per tile)
+            // this warp's 32 rows are stored: fence + count (the consumer waits for XS_EPI_WARPS counts per tile), deferred
             __syncwarp();
-            if (lane == 0) { __threadfence(); atomicAdd(t.dst_ready + blk, 1u); }
+            pend = t.dst_ready + blk;
         }
+        if (pend && lane == 0) { __threadfence(); atomicAdd(pend, 1u); }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

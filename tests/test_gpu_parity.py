@@ -128,6 +128,36 @@ def test_ctc_exact_ties_break_by_raw_string(gasr, ctx, O):
     assert gp == op and gs == os_
 
 
+def test_ctc_general_kernel_ties_and_select(gasr, ctx, O):
+    """The general decoder (vocabulary > 32 or beam > 32) prunes with a radix select + rank sort: exact score ties at the
+    threshold and inside the kept window must still come out in raw-string order, also when (nearly) every candidate
+    ties -- more survivors than threads, the bitonic fallback."""
+    rng = np.random.default_rng(23)
+    for V, beams in ((40, (1, 3, 33, 70)), (29, (40, 128)), (47, (100,))):
+        vocab = bytes(range(1, V + 1)) if V != 29 else __import__("synth").VOCAB29
+        for trial in range(3):
+            T = int(rng.integers(2, 8))
+            q = rng.integers(1, 4, size=(T, 2, V)).astype(np.float32)
+            P = (q / 8.0).astype(np.float32)
+            for beam in beams:
+                nb = min(beam, 5)
+                gp, gs = ctx.ctc_decode_host(P, gasr.DOMAIN_PROB, beam, 0, vocab, nbest=nb)
+                op, os_ = O.ctc_decode(P, vocab, 0, beam, domain="prob", nbest=nb)
+                assert gp == op, (V, T, beam, trial)
+                assert gs == os_
+    # uniform input: every candidate ties (47 x 100 = 4700 candidates > 1024 threads)
+    for V, beam, T in ((47, 100, 5), (29, 128, 4), (40, 20, 6)):
+        vocab = bytes(range(1, V + 1)) if V != 29 else __import__("synth").VOCAB29
+        P = np.full((T, 2, V), 1.0 / 64.0, dtype=np.float32)
+        gp, gs = ctx.ctc_decode_host(P, gasr.DOMAIN_PROB, beam, 0, vocab, nbest=4)
+        op, os_ = O.ctc_decode(P, vocab, 0, beam, domain="prob", nbest=4)
+        assert gp == op and gs == os_
+        lp = np.log(P)
+        gp, gs = ctx.ctc_decode_host(lp, gasr.DOMAIN_LOG, beam, 0, vocab, nbest=4)
+        op, os_ = O.ctc_decode(lp, vocab, 0, beam, domain="log", nbest=4)
+        assert gp == op and gs == os_
+
+
 def test_ctc_zero_probabilities_and_minus_inf(gasr, ctx, O):
     rng = np.random.default_rng(2)
     P = _softmax_probs(rng, 12, 3, 5)
