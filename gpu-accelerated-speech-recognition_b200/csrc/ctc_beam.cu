@@ -267,7 +267,9 @@ __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
     };
     __shared__ int s_kept, s_nodes, s_m;
     __shared__ unsigned s_hist[256], s_prefix, s_need, s_lo, s_hi, s_nv;
+    __shared__ int s_wcnt[32];
     const int lane = tid & 31, warp = tid >> 5;
+    const unsigned vinv = 0xffffffffu / (unsigned)p.V + 1u;             // ceil(2^32 / V): exact quotients for c * V < 2^32
 
     int *parent = p.parent + (size_t)utt * p.cap;
     int *meta = p.meta + (size_t)utt * p.cap;
@@ -305,15 +307,27 @@ __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
         }
         for (int c = tid; c < ncand; c += NT) { redir0[c] = kNoRedir; redir1[c] = kNoRedir; }
         if (tid == 0) { s_m = 0; s_lo = 0xffffffffu; s_hi = 0u; s_nv = 0u; }
-        if (tid < k) {
-            const int nd = st.node[tid], pn = st.pnode[tid];
+        {
+            // twin (same prefix, other "ends in blank" flag) and parent states of every kept state: each is unique if it
+            // exists, so slices of the scan (2^tsh threads per state) combine with a max
+            int tsh = 0;
+            while (tsh < 5 && (2 << tsh) * k <= NT) tsh++;
+            const int i = tid >> tsh, sub = tid & ((1 << tsh) - 1);
             int tw = kNone, p0 = kNone, p1 = kNone;
-            for (int j = 0; j < k; j++) {
-                const int nj = st.node[j];
-                if (nj == nd && j != tid) tw = j;
-                if (nj == pn) { if (st.eb[j]) p1 = j; else p0 = j; }
+            if (i < k) {
+                const int nd = st.node[i], pn = st.pnode[i];
+                for (int j = sub; j < k; j += 1 << tsh) {
+                    const int nj = st.node[j];
+                    if (nj == nd && j != i) tw = j;
+                    if (nj == pn) { if (st.eb[j]) p1 = j; else p0 = j; }
+                }
             }
-            twin[tid] = (short)tw; P0[tid] = (short)p0; P1[tid] = (short)p1;
+            for (int off = 1; off < (1 << tsh); off <<= 1) {
+                tw = max(tw, __shfl_xor_sync(0xffffffffu, tw, off));
+                p0 = max(p0, __shfl_xor_sync(0xffffffffu, p0, off));
+                p1 = max(p1, __shfl_xor_sync(0xffffffffu, p1, off));
+            }
+            if (i < k && sub == 0) { twin[i] = (short)tw; P0[i] = (short)p0; P1[i] = (short)p1; }
         }
         __syncthreads();
         // ---- B: kept child states claim the extend candidates that land on them --------------------------
@@ -328,7 +342,7 @@ __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
         for (int c = tid; c < n_pad; c += NT) {
             unsigned long long key = 0ull;
             if (c < ncand) {
-                const int i = c / V, v = c - i * V;
+                const int i = V == 1 ? c : (int)__umulhi((unsigned)c, vinv), v = c - i * V;      // c / V (c < 2^16, V <= 255)
                 const float pv = lp[v];
                 const float s = comb<DOMAIN>(st.score[i], pv);
                 const int tw = twin[i];
@@ -602,6 +616,8 @@ __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
                 depth2[(cur ^ 1) * B + tid] = depth2[cur * B + my_i] + (stay2 ? 0 : 1);
             }
         }
+        const unsigned new_bal = __ballot_sync(0xffffffffu, my_new != 0);
+        if (lane == 0) s_wcnt[warp] = __popc(new_bal);
         __syncthreads();
         if (use_rel) {
             // prefix relations of the new beam from the current one and this frame's choices (old node ids still in st)
@@ -620,8 +636,8 @@ __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
         }
         if (tid < B && valid) {
             if (my_new) {
-                int off = 0;
-                for (int j = 0; j < tid; j++) off += newflag[j];
+                int off = __popc(new_bal & ((1u << lane) - 1u));
+                for (int w = 0; w < warp; w++) off += s_wcnt[w];
                 const int nd = s_nodes + off;
                 const int pn = st.node[my_i];
                 parent[nd] = pn;
