@@ -104,6 +104,15 @@ int xproj_tc_split_rows_range(gasr_ctx *ctx, const float *A, int lda, int M_tota
 int launch_xproj_tc(gasr_ctx *ctx, const float *A, int lda, int M, int K, int N, const void *wbuf, void *abuf,
                     const float *bias, float *C, int ldc, int precision, cudaStream_t st);
 
+// fused GRU timestep (gru_tc.cu): permuted W_hh^T planes + ping-pong bf16 planes of h, TMA descriptors built once
+struct GruTcPlan { CUtensorMap maps[2][2]; CUtensorMap wmaps[2]; void *plane[2][2]; int N, H, Kp; };
+bool gru_tc_supported(int N, int H, int ldxp, int ldo, int col0);
+size_t gru_tc_w_bytes(int H);
+size_t gru_tc_plane_bytes(int N, int H);
+int gru_tc_prepare(gasr_ctx *ctx, GruTcPlan &pl, const float *w_hh, int N, int H, void *wbuf, void *planes, cudaStream_t st);
+int gru_tc_step(gasr_ctx *ctx, const GruTcPlan &pl, int src, const float *xp, int ldxp, const float *b_hh, const float *hprev,
+                int ldh, float *out, int ldo, bool overlap, cudaStream_t st);
+
 struct RnnLayerArgs {
     int cell, T, N, H, reverse;
     const float *xproj;   // [T*N, ldxp]: x*W_ih + (b_ih [+ b_hh for tanh]) for this direction

@@ -469,21 +469,36 @@ int launch_rnn_recurrence(gasr_ctx *ctx, const RnnLayerArgs &a, cudaStream_t st)
     }
     GASR_CHECK(a.N <= 65535, "rnn_recurrence: batch too large for the per-step path");
     const char *force_g = getenv("GASR_GRU");
-    if (a.cell == GASR_CELL_GRU && !(force_g && force_g[0] == 's') && a.N >= 32 && xproj_tc_supported(a.N, a.H, 3 * a.H) &&
-        a.s0 == 0 && (a.s1 == 0 || a.s1 == a.T)) {
-        // GRU with a real batch: per timestep ONE tcgen05 GEMM hh = h_{t-1} * W_hh + b_hh (fp32-grade 3 x bf16 split,
-        // W_hh^T prepared once, TMA descriptors reused) + one gate kernel, instead of a kernel that streams W_hh from L2
-        // for every (utterance, column) thread
+    const bool gru_batched = a.cell == GASR_CELL_GRU && !(force_g && force_g[0] == 's') && a.N >= 32 && a.s0 == 0 &&
+                             (a.s1 == 0 || a.s1 == a.T);
+    const bool gru_fused = gru_batched && !(force_g && force_g[0] == 'g') && gru_tc_supported(a.N, a.H, a.ldxp, a.ldo, a.col0) &&
+                           ((reinterpret_cast<uintptr_t>(a.xproj) | reinterpret_cast<uintptr_t>(a.out) |
+                             reinterpret_cast<uintptr_t>(a.b_hh)) & 15) == 0;
+    if (gru_fused || (gru_batched && xproj_tc_supported(a.N, a.H, 3 * a.H))) {
+        // GRU with a real batch, one launch per timestep (gru_tc.cu): tcgen05 GEMM h_{t-1} * W_hh (fp32-grade 3 x bf16
+        // split, permuted W_hh^T prepared once, TMA descriptors reused) with the gate math in its epilogue, which also
+        // writes the bf16 planes the next step reads.  (GASR_GRU=g: the earlier three-launch form -- split, GEMM
+        // hh = h W_hh + b_hh, gate kernel; GASR_GRU=s: one SIMT kernel per step.)
         const int H = a.H, G3 = 3 * a.H;
-        const size_t wb = align_up(xproj_tc_w_bytes(H, G3), 1024), ab = align_up(xproj_tc_a_bytes(a.N, H), 1024);
-        const size_t hb = align_up(sizeof(float) * (size_t)a.N * G3, 1024);
         Workspace &wsg = ctx->ws_sel ? ctx->ws_gru_b : ctx->ws_gru;
-        GASR_TRY(ws_reserve(ctx, wsg, wb + ab + hb + 1024));
-        unsigned char *base = static_cast<unsigned char *>(wsg.ptr);
-        float *hh = reinterpret_cast<float *>(base + wb + ab);
-        GASR_TRY(xproj_tc_prepare_weights(ctx, a.w_hh, H, G3, base, st));
         XprojTcPlan pl;
-        GASR_TRY(xproj_tc_plan(pl, a.N, H, G3, base, base + wb));
+        GruTcPlan gp;
+        float *hh = nullptr;
+        unsigned char *base = nullptr;
+        if (gru_fused) {
+            const size_t wb = align_up(gru_tc_w_bytes(H), 1024);
+            GASR_TRY(ws_reserve(ctx, wsg, wb + 2 * gru_tc_plane_bytes(a.N, H) + 1024));
+            base = static_cast<unsigned char *>(wsg.ptr);
+            GASR_TRY(gru_tc_prepare(ctx, gp, a.w_hh, a.N, H, base, base + wb, st));
+        } else {
+            const size_t wb = align_up(xproj_tc_w_bytes(H, G3), 1024), ab = align_up(xproj_tc_a_bytes(a.N, H), 1024);
+            const size_t hb = align_up(sizeof(float) * (size_t)a.N * G3, 1024);
+            GASR_TRY(ws_reserve(ctx, wsg, wb + ab + hb + 1024));
+            base = static_cast<unsigned char *>(wsg.ptr);
+            hh = reinterpret_cast<float *>(base + wb + ab);
+            GASR_TRY(xproj_tc_prepare_weights(ctx, a.w_hh, H, G3, base, st));
+            GASR_TRY(xproj_tc_plan(pl, a.N, H, G3, base, base + wb));
+        }
         dim3 ggrid(ceil_div(H, 128), a.N);
         auto issue_steps = [&]() -> int {
             for (int s = 0; s < a.T; s++) {
@@ -492,26 +507,31 @@ int launch_rnn_recurrence(gasr_ctx *ctx, const RnnLayerArgs &a, cudaStream_t st)
                 const float *xp = a.xproj + (size_t)t * a.N * a.ldxp;
                 float *o = a.out + (size_t)t * a.N * a.ldo + a.col0;
                 const float *hp = s == 0 ? nullptr : a.out + (size_t)tp * a.N * a.ldo + a.col0;
+                if (gru_fused) {
+                    GASR_TRY(gru_tc_step(ctx, gp, s & 1, xp, a.ldxp, a.b_hh, hp, a.ldo, o, a.ldo, s > 0 && !getenv("GASR_GRU_NO_PDL"), st));
+                    continue;
+                }
                 if (s > 0) GASR_TRY(xproj_tc_run(ctx, pl, hp, a.ldo, a.b_hh, hh, G3, GASR_PREC_FP32, st));
                 gru_gate_kernel<<<ggrid, 128, 0, st>>>(xp, a.ldxp, s > 0 ? hh : nullptr, a.b_hh, hp, a.ldo, o, a.ldo, a.N, H);
                 ctx->launches += 1;
             }
             return GASR_OK;
         };
-        // 3 launches per timestep: the loop is launch-bound from the host.  The whole T-step sequence is captured once
-        // into a CUDA graph (operands are stable across calls: workspaces, weights, layer buffers) and replayed.
+        // The step loop is launch-bound from the host.  The whole T-step sequence is captured once into a CUDA graph
+        // (operands are stable across calls: workspaces, weights, layer buffers) and replayed; the weight preparation
+        // and the zeroing of the h planes above stay outside the graph (they run on every call).
         if (a.T >= 64 && !getenv("GASR_NO_GRAPH")) {
             gasr_ctx::StepGraph key = {};
             key.k[0] = a.xproj; key.k[1] = a.out; key.k[2] = a.w_hh; key.k[3] = base; key.k[4] = a.b_hh;
-            const int dims[8] = {a.T, a.N, H, a.reverse, a.col0, a.ldo, a.ldxp, 0};
+            const int dims[8] = {a.T, a.N, H, a.reverse, a.col0, a.ldo, a.ldxp, gru_fused ? 1 : 0};
             memcpy(key.dims, dims, sizeof(dims));
             for (auto &g : ctx->step_graphs)
                 if (memcmp(g.k, key.k, sizeof(key.k)) == 0 && memcmp(g.dims, key.dims, sizeof(key.dims)) == 0) {
                     GASR_CUDA(cudaGraphLaunch(g.exec, st));
-                    ctx->launches += 3LL * a.T - 2;
+                    ctx->launches += gru_fused ? (long long)a.T : 3LL * a.T - 2;
                     return GASR_OK;
                 }
-            if (!(ctx->attr_mask & 1024u)) {          // function attributes cannot be set while capturing: warm the GEMM up
+            if (!gru_fused && !(ctx->attr_mask & 1024u)) {   // function attributes cannot be set while capturing: warm the GEMM up
                 GASR_TRY(xproj_tc_run(ctx, pl, a.out + a.col0, a.ldo, a.b_hh, hh, G3, GASR_PREC_FP32, st));
             }
             cudaGraph_t graph = nullptr;

@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--L", type=int, default=1)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--kind", default="random", choices=["random", "peaky", "flat"])
+    ap.add_argument("--cell", default="tanh", choices=["tanh", "gru"])
+    ap.add_argument("--bidir", action="store_true")
     a = ap.parse_args()
     ctx = gasr.Context(0)
     V = 29
@@ -41,15 +43,16 @@ def main():
                   f"fallback_frames={fb} mean_survivors={sv / (a.T * a.N):.1f}")
     elif a.stage == "rnn":
         x = synth.spectrogram_batch(1, a.T, a.N, a.D)
-        w = synth.rnn_weights(2, a.D, a.H, a.L)
+        gru = a.cell == "gru"
+        w = synth.rnn_weights(2, a.D, a.H, a.L, cell_gates=3 if gru else 1, bidir=a.bidir)
         dx = ctx.to_device(x)
         dw = [[ctx.to_device(m) for m in lst] for lst in w]
-        hid = [ctx.malloc(a.T * a.N * a.H * 4) for _ in range(a.L)]
+        hid = [ctx.malloc(a.T * a.N * a.H * (2 if a.bidir else 1) * 4) for _ in range(a.L)]
         for it in range(a.iters):
             ctx.sync(); ctx.timer_start()
-            ctx.rnn_forward(gasr.CELL_TANH, False, a.T, a.N, a.D, a.H, a.L, dw[0], dw[1], dw[2], dw[3], dx, hid)
+            ctx.rnn_forward(gasr.CELL_GRU if gru else gasr.CELL_TANH, a.bidir, a.T, a.N, a.D, a.H, a.L, dw[0], dw[1], dw[2], dw[3], dx, hid)
             ms = ctx.timer_stop()
-            print(f"rnn T={a.T} N={a.N} H={a.H} L={a.L}: {ms:.3f} ms ({1e3 * ms / a.T / a.L:.2f} us/step/layer)")
+            print(f"rnn {a.cell}{' bidir' if a.bidir else ''} T={a.T} N={a.N} H={a.H} L={a.L}: {ms:.3f} ms ({1e3 * ms / a.T / a.L:.2f} us/step/layer)")
     elif a.stage == "linear":
         rows = a.T * a.N
         x = np.random.default_rng(0).normal(size=(rows, a.H)).astype(np.float32)
