@@ -12,7 +12,8 @@
 //   * the epilogue thread of accumulator row n (utterance n) therefore has everything it needs for 32 units of h_t: it
 //     adds the input projections and biases, applies the gates, writes h_t (fp32, the layer's output) AND the bf16
 //     hi/lo planes of h_t that the next step's TMA loads read (ping-pong plane buffers) -- no split kernel, no hh;
-//   * xp / h_{t-1} lines are prefetched into L2 while the MMAs run.
+//   * the epilogue threads request their xp / h_{t-1} values before they wait for the accumulator, so the scattered
+//     thread-per-row loads complete while the MMAs run.
 // Grid = ceil(H / 32) x ceil(N / 128) CTAs (25 x 2 at cfg3; both directions of a layer run concurrently on two streams).
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -38,7 +39,20 @@ struct GruTcParams {
     __nv_bfloat16 *nhi, *nlo;                // bf16 planes of h_t for the next step, [N, Kp]
 };
 
-__device__ __forceinline__ float gt_sigmoid(float v) { return 1.0f / (1.0f + expf(-v)); }
+// Gate non-linearities on the SFU (ex2.approx, rcp.approx; absolute error ~1e-7, the parity bar is 1e-4): with libm's
+// expf / division / tanhf the epilogue's 48 transcendental values per thread took 4.9 us of a 17 us step.
+__device__ __forceinline__ float gt_sigmoid(float v) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return r;
+}
+__device__ __forceinline__ float gt_tanh(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
+}
 
 __device__ __forceinline__ void gt_tmem_ld16(uint32_t (&v)[16], uint32_t taddr) {
     asm volatile(
@@ -144,11 +158,19 @@ gru_tc_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         const bool live = row < p.N;
         const float *xr = p.xp + (size_t)(live ? row : 0) * p.ldxp;
         const float *hp = p.hprev ? p.hprev + (size_t)(live ? row : 0) * p.ldh : nullptr;
-        if (live) {
-            // this thread's input lines: pull them into L2 while the MMAs run
+        // this thread's inputs (16 units x {xp_r, xp_z, xp_n, h_{t-1}}) do not depend on the MMAs: request them now, they
+        // arrive while the main loop runs (thread-per-row accesses are scattered, their latency must not be exposed)
+        const int jb = j0 + half * 16;
+        float4 xr4[4], xz4[4], xn4[4], h4[4];
 #pragma unroll
-            for (int g = 0; g < 3; g++) asm volatile("prefetch.global.L2 [%0];" ::"l"(xr + g * p.H + j0));
-            if (hp) asm volatile("prefetch.global.L2 [%0];" ::"l"(hp + j0));
+        for (int g4 = 0; g4 < 4; g4++) {
+            const int j = jb + 4 * g4;
+            const bool in = live && j < p.H;                             // H % 4 == 0: a group of four is all in or all out
+            const int jc = in ? j : 0;
+            xr4[g4] = *reinterpret_cast<const float4 *>(xr + jc);
+            xz4[g4] = *reinterpret_cast<const float4 *>(xr + p.H + jc);
+            xn4[g4] = *reinterpret_cast<const float4 *>(xr + 2 * p.H + jc);
+            h4[g4] = hp ? *reinterpret_cast<const float4 *>(hp + jc) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         mbar_wait(tfull, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -159,22 +181,16 @@ gru_tc_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             gt_tmem_ld16(az, taddr + GT_UNITS);
             gt_tmem_ld16(an, taddr + 2 * GT_UNITS);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int jb = j0 + half * 16;
             if (live) {
 #pragma unroll
                 for (int g4 = 0; g4 < 4; g4++) {
                     const int j = jb + 4 * g4;
-                    if (j >= p.H) break;                                 // H % 4 == 0: a group of four is all in or all out
-                    const float4 xr4 = *reinterpret_cast<const float4 *>(xr + j);
-                    const float4 xz4 = *reinterpret_cast<const float4 *>(xr + p.H + j);
-                    const float4 xn4 = *reinterpret_cast<const float4 *>(xr + 2 * p.H + j);
+                    if (j >= p.H) break;
                     const float4 br4 = __ldg(reinterpret_cast<const float4 *>(p.b_hh + j));
                     const float4 bz4 = __ldg(reinterpret_cast<const float4 *>(p.b_hh + p.H + j));
                     const float4 bn4 = __ldg(reinterpret_cast<const float4 *>(p.b_hh + 2 * p.H + j));
-                    float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (hp) h4 = *reinterpret_cast<const float4 *>(hp + j);
-                    const float xrv[4] = {xr4.x, xr4.y, xr4.z, xr4.w}, xzv[4] = {xz4.x, xz4.y, xz4.z, xz4.w};
-                    const float xnv[4] = {xn4.x, xn4.y, xn4.z, xn4.w}, hv[4] = {h4.x, h4.y, h4.z, h4.w};
+                    const float xrv[4] = {xr4[g4].x, xr4[g4].y, xr4[g4].z, xr4[g4].w}, xzv[4] = {xz4[g4].x, xz4[g4].y, xz4[g4].z, xz4[g4].w};
+                    const float xnv[4] = {xn4[g4].x, xn4[g4].y, xn4[g4].z, xn4[g4].w}, hv[4] = {h4[g4].x, h4[g4].y, h4[g4].z, h4[g4].w};
                     const float brv[4] = {br4.x, br4.y, br4.z, br4.w}, bzv[4] = {bz4.x, bz4.y, bz4.z, bz4.w};
                     const float bnv[4] = {bn4.x, bn4.y, bn4.z, bn4.w};
                     float o[4];
@@ -186,7 +202,7 @@ gru_tc_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                         const float gn = hp ? __uint_as_float(an[4 * g4 + e]) + bnv[e] : bnv[e];
                         const float r = gt_sigmoid(xrv[e] + gr);
                         const float z = gt_sigmoid(xzv[e] + gz);
-                        const float nn = tanhf(xnv[e] + r * gn);
+                        const float nn = gt_tanh(xnv[e] + r * gn);
                         o[e] = (1.0f - z) * nn + z * hv[e];
                     }
                     *reinterpret_cast<float4 *>(p.out + (size_t)row * p.ldo + j) = make_float4(o[0], o[1], o[2], o[3]);
