@@ -130,7 +130,7 @@ int gasr_ctx_destroy(gasr_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->dev_blocks) cudaFree(kv.first);
     for (auto &kv : ctx->host_blocks) cudaFreeHost(kv.first);
-    Workspace *wss[] = {&ctx->ws_ctc, &ctx->ws_rnn, &ctx->ws_misc, &ctx->ws_out, &ctx->ws_gru, &ctx->ws_rnn_b, &ctx->ws_misc_b, &ctx->ws_gru_b};
+    Workspace *wss[] = {&ctx->ws_ctc, &ctx->ws_rnn, &ctx->ws_misc, &ctx->ws_out, &ctx->ws_gru, &ctx->ws_lin, &ctx->ws_rnn_b, &ctx->ws_misc_b, &ctx->ws_gru_b};
     for (cudaEvent_t e : ctx->ev_bi) if (e) cudaEventDestroy(e);
     for (auto &g : ctx->step_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (Workspace *w : wss) if (w->ptr) cudaFree(w->ptr);

@@ -57,7 +57,7 @@ struct gasr_ctx {
     long long launches = 0;
     size_t device_bytes = 0, host_bytes = 0;
     std::map<void *, size_t> dev_blocks, host_blocks;
-    gasr::Workspace ws_ctc, ws_rnn, ws_misc, ws_out, ws_gru;
+    gasr::Workspace ws_ctc, ws_rnn, ws_misc, ws_out, ws_gru, ws_lin;
     gasr::Workspace ws_rnn_b, ws_misc_b, ws_gru_b;   // second set: the backward direction of a bidirectional layer runs concurrently
     int ws_sel = 0;                      // which set the recurrent-layer helpers use (0 / 1)
     // instantiated CUDA graphs of launch-bound per-timestep loops (GRU recurrence), keyed by their operands
@@ -112,6 +112,12 @@ size_t gru_tc_plane_bytes(int N, int H);
 int gru_tc_prepare(gasr_ctx *ctx, GruTcPlan &pl, const float *w_hh, int N, int H, void *wbuf, void *planes, cudaStream_t st);
 int gru_tc_step(gasr_ctx *ctx, const GruTcPlan &pl, int src, const float *xp, int ldxp, const float *b_hh, const float *hprev,
                 int ldh, float *out, int ldo, bool overlap, cudaStream_t st);
+
+// Linear (<= 32 outputs) + log-softmax over many rows on the tensor cores: operand split + one launch of the streaming
+// tile engine with a single output-layer target (xproj_stream.cu); y must have ldy >= 32, ldy % 4 == 0
+bool linear_tc_supported(int rows, int in, int out, int ldy, const float *y, int act);
+int launch_linear_logsoftmax_tc(gasr_ctx *ctx, const float *x, int ldx, const float *W, const float *b, float *y, int ldy,
+                                int rows, int in, int out, cudaStream_t st);
 
 struct RnnLayerArgs {
     int cell, T, N, H, reverse;

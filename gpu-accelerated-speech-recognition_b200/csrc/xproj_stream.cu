@@ -318,4 +318,53 @@ int launch_xproj_stream(gasr_ctx *ctx, const XsMaps &maps, const XsParams &p, in
     return GASR_OK;
 }
 
+// ---- one-shot use of the tile engine: Linear (<= 32 outputs) + log-softmax over a large row count -----------------------
+// The SIMT kernel of linear.cu keeps W in shared memory and reads x with broadcast loads; for wide inputs (cfg3: 1600) it
+// has one CTA per SM and ~1 KB in flight per SM, 15 ms for 256 000 rows.  Here: x -> bf16 hi/lo planes (one pass), then the
+// persistent GEMM above with a single output-layer target whose dependencies are preset -- TMA-fed, fp32-grade 3-term
+// split, log-softmax in the epilogue.
+bool linear_tc_supported(int rows, int in, int out, int ldy, const float *y, int act) {
+    return act == GASR_ACT_LOGSOFTMAX && out >= 1 && out <= 32 && in >= 1024 && rows >= 4096 && ldy >= 32 && ldy % 4 == 0 &&
+           (reinterpret_cast<uintptr_t>(y) & 15) == 0 && !getenv("GASR_LINEAR_SIMT");
+}
+
+int launch_linear_logsoftmax_tc(gasr_ctx *ctx, const float *x, int ldx, const float *W, const float *b, float *y, int ldy,
+                                int rows, int in, int out, cudaStream_t st) {
+    const int Kp = ceil_div(in, TC_BK) * TC_BK, nb = ceil_div(rows, TC_BM);
+    size_t o = 0;
+    const size_t off_wpad = o; o = align_up(o + sizeof(float) * (size_t)in * 32, 1024);
+    const size_t off_bpad = o; o = align_up(o + 128, 1024);
+    const size_t off_wbuf = o; o = align_up(o + xproj_tc_w_bytes(in, 32), 1024);
+    const size_t off_abuf = o; o = align_up(o + xproj_tc_a_bytes(rows, in), 1024);
+    const size_t off_flags = o; o = align_up(o + sizeof(unsigned) * (2 * (size_t)nb + 32), 1024);
+    GASR_TRY(ws_reserve(ctx, ctx->ws_lin, o));
+    unsigned char *base = static_cast<unsigned char *>(ctx->ws_lin.ptr);
+    float *wpad = reinterpret_cast<float *>(base + off_wpad), *bpad = reinterpret_cast<float *>(base + off_bpad);
+    unsigned *flags = reinterpret_cast<unsigned *>(base + off_flags);
+    // W[in, out] -> [in, 32] (zero columns beyond out), bias -> 32 entries
+    GASR_CUDA(cudaMemsetAsync(base + off_wpad, 0, off_wbuf - off_wpad, st));
+    GASR_CUDA(cudaMemcpy2DAsync(wpad, 32 * sizeof(float), W, (size_t)out * sizeof(float), (size_t)out * sizeof(float), in,
+                                cudaMemcpyDeviceToDevice, st));
+    if (b) GASR_CUDA(cudaMemcpyAsync(bpad, b, sizeof(float) * out, cudaMemcpyDeviceToDevice, st));
+    GASR_TRY(xproj_tc_prepare_weights(ctx, wpad, in, 32, base + off_wbuf, st));
+    GASR_TRY(xproj_tc_split_rows(ctx, x, ldx, rows, in, base + off_abuf, st));
+    GASR_CUDA(cudaMemsetAsync(flags, 0xff, sizeof(unsigned) * nb, st));                          // every source block complete
+    GASR_CUDA(cudaMemsetAsync(flags + nb, 0, sizeof(unsigned) * ((size_t)nb + 32), st));         // tile counters, abort, error
+    XsMaps maps;
+    GASR_TRY(tc_make_map(&maps.m[0], base + off_abuf, rows, Kp, TC_BM));
+    GASR_TRY(tc_make_map(&maps.m[1], base + off_abuf + xproj_tc_a_bytes(rows, in) / 2, rows, Kp, TC_BM));
+    GASR_TRY(tc_make_map(&maps.m[2], base + off_wbuf, 32, Kp, 32));
+    GASR_TRY(tc_make_map(&maps.m[3], base + off_wbuf + xproj_tc_w_bytes(in, 32) / 2, 32, Kp, 32));
+    XsParams p = {};
+    p.M = rows; p.n_blocks = nb; p.n_targets = 1;
+    p.abort = flags + 2 * (size_t)nb;
+    p.error = reinterpret_cast<int *>(flags + 2 * (size_t)nb + 8);
+    XsTarget &t = p.target[0];
+    t.kind = XS_KIND_LOGSOFTMAX; t.cta0 = 0; t.nctas = nb < ctx->sm_count ? nb : ctx->sm_count;
+    t.n_tiles = 1; t.bn = 32; t.kblocks = Kp / TC_BK; t.terms = 3; t.V = out;
+    t.C = y; t.ldc = ldy; t.bias = bpad;
+    t.src_done = flags; t.src_need = 1; t.dst_ready = flags + nb;
+    return launch_xproj_stream(ctx, maps, p, t.nctas, st);
+}
+
 }  // namespace gasr

@@ -330,6 +330,23 @@ def test_linear_fused_activations(gasr, ctx, O, rows, in_, out, act):
     assert np.abs(got - ref).max() < AM_TOL
 
 
+@pytest.mark.parametrize("rows,in_,out", [(4500, 1600, 29), (4096, 1024, 32), (9001, 1100, 5)])
+def test_linear_logsoftmax_tensor_core_path(gasr, ctx, O, rows, in_, out):
+    """Wide inputs and many rows (cfg3's output layer: 256 000 x 1600 -> 29) go through the tcgen05 tile engine with the
+    log-softmax epilogue (output leading dimension 32); it must agree with the oracle like the SIMT kernel does."""
+    rng = np.random.default_rng(rows + in_)
+    x = rng.normal(size=(rows, in_)).astype(np.float32)
+    W = (rng.normal(size=(in_, out)) / np.sqrt(in_)).astype(np.float32)
+    b = rng.normal(size=(out,)).astype(np.float32)
+    ref = O.linear(x, W, b, act="logsoftmax")
+    dx, dW, db, dy = ctx.to_device(x), ctx.to_device(W), ctx.to_device(b), ctx.malloc(rows * 32 * 4)
+    ctx.linear(dx, in_, dW, db, dy, 32, rows, in_, out, gasr.ACT_LOGSOFTMAX)
+    got = ctx.to_host(dy, (rows, 32))[:, :out]
+    for q in (dx, dW, db, dy):
+        ctx.free(q)
+    assert np.abs(got - ref).max() < AM_TOL
+
+
 def _run_rnn(gasr, ctx, cell, bidir, T, N, D, H, L, x, w_ih, w_hh, b_ih, b_hh):
     Dn = 2 if bidir else 1
     dx = ctx.to_device(x)

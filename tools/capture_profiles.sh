@@ -13,6 +13,11 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:xpro
 unset GASR_STREAM_DEBUG GASR_DEBUG_REC_ALONE
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:ctc_beam_cta2 -c 1 -f -o $OUT/r1_ctc_cta2 \
     python tools/microbench.py ctc --T 1000 --kind flat --iters 1 > $OUT/r1_ncu_ctc.log 2>&1
+timeout 250 ncu --set full --clock-control none --import-source on -k regex:ctc_beam_kernel -c 1 -f -o $OUT/r1_ctc_general \
+    python tools/microbench.py ctc --T 2000 --beam 128 --kind random --iters 1 > $OUT/r1_ncu_ctc_general.log 2>&1
+GASR_NO_GRAPH=1 timeout 200 ncu --set full --clock-control none --cache-control none --import-source on -k regex:gru_tc_step --launch-skip 30 -c 1 -f \
+    -o $OUT/r1_gru_step python tools/microbench.py rnn --cell gru --T 60 --N 256 --H 800 --D 161 --L 1 --iters 1 > $OUT/r1_ncu_gru_step.log 2>&1
+timeout 300 python tools/config_sweep.py > $OUT/r1_config_sweep.txt 2>&1
 GASR_STREAM=0 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/r1_launches_chunked.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/r1_ncu_launches.log 2>&1
 GASR_STREAM=0 timeout 120 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/r1_bench_chunked.json 2>/dev/null

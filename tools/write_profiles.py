@@ -4,7 +4,7 @@ import csv, io, json, shutil, subprocess
 def sh(c):
     return subprocess.run(c, shell=True, capture_output=True, text=True).stdout
 
-for f in ("r1_launches_chunked.csv", "r1_bench_streaming.json", "r1_bench_chunked.json"):
+for f in ("r1_launches_chunked.csv", "r1_bench_streaming.json", "r1_bench_chunked.json", "r1_config_sweep.txt"):
     shutil.copy(f"gpurun_out/{f}", f"profiles/{f}")
 rows = list(csv.reader(io.StringIO(sh("ncu -i gpurun_out/r1_rnn_stream.ncu-rep --page raw --csv"))))
 h, u, d = rows[0], rows[1], rows[2]
@@ -22,7 +22,9 @@ SO = "gpu-accelerated-speech-recognition_b200/libgasr.so"
 SRC = "gpu-accelerated-speech-recognition_b200/csrc/"
 for k, regex, hint, src in (("rnn_stream", "rnn_stream", ["rnn_stream_kernel", "Li512E"], "rnn_stream.cu"),
                             ("xproj_stream", "xproj_stream", ["xproj_stream"], "xproj_stream.cu"),
-                            ("ctc_cta2", "ctc_beam_cta2", ["ctc_beam_cta2", "Li1ELi16ELi8E"], "ctc_beam.cu")):
+                            ("ctc_cta2", "ctc_beam_cta2", ["ctc_beam_cta2", "Li1ELi16ELi8E"], "ctc_beam.cu"),
+                            ("ctc_general", "ctc_beam_kernel", ["ctc_beam_kernel", "Li1E", "Li1024E"], "ctc_beam.cu"),
+                            ("gru_step", "gru_tc_step", ["gru_tc_step_kernel"], "gru_tc.cu")):
     summ = sh(f"python tools/ncu_summary.py gpurun_out/r1_{k}.ncu-rep")
     lines = sh(f"python tools/ncu_lines.py gpurun_out/r1_{k}.ncu-rep {regex} --hint {' '.join(hint)} --so {SO} --src {SRC}{src} --top 25")
     extra = ""
@@ -31,7 +33,7 @@ for k, regex, hint, src in (("rnn_stream", "rnn_stream", ["rnn_stream_kernel", "
                 sh("python tools/phase_profile.py gpurun_out/r1_ctc_cta2.ncu-rep") + "```\n"
     open(f"profiles/r1_{k}.md", "w").write(
         f"# ncu --set full --clock-control none: `{regex}` (round 1)\n\nCaptured with `tools/capture_profiles.sh` on a B200 (kernel run "
-        f"ALONE with its dependencies preset -- see profiles/README.md).\n\n{summ}\n{extra}\n## Per-source-line warp-state samples "
+        f"ALONE{' with its dependencies preset' if 'stream' in k else ''} -- see profiles/README.md).\n\n{summ}\n{extra}\n## Per-source-line warp-state samples "
         f"(top 25; `tools/ncu_lines.py`)\n\n```\n{lines}```\n")
 chunked = json.loads(open("profiles/r1_bench_chunked.json").read().strip().splitlines()[-1])
 with open("profiles/r1_launches_chunked.md", "w") as f:
