@@ -40,10 +40,14 @@ xproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles = (raw + 1023u) & ~1023u;                       // SWIZZLE_128B tiles need 1024-byte alignment
-    const uint32_t bars = tiles + TC_STAGES * TC_STAGE_BYTES;            // full[S], empty[S], tmem_full, tmem_slot
+    // stage = A_hi, A_lo, B_hi, B_lo (fp32-grade) or just A_hi, B_hi (bf16): the bf16 mode's 96 KB ring lets two CTAs share
+    // an SM, so one CTA's epilogue overlaps the other's main loop
+    const uint32_t stage_bytes = (p.terms == 3 ? 4u : 2u) * TC_TILE_BYTES;
+    const uint32_t off_b_hi = (p.terms == 3 ? 2u : 1u) * TC_TILE_BYTES;
+    const uint32_t bars = tiles + TC_STAGES * stage_bytes;               // full[S], empty[S], tmem_full, tmem_slot
     const uint32_t full0 = bars, empty0 = bars + 8 * TC_STAGES, tfull = bars + 16 * TC_STAGES;
     unsigned char *gen_tiles = smem_raw + (tiles - raw);
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen_tiles + TC_STAGES * TC_STAGE_BYTES + 16 * TC_STAGES + 8);
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen_tiles + TC_STAGES * stage_bytes + 16 * TC_STAGES + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
@@ -68,10 +72,10 @@ xproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             for (int kb = 0; kb < p.kblocks; kb++) {
                 const int s = kb % TC_STAGES;
                 mbar_wait(empty0 + 8 * s, ((kb / TC_STAGES) & 1) ^ 1);
-                const uint32_t st = tiles + s * TC_STAGE_BYTES;
-                mbar_expect_tx(full0 + 8 * s, (p.terms == 3 ? 4 : 2) * TC_TILE_BYTES);
+                const uint32_t st = tiles + s * stage_bytes;
+                mbar_expect_tx(full0 + 8 * s, stage_bytes);
                 tma_load_2d(st, &map_a_hi, full0 + 8 * s, kb * TC_BK, m0);
-                tma_load_2d(st + 2 * TC_TILE_BYTES, &map_b_hi, full0 + 8 * s, kb * TC_BK, n0);
+                tma_load_2d(st + off_b_hi, &map_b_hi, full0 + 8 * s, kb * TC_BK, n0);
                 if (p.terms == 3) {
                     tma_load_2d(st + TC_TILE_BYTES, &map_a_lo, full0 + 8 * s, kb * TC_BK, m0);
                     tma_load_2d(st + 3 * TC_TILE_BYTES, &map_b_lo, full0 + 8 * s, kb * TC_BK, n0);
@@ -87,9 +91,9 @@ xproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                 const int s = kb % TC_STAGES;
                 mbar_wait(full0 + 8 * s, (kb / TC_STAGES) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t st = tiles + s * TC_STAGE_BYTES;
+                const uint32_t st = tiles + s * stage_bytes;
                 const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + TC_TILE_BYTES);
-                const uint64_t b_hi = umma_desc_sw128(st + 2 * TC_TILE_BYTES), b_lo = umma_desc_sw128(st + 3 * TC_TILE_BYTES);
+                const uint64_t b_hi = umma_desc_sw128(st + off_b_hi), b_lo = umma_desc_sw128(st + 3 * TC_TILE_BYTES);
 #pragma unroll
                 for (int k4 = 0; k4 < TC_BK / 16; k4++) {
                     const uint64_t adv = (uint64_t)(k4 * 32 >> 4);     // 16 bf16 = 32 bytes along K inside the swizzle atom
@@ -280,7 +284,8 @@ int xproj_tc_run(gasr_ctx *ctx, const XprojTcPlan &pl, const float *A, int lda, 
         ctx->attr_mask |= 1024u;
     }
     dim3 grid(ceil_div(pl.N, TC_BN), ceil_div(pl.M, TC_BM));   // TMA zero-fills the rows of W^T beyond N
-    xproj_tcgen05_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(pl.maps[0], pl.maps[1], pl.maps[2], pl.maps[3], p);
+    const size_t smem = p.terms == 3 ? (size_t)TC_SMEM_BYTES : (size_t)TC_SMEM_BYTES - TC_STAGES * 2 * TC_TILE_BYTES;
+    xproj_tcgen05_kernel<<<grid, TC_THREADS, smem, st>>>(pl.maps[0], pl.maps[1], pl.maps[2], pl.maps[3], p);
     GASR_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return GASR_OK;
