@@ -850,10 +850,14 @@ static int asr_run_streaming(gasr_asr *a, const float *x_dev, const float *x_hos
         // host input: the batch is copied in slices on the copy stream; each slice is split into its bf16 planes and
         // then marked ready, so the pipeline starts after the first slice and the rest of the copy hides behind it
         GASR_CUDA(cudaEventRecord(a->ev_go, main_st));
+        GASR_CUDA(cudaStreamWaitEvent(ctx->side[2], a->ev_go, 0));
+    }
+    // Only the first slices are queued before the kernels are launched (enough to keep the copy engine busy meanwhile);
+    // queueing all 16 first cost ~50 API calls of host time before the recurrence kernel could start.
+    const int slices = x_host ? (nb >= 16 ? 16 : 1) : 0, slices_first = slices < 4 ? slices : 4;
+    auto issue_slices = [&](int s_begin, int s_end) -> int {
         cudaStream_t cp_st = ctx->side[2];
-        GASR_CUDA(cudaStreamWaitEvent(cp_st, a->ev_go, 0));
-        const int slices = nb >= 16 ? 16 : 1;
-        for (int sidx = 0; sidx < slices; sidx++) {
+        for (int sidx = s_begin; sidx < s_end; sidx++) {
             const int b0 = (int)((long long)nb * sidx / slices), b1 = (int)((long long)nb * (sidx + 1) / slices);
             if (b1 == b0) continue;
             const size_t r0 = (size_t)b0 * 128, nr = (size_t)(b1 - b0) * 128;
@@ -861,8 +865,10 @@ static int asr_run_streaming(gasr_asr *a, const float *x_dev, const float *x_hos
             GASR_TRY(xproj_tc_split_rows_range(ctx, a->x_dev, c.in, rows, (int)r0, (int)nr, c.in, a->x_planes, cp_st));
             GASR_CUDA(cudaMemsetAsync(x_ready + b0, 0xff, sizeof(unsigned) * (size_t)(b1 - b0), cp_st));
         }
-        GASR_CUDA(cudaEventRecord(a->ev_cp, cp_st));
-    }
+        if (s_end == slices && slices > 0) GASR_CUDA(cudaEventRecord(a->ev_cp, cp_st));
+        return GASR_OK;
+    };
+    GASR_TRY(issue_slices(0, slices_first));
     const bool dbg = getenv("GASR_STREAM_DEBUG") != nullptr;
     if (dbg) { GASR_CUDA(cudaStreamSynchronize(main_st)); fprintf(stderr, "[stream] prep ok\n"); }
 
@@ -996,6 +1002,7 @@ static int asr_run_streaming(gasr_asr *a, const float *x_dev, const float *x_hos
     GASR_CUDA(cudaEventRecord(a->ev_d0, dec_st));
     GASR_TRY(ctc_decode_launch(ctx, ca, dec_st));
     GASR_CUDA(cudaEventRecord(a->ev_d1, dec_st));
+    GASR_TRY(issue_slices(slices_first, slices));              // the rest of the input copy, behind the running pipeline
     GASR_CUDA(cudaStreamWaitEvent(main_st, a->ev_r1, 0));
     GASR_CUDA(cudaStreamWaitEvent(main_st, a->ev_g1, 0));
     GASR_CUDA(cudaStreamWaitEvent(main_st, a->ev_d1, 0));
