@@ -854,7 +854,15 @@ static int asr_run_streaming(gasr_asr *a, const float *x_dev, const float *x_hos
     }
     // Only the first slices are queued before the kernels are launched (enough to keep the copy engine busy meanwhile);
     // queueing all 16 first cost ~50 API calls of host time before the recurrence kernel could start.
-    const int slices = x_host ? (nb >= 16 ? 16 : 1) : 0, slices_first = slices < 4 ? slices : 4;
+    const int slices = x_host ? (nb >= 16 ? 16 : 1) : 0;
+    int slices_first = slices < 4 ? slices : 4;
+    if (x_host) {
+        // Pageable host memory: the driver stages such copies, and staging them while the persistent kernels hold the
+        // GPU never completed (the watchdogs fired).  Only pinned / registered buffers are copied behind the launches.
+        cudaPointerAttributes at = {};
+        if (cudaPointerGetAttributes(&at, x_host) != cudaSuccess || at.type != cudaMemoryTypeHost) { cudaGetLastError(); slices_first = slices; }
+    }
+    if (const char *e = getenv("GASR_STREAM_FIRST_SLICES")) slices_first = atoi(e) < slices ? atoi(e) : slices;
     auto issue_slices = [&](int s_begin, int s_end) -> int {
         cudaStream_t cp_st = ctx->side[2];
         for (int sidx = s_begin; sidx < s_end; sidx++) {

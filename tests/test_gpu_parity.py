@@ -498,6 +498,27 @@ def test_pipeline_end_to_end(gasr, ctx, O, T, N, D, H, L, beam):
     pipe.close()
 
 
+def test_streaming_full_size_from_pageable_and_pinned_host_memory(gasr, ctx):
+    """cfg2-sized batch through gasr_asr_run_host from an ordinary (pageable) numpy array and from a pinned block: both must
+    stay in the streaming mode (no watchdog, no fallback) and return identical transcripts and scores."""
+    import synth
+    T, N, D, H, L, V, beam = 1000, 64, 161, 512, 3, 29, 16
+    x = synth.spectrogram_batch(5, T, N, D)
+    w = synth.rnn_weights(6, D, H, L)
+    fc = synth.fc_weights(7, H, V)
+    pipe = gasr.AsrPipeline(ctx, gasr.CELL_TANH, False, T, N, D, H, L, V, beam, 0, synth.VOCAB29)
+    pipe.set_weights(*w, *fc)
+    xp = ctx.pinned(x.shape)
+    xp[...] = x
+    res = []
+    for src in (x, xp, x):
+        paths, scores = pipe.run_host(src)
+        assert pipe.stage_launches()[1] == -1, "left the streaming mode"
+        res.append((paths, list(scores)))
+    assert res[0] == res[1] == res[2]
+    pipe.close()
+
+
 def test_streaming_falls_back_to_chunked_when_a_producer_is_lost(gasr, ctx, O, monkeypatch):
     """The streaming mode waits inside kernels for other kernels.  If one of them never runs (injected here), the in-kernel
     watchdogs end the step with an error word instead of a hang and the pipeline object drops to the time-chunked mode,
