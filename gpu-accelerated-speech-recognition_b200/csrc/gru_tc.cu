@@ -9,8 +9,8 @@
 // at cfg3 widths, most of it launch gaps and the 2 x 2.4 MB round trip of hh.  Here
 //   * the columns of W_hh^T are permuted at preparation time so that an accumulator tile holds the r, z and n
 //     pre-activations of the SAME 32 hidden units: tile = [r(32) | z(32) | n(32)] = 96 columns (UMMA N = 96);
-//   * the epilogue thread of accumulator row n (utterance n) therefore has everything it needs for 32 units of h_t: it
-//     adds the input projections and biases, applies the gates, writes h_t (fp32, the layer's output) AND the bf16
+//   * an epilogue thread of accumulator row n (utterance n; two threads per row, 16 units each) therefore has everything
+//     it needs for its units of h_t: it adds the input projections and biases, applies the gates, writes h_t (fp32, the layer's output) AND the bf16
 //     hi/lo planes of h_t that the next step's TMA loads read (ping-pong plane buffers) -- no split kernel, no hh;
 //   * the epilogue threads request their xp / h_{t-1} values before they wait for the accumulator, so the scattered
 //     thread-per-row loads complete while the MMAs run.
