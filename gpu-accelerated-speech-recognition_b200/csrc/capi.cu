@@ -108,6 +108,17 @@ int gasr_ctx_create(int device, gasr_ctx **out) {
         return GASR_ERR_UNSUPPORTED;
     }
     gasr_ctx *ctx = new gasr_ctx();
+    {   // environment switches are read here and nowhere else
+        gasr_options &o = ctx->opt;
+        auto chr = [](const char *n) -> char { const char *e = getenv(n); return e ? e[0] : (char)0; };
+        auto num = [](const char *n, int dflt) -> int { const char *e = getenv(n); return e ? atoi(e) : dflt; };
+        o.rnn = chr("GASR_RNN"); o.rnn_mc = num("GASR_RNN_MC", 1); o.rnn_groups = num("GASR_RNN_G", 2);
+        o.ctc_kernel = chr("GASR_CTC_KERNEL"); o.ctc_mw = num("GASR_CTC_MW", 8); o.ctc_pad = num("GASR_CTC_PAD", 0);
+        o.gru = chr("GASR_GRU"); o.gru_no_pdl = getenv("GASR_GRU_NO_PDL") != nullptr; o.no_graph = getenv("GASR_NO_GRAPH") != nullptr;
+        o.bidir_serial = getenv("GASR_BIDIR_SERIAL") != nullptr; o.linear_simt = getenv("GASR_LINEAR_SIMT") != nullptr;
+        o.xproj = chr("GASR_XPROJ"); o.chunk = num("GASR_CHUNK", -1); o.stream = num("GASR_STREAM", -1); o.wave = num("GASR_WAVE", -1);
+        o.stream_gemm_ctas = num("GASR_STREAM_GEMM_CTAS", 24); o.rnn_nsub = num("GASR_RNN_NSUB", -1);
+    }
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
@@ -130,7 +141,7 @@ int gasr_ctx_destroy(gasr_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->dev_blocks) cudaFree(kv.first);
     for (auto &kv : ctx->host_blocks) cudaFreeHost(kv.first);
-    Workspace *wss[] = {&ctx->ws_ctc, &ctx->ws_rnn, &ctx->ws_misc, &ctx->ws_out, &ctx->ws_gru, &ctx->ws_lin, &ctx->ws_rnn_b, &ctx->ws_misc_b, &ctx->ws_gru_b};
+    Workspace *wss[] = {&ctx->ws_ctc, &ctx->ws_rnn, &ctx->ws_misc, &ctx->ws_out, &ctx->ws_gru, &ctx->ws_lin, &ctx->ws_rnn_b, &ctx->ws_misc_b, &ctx->ws_gru_b, &ctx->ws_wide};
     for (cudaEvent_t e : ctx->ev_bi) if (e) cudaEventDestroy(e);
     for (auto &g : ctx->step_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (Workspace *w : wss) if (w->ptr) cudaFree(w->ptr);

@@ -46,7 +46,26 @@ struct Workspace {
 
 }  // namespace gasr
 
+// Environment switches, read ONCE when the context is created (never on a per-call path).
+struct gasr_options {
+    char rnn = 0;            // GASR_RNN: w = wide tcgen05 recurrence, f / m / ... = the round-1 kernels (first letter)
+    int rnn_mc = 1;          // GASR_RNN_MC: TMA multicast of the h boxes in the wide recurrence
+    int rnn_groups = 2;      // GASR_RNN_G: groups of 128 utterances per cluster (1 or 2)
+    char ctc_kernel = 0;     // GASR_CTC_KERNEL
+    int ctc_mw = 8;          // GASR_CTC_MW
+    int ctc_pad = 0;         // GASR_CTC_PAD
+    char gru = 0;            // GASR_GRU
+    bool gru_no_pdl = false, no_graph = false, bidir_serial = false, linear_simt = false;
+    char xproj = 0;          // GASR_XPROJ
+    int chunk = -1;          // GASR_CHUNK (-1: default)
+    int stream = -1;         // GASR_STREAM (-1: default)
+    int wave = -1;           // GASR_WAVE (-1: default): throughput (wave) engine on/off
+    int stream_gemm_ctas = 24;
+    int rnn_nsub = -1;
+};
+
 struct gasr_ctx {
+    gasr_options opt;
     int device = 0;
     int sm_count = 0;
     int max_smem_optin = 0;
@@ -58,6 +77,7 @@ struct gasr_ctx {
     size_t device_bytes = 0, host_bytes = 0;
     std::map<void *, size_t> dev_blocks, host_blocks;
     gasr::Workspace ws_ctc, ws_rnn, ws_misc, ws_out, ws_gru, ws_lin;
+    gasr::Workspace ws_wide;             // planes + W_hh^T planes of the wide recurrence (C-ABI path)
     gasr::Workspace ws_rnn_b, ws_misc_b, ws_gru_b;   // second set: the backward direction of a bidirectional layer runs concurrently
     int ws_sel = 0;                      // which set the recurrent-layer helpers use (0 / 1)
     // instantiated CUDA graphs of launch-bound per-timestep loops (GRU recurrence), keyed by their operands
@@ -138,6 +158,7 @@ struct CtcArgs {
     // streaming pipeline: scores of frame t may be read once lp_ready[t / lp_fpb] >= lp_need (device counters)
     const unsigned *lp_ready = nullptr; int lp_need = 0, lp_fpb = 1; int *error = nullptr; volatile unsigned *abort = nullptr;
     bool vocab_resident = false;   // the vocabulary was uploaded by ctc_decode_upload_vocab
+    int frame_rows = 0;            // rows of `scores` per frame (0: N)
 };
 int ctc_decode_reserve(gasr_ctx *ctx, const CtcArgs &a);                  // allocations only (device-synchronising)
 int ctc_decode_upload_vocab(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st);

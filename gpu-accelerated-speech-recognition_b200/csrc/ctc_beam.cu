@@ -105,6 +105,7 @@ __device__ __forceinline__ float ord2f(uint32_t k) {
 struct CtcParams {
     const float *scores;
     int T, N, V, ld, beam, blank;
+    int frame_rows; // rows of `scores` per frame (>= N; the wave engine pads the batch to whole groups of 128)
     int Vp;        // child-table row pitch (ints)
     int n_pad;     // power of two >= beam * V
     int cap;       // trie nodes per utterance
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
     int *meta = p.meta + (size_t)utt * p.cap;
     int *child = p.child + (size_t)utt * p.cap * Vp;
     const float *S = p.scores + (size_t)utt * p.ld;
-    const size_t frame_stride = (size_t)p.N * p.ld;
+    const size_t frame_stride = (size_t)p.frame_rows * p.ld;
 
     // ---- init: one virtual parent (empty prefix, "ends in blank", unit score); frame 0 then yields the
     //      reference's t = 0 states (kernelInitialPath, CTCBeamSearch.cu:337-364) -------------------------
@@ -773,7 +774,7 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
     int *meta = p.meta + (size_t)utt * p.cap;
     int *child = p.child + (size_t)utt * p.cap * Vp;
     const float *S = p.scores + (size_t)utt * p.ld;
-    const size_t frame_stride = (size_t)p.N * p.ld;
+    const size_t frame_stride = (size_t)p.frame_rows * p.ld;
 
     // every warp writes the same bytes; only __syncwarp ordering is needed for its own reads
     if (active) vch_s[lane] = p.vocab[lane];
@@ -1247,7 +1248,7 @@ __global__ void __launch_bounds__(128) ctc_beam_cta_kernel(const CtcParams p) {
     int *meta = p.meta + (size_t)utt * p.cap;
     int *child = p.child + (size_t)utt * p.cap * Vp;
     const float *S = p.scores + (size_t)utt * p.ld;
-    const size_t frame_stride = (size_t)p.N * p.ld;
+    const size_t frame_stride = (size_t)p.frame_rows * p.ld;
     int4 *gstate = reinterpret_cast<int4 *>(p.state + (size_t)utt * p.state_stride);
     constexpr int kStateVec = (int)(sizeof(CtaBeam<BMAX>) / sizeof(int4));
 
@@ -1745,7 +1746,7 @@ __global__ void __launch_bounds__(MW * 32 + 64) ctc_beam_cta2_kernel(const CtcPa
     int *anc = p.anc + (size_t)utt * p.cap;
     int *child = p.child + (size_t)utt * p.cap * Vp;
     const float *S = p.scores + (size_t)utt * p.ld;
-    const size_t frame_stride = (size_t)p.N * p.ld;
+    const size_t frame_stride = (size_t)p.frame_rows * p.ld;
 
     if (tid < V) vch_s[tid] = p.vocab[tid];
     if (tid < Vp) child[tid] = 0;
@@ -2369,6 +2370,8 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
 
     CtcParams p;
     p.scores = a.scores; p.T = a.T; p.N = a.N; p.V = a.V; p.ld = a.ld; p.beam = a.beam; p.blank = a.blank;
+    p.frame_rows = a.frame_rows > 0 ? a.frame_rows : a.N;
+    GASR_CHECK(p.frame_rows >= a.N, "ctc_decode: frame_rows %d < N %d", p.frame_rows, a.N);
     p.Vp = L.Vp; p.n_pad = L.n_pad; p.cap = L.cap; p.max_len = a.max_len; p.nbest = a.nbest;
     p.vocab = reinterpret_cast<const char *>(ws + L.off_vocab);
     p.parent = reinterpret_cast<int *>(ws + L.off_parent);
@@ -2384,8 +2387,9 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
     p.t0 = t0; p.t1 = t1; p.use_rel = general_rel ? 1 : 0;
     p.state = ws + L.off_state; p.state_stride = L.state_stride;
     p.lp_ready = a.lp_ready; p.lp_need = a.lp_need; p.lp_fpb = a.lp_fpb > 0 ? a.lp_fpb : 1; p.error = a.error; p.abort = a.abort;
-    const char *force_k = getenv("GASR_CTC_KERNEL");
-    const bool use_cta = fast && (a.lp_ready != nullptr || (force_k ? force_k[0] == 'c' : a.N <= 2 * ctx->sm_count));
+    const char force_kc = ctx->opt.ctc_kernel;
+    const char *force_k = force_kc ? &force_kc : nullptr;
+    const bool use_cta = fast && (a.lp_ready != nullptr || (force_k ? (force_k[0] == 'c' || force_k[0] == 'd') : a.N <= 2 * ctx->sm_count));
     GASR_CHECK(a.lp_ready == nullptr || (fast && t0 == 0 && t1 == a.T), "ctc_decode: streaming needs beam <= 32, vocab <= 32, whole sequence");
     {
         // probe cells of the prune lower bound: the (parent rank, score rank) pairs with the smallest (i+1)(j+1)
@@ -2410,9 +2414,8 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
         // latency path, second generation: 8 main warps + fetch warp + trie warp per utterance, whole sequence.  No
         // shared-memory padding: in the streaming pipeline these CTAs may share an SM with a GEMM CTA (whose few
         // threads leave the issue slots free); the recurrence CTAs fill their SMs' register file, so nothing lands there.
-        const size_t pad = getenv("GASR_CTC_PAD") ? (size_t)atoi(getenv("GASR_CTC_PAD")) : 0;
-        const char *mw_env = getenv("GASR_CTC_MW");
-        const int mw = mw_env ? atoi(mw_env) : 8;
+        const size_t pad = (size_t)ctx->opt.ctc_pad;
+        const int mw = ctx->opt.ctc_mw;
 #define GASR_CTA2(DOM, BM)                                                                          \
     do {                                                                                            \
         if (mw == 4) ctc_beam_cta2_kernel<DOM, BM, 4><<<a.N, 192, pad, st>>>(p);                    \

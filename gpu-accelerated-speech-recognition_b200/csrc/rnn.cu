@@ -21,6 +21,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "rnn_wide.cuh"
 #include "rnn_stream.cuh"
 
 namespace cg = cooperative_groups;
@@ -424,13 +425,35 @@ int launch_rnn_recurrence(gasr_ctx *ctx, const RnnLayerArgs &a, cudaStream_t st)
     GASR_CHECK(a.T >= 0 && a.N >= 0 && a.H >= 1, "rnn_recurrence: bad shape");
     GASR_CHECK(a.cell == GASR_CELL_TANH || (a.cell == GASR_CELL_GRU && a.b_hh), "rnn_recurrence: bad cell");
     if (a.T == 0 || a.N == 0) return GASR_OK;
+    {
+        // Many utterances: groups of 128 on the tcgen05 tensor cores (rnn_wide.cu).  The planes it exchanges h through live
+        // in the ctx workspace, so only whole-sequence calls take this path here; the wave engine (asr_wave.cu) owns its
+        // planes and resumes chunk by chunk.
+        const char force = ctx->opt.rnn;
+        const bool whole = a.s0 == 0 && (a.s1 == 0 || a.s1 == a.T);
+        const bool want = force ? force == 'w' : a.N >= 96;
+        if (want && whole && a.cell == GASR_CELL_TANH && !a.reverse && rnn_wide_supported(ctx, a.H) && cluster_kernel_supported(ctx, a)) {
+            const int Npad = ceil_div(a.N, 128) * 128;
+            const size_t pb = rnn_wide_plane_bytes(a.T, Npad, a.H), wb = xproj_tc_w_bytes(a.H, a.H);
+            GASR_TRY(ws_reserve(ctx, ctx->ws_wide, 2 * pb + wb + 2048));
+            unsigned char *base = static_cast<unsigned char *>(ctx->ws_wide.ptr);
+            RnnWidePlan pl;
+            GASR_TRY(rnn_wide_plan(ctx, pl, a.w_hh, a.T, a.N, a.H, base + 2 * pb, base, st));
+            RnnWideRun r = {};
+            r.s0 = 0; r.s1 = a.T; r.xp = a.xproj; r.ldxp = a.ldxp; r.xp_rows_per_frame = a.N;
+            r.out = a.out; r.ldo = a.ldo; r.col0 = a.col0; r.out_rows_per_frame = a.N;
+            r.groups_per_cluster = ctx->opt.rnn_groups; r.multicast = ctx->opt.rnn_mc;
+            return launch_rnn_wide(ctx, pl, r, st);
+        }
+    }
     if (cluster_kernel_supported(ctx, a)) {
         RnnClusterParams p;
         p.xproj = a.xproj; p.ldxp = a.ldxp; p.w_hh = a.w_hh; p.out = a.out; p.ldo = a.ldo; p.col0 = a.col0;
         p.T = a.T; p.N = a.N; p.H = a.H; p.CS = a.H / RC_HC; p.reverse = a.reverse;
         p.s0 = a.s0; p.s1 = a.s1 > 0 ? a.s1 : a.T;
         const int groups = ceil_div(a.N, RC_NB);
-        const char *force = getenv("GASR_RNN");
+        const char force_c = ctx->opt.rnn;
+        const char *force = force_c ? &force_c : nullptr;
         // whole-sequence calls: the latency-optimised persistent kernel (rnn_stream.cu); chunk-resumed calls and the
         // envelope outside it (more than 16 co-resident clusters) stay on the kernels below
         if (!(force && (force[0] == 'f' || force[0] == 'm')) && !a.reverse && p.s0 == 0 && p.s1 == a.T &&
@@ -468,7 +491,8 @@ int launch_rnn_recurrence(gasr_ctx *ctx, const RnnLayerArgs &a, cudaStream_t st)
         return GASR_OK;
     }
     GASR_CHECK(a.N <= 65535, "rnn_recurrence: batch too large for the per-step path");
-    const char *force_g = getenv("GASR_GRU");
+    const char force_gc = ctx->opt.gru;
+    const char *force_g = force_gc ? &force_gc : nullptr;
     const bool gru_batched = a.cell == GASR_CELL_GRU && !(force_g && force_g[0] == 's') && a.N >= 32 && a.s0 == 0 &&
                              (a.s1 == 0 || a.s1 == a.T);
     const bool gru_fused = gru_batched && !(force_g && force_g[0] == 'g') && gru_tc_supported(a.N, a.H, a.ldxp, a.ldo, a.col0) &&
@@ -508,7 +532,7 @@ int launch_rnn_recurrence(gasr_ctx *ctx, const RnnLayerArgs &a, cudaStream_t st)
                 float *o = a.out + (size_t)t * a.N * a.ldo + a.col0;
                 const float *hp = s == 0 ? nullptr : a.out + (size_t)tp * a.N * a.ldo + a.col0;
                 if (gru_fused) {
-                    GASR_TRY(gru_tc_step(ctx, gp, s & 1, xp, a.ldxp, a.b_hh, hp, a.ldo, o, a.ldo, s > 0 && !getenv("GASR_GRU_NO_PDL"), st));
+                    GASR_TRY(gru_tc_step(ctx, gp, s & 1, xp, a.ldxp, a.b_hh, hp, a.ldo, o, a.ldo, s > 0 && !ctx->opt.gru_no_pdl, st));
                     continue;
                 }
                 if (s > 0) GASR_TRY(xproj_tc_run(ctx, pl, hp, a.ldo, a.b_hh, hh, G3, GASR_PREC_FP32, st));
@@ -520,7 +544,7 @@ int launch_rnn_recurrence(gasr_ctx *ctx, const RnnLayerArgs &a, cudaStream_t st)
         // The step loop is launch-bound from the host.  The whole T-step sequence is captured once into a CUDA graph
         // (operands are stable across calls: workspaces, weights, layer buffers) and replayed; the weight preparation
         // and the zeroing of the h planes above stay outside the graph (they run on every call).
-        if (a.T >= 64 && !getenv("GASR_NO_GRAPH")) {
+        if (a.T >= 64 && !ctx->opt.no_graph) {
             gasr_ctx::StepGraph key = {};
             key.k[0] = a.xproj; key.k[1] = a.out; key.k[2] = a.w_hh; key.k[3] = base; key.k[4] = a.b_hh;
             const int dims[8] = {a.T, a.N, H, a.reverse, a.col0, a.ldo, a.ldxp, gru_fused ? 1 : 0};

@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgasr.so")
+LIB_PATH = os.environ.get("GASR_LIB") or os.path.join(_HERE, "libgasr.so")   # GASR_LIB: an instrumented build (tools only)
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_TRUNCATED = range(6)
 ACT_NONE, ACT_RELU, ACT_LOGSOFTMAX = 0, 1, 2

@@ -1,0 +1,58 @@
+"""GPU parity tests of the round-2 throughput path (-m gpu): the tcgen05 recurrence for groups of 128 utterances
+(rnn_wide.cu), called through the C ABI (gasr_rnn_forward), against the CPU oracle.  Tolerance: 1e-4 absolute on fp32
+acoustic-model values (BASELINE.json north_star)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "gpu-accelerated-speech-recognition_b200"))
+
+pytestmark = pytest.mark.gpu
+
+AM_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def gasr():
+    import gasr as g
+    return g
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+def _rnn(gasr, ctx, T, N, D, H, L, x, w_ih, w_hh, b_ih, b_hh):
+    dx = ctx.to_device(x)
+    dw = [[ctx.to_device(m) for m in lst] for lst in (w_ih, w_hh, b_ih, b_hh)]
+    hid = [ctx.malloc(T * N * H * 4) for _ in range(L)]
+    ctx.rnn_forward(gasr.CELL_TANH, False, T, N, D, H, L, dw[0], dw[1], dw[2], dw[3], dx, hid)
+    out = [ctx.to_host(h, (T * N, H)) for h in hid]
+    for p in [dx] + hid + [m for lst in dw for m in lst]:
+        ctx.free(p)
+    return out
+
+
+# (multicast, groups per cluster): the options are read when the context is created
+@pytest.mark.parametrize("mc,groups", [(0, 1), (0, 2), (1, 1), (1, 2)])
+@pytest.mark.parametrize("H,N,T,L", [(512, 128, 24, 1), (512, 300, 17, 2), (256, 256, 20, 1), (128, 200, 12, 1), (64, 130, 9, 2)])
+def test_wide_recurrence_vs_oracle(gasr, O, monkeypatch, mc, groups, H, N, T, L):
+    import synth
+    monkeypatch.setenv("GASR_RNN", "w")
+    monkeypatch.setenv("GASR_RNN_MC", str(mc))
+    monkeypatch.setenv("GASR_RNN_G", str(groups))
+    ctx = gasr.Context(0)
+    D = 37
+    x = synth.spectrogram_batch(H + N, T, N, D)
+    w_ih, w_hh, b_ih, b_hh = synth.rnn_weights(H * 3 + 1, D, H, L)
+    out = _rnn(gasr, ctx, T, N, D, H, L, x, w_ih, w_hh, b_ih, b_hh)
+    ctx.close()
+    ref = O.rnn_forward(x, T, N, w_ih, w_hh, b_ih, b_hh, nthreads=8)
+    for l in range(L):
+        err = np.abs(out[l] - ref[l]).max()
+        assert err < AM_TOL, f"layer {l}: {err}"
