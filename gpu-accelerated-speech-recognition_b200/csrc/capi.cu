@@ -8,6 +8,7 @@
 #include <chrono>
 #include <vector>
 
+#include "asr.cuh"
 #include "common.cuh"
 #include "rnn_stream.cuh"
 #include "stream.cuh"
@@ -359,21 +360,7 @@ int gasr_rnn_cell_forward(gasr_ctx *ctx, const float *x, const float *h_prev, co
 
 namespace gasr {
 
-// Optional per-kernel timing: events recorded between launches on the same stream (no host sync).
-struct StageEvents {
-    std::vector<cudaEvent_t> pool;
-    std::vector<int> tag;        // tag[i] = stage that ends at event i (0 proj, 1 recurrence, 2 linear, 3 decode, -1 start)
-    size_t used = 0;
-    int mark(int stage, cudaStream_t st) {
-        if (used == pool.size()) {
-            cudaEvent_t e;
-            if (cudaEventCreate(&e) != cudaSuccess) return GASR_ERR_CUDA;
-            pool.push_back(e); tag.push_back(-1);
-        }
-        tag[used] = stage;
-        return cudaEventRecord(pool[used++], st) == cudaSuccess ? GASR_OK : GASR_ERR_CUDA;
-    }
-};
+
 
 // One layer, one direction: xproj = src*W_ih + bias (all timesteps), then the persistent recurrence.
 static int rnn_layer_direction(gasr_ctx *ctx, int cell, int T, int N, int in_l, int H, const float *src, int ld_src,
@@ -386,8 +373,7 @@ static int rnn_layer_direction(gasr_ctx *ctx, int cell, int T, int N, int in_l, 
     } else {
         GASR_CUDA(cudaMemcpyAsync(bias, b_ih, sizeof(float) * G * H, cudaMemcpyDeviceToDevice, st));
     }
-    const char *force = getenv("GASR_XPROJ");
-    const bool use_tc = !(force && force[0] == 's') && ld_src == in_l && xproj_tc_supported(T * N, in_l, G * H);
+    const bool use_tc = ctx->opt.xproj != 's' && ld_src == in_l && xproj_tc_supported(T * N, in_l, G * H);
     if (use_tc) {
         // tensor-core path: W^T and A are split into bf16 hi/lo planes in the misc workspace
         const size_t wb = xproj_tc_w_bytes(in_l, G * H), ab = xproj_tc_a_bytes(T * N, in_l);
@@ -422,7 +408,7 @@ int rnn_forward_impl(gasr_ctx *ctx, int cell, int bidir, int T, int N, int in, i
     GASR_TRY(ws_reserve(ctx, ctx->ws_rnn, xp_bytes + align_up(sizeof(float) * G * H, 256)));
     // the two directions of a bidirectional layer are independent (same input, disjoint output columns): the backward one
     // runs on a side stream with its own workspaces
-    const bool fork = D == 2 && st == ctx->stream && !getenv("GASR_BIDIR_SERIAL");
+    const bool fork = D == 2 && st == ctx->stream && !ctx->opt.bidir_serial;
     if (fork) {
         GASR_TRY(ws_reserve(ctx, ctx->ws_rnn_b, xp_bytes + align_up(sizeof(float) * G * H, 256)));
         for (cudaEvent_t &e : ctx->ev_bi)
@@ -495,40 +481,7 @@ int gasr_ctc_decode_host(gasr_ctx *ctx, const float *scores_host, int domain, in
 }  // extern "C"
 
 /* ---- fused pipeline ------------------------------------------------------------------------------------ */
-struct gasr_asr {
-    gasr_ctx *ctx = nullptr;
-    gasr_asr_config cfg;
-    std::vector<char> vocab;
-    int D = 1, G = 1, ldp = 0;
-    std::vector<float *> w_ih, w_hh, b_ih, b_hh, hiddens;
-    float *fc_w = nullptr, *fc_b = nullptr, *x_dev = nullptr, *logp = nullptr;
-    bool have_weights = false;
-    gasr::StageEvents prof;
-    float stage_ms[4] = {0, 0, 0, 0};
-    int stage_launches[4] = {0, 0, 0, 0};
-    // pipelined execution: time chunks flow through (layer 0 .. L-1, linear + decode) on separate streams
-    int chunk = 0;                              // frames per chunk (0 = sequential path)
-    float *xproj_all = nullptr, *bias_all = nullptr;   // [L][T*N*H], [L][H]
-    std::vector<void *> tc_abuf, tc_wbuf;       // per layer: bf16 hi/lo planes of the layer input / of W_ih^T
-    bool use_tc = false;
-    // streaming execution (stream_*): persistent kernels coupled by progress counters, no kernel boundaries in time
-    bool stream_ok = false;
-    int stream_fpb = 0, stream_blocks = 0, stream_gemm_ctas = 0;
-    void *x_planes = nullptr;                   // bf16 hi/lo planes of the input batch [rows, Kp]
-    std::vector<void *> h_planes;               // per layer: bf16 hi/lo planes of the hidden sequence [rows, H] x 2
-    void *fc_wbuf = nullptr;                    // W_fc^T hi/lo planes, padded to 32 output rows
-    float *fc_b_pad = nullptr;
-    unsigned *flags = nullptr;                  // [h_done L][xp_ready L][lp_ready][x_ready][misc 16] x blocks
-    size_t flags_bytes = 0;
-    int *host_words = nullptr, *host_words_dev = nullptr;   // mapped host memory: [0] go, [1] error
-    int epoch = 0;
-    gasr::XsMaps xs_maps;
-    cudaEvent_t ev_cp = nullptr, ev_go = nullptr, ev_r0 = nullptr, ev_r1 = nullptr, ev_g0 = nullptr, ev_g1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
-    std::vector<cudaEvent_t> sync_ev;           // cross-stream dependencies (no timing)
-    std::vector<cudaEvent_t> t0_ev, t1_ev;      // per-launch timing pairs
-    std::vector<int> t_tag;
-    size_t n_timed = 0;
-};
+
 
 extern "C" {
 
@@ -552,6 +505,10 @@ int gasr_asr_create(gasr_ctx *ctx, const gasr_asr_config *cfg, const char *vocab
     a->w_ih.assign(cfg->L * D, nullptr); a->w_hh.assign(cfg->L * D, nullptr);
     a->b_ih.assign(cfg->L * D, nullptr); a->b_hh.assign(cfg->L * D, nullptr);
     a->hiddens.assign(cfg->L, nullptr);
+    // Execution mode.  Default: the wave engine (asr_wave.cu) -- stream-ordered time chunks over groups of 128 utterances,
+    // no kernel ever waits for another kernel.  GASR_STREAM=1 opts into the round-1 latency mode (three persistent kernels
+    // coupled by progress counters: needs a whole idle GPU); GASR_WAVE=0 selects the older chunked path.
+    const bool want_wave = ctx->opt.wave != 0 && ctx->opt.stream != 1 && wave_supported(ctx, *cfg);
     for (int l = 0; l < cfg->L; l++) {
         const int in_l = l == 0 ? cfg->in : D * H;
         for (int d = 0; d < D; d++) {
@@ -560,24 +517,29 @@ int gasr_asr_create(gasr_ctx *ctx, const gasr_asr_config *cfg, const char *vocab
             alloc(&a->b_ih[l * D + d], (size_t)G * H);
             alloc(&a->b_hh[l * D + d], (size_t)G * H);
         }
-        alloc(&a->hiddens[l], rows * D * H);
+        if (!want_wave) alloc(&a->hiddens[l], rows * D * H);
     }
     alloc(&a->fc_w, (size_t)D * H * cfg->V);
     alloc(&a->fc_b, (size_t)cfg->V);
     alloc(&a->x_dev, rows * cfg->in);
+    if (want_wave) {
+        a->ldp = 32;
+        if (st == GASR_OK) st = wave_create(a);
+        if (st != GASR_OK) { gasr_asr_destroy(a); return st; }
+        *out = a;
+        return GASR_OK;
+    }
     alloc(&a->logp, rows * a->ldp);
     {
         // time-chunked pipelining needs the chunk-resumable kernels: cluster recurrence + warp decoder
-        int want = 50;
-        if (const char *e = getenv("GASR_CHUNK")) want = atoi(e);
+        const int want = ctx->opt.chunk >= 0 ? ctx->opt.chunk : 50;
         const bool h_ok = (H == 64 || H == 128 || H == 256 || H == 512) && ctx->cluster_ok;
         if (want > 0 && cfg->cell == GASR_CELL_TANH && !cfg->bidirectional && h_ok && cfg->beam <= 32 && cfg->V <= 32 &&
             cfg->T >= 2 * want) {
             a->chunk = want;
             alloc(&a->xproj_all, (size_t)cfg->L * rows * H);
             alloc(&a->bias_all, (size_t)cfg->L * H);
-            const char *force = getenv("GASR_XPROJ");
-            a->use_tc = !(force && force[0] == 's') && xproj_tc_supported((int)rows, cfg->in, H);
+            a->use_tc = ctx->opt.xproj != 's' && xproj_tc_supported((int)rows, cfg->in, H);
             if (a->use_tc) {
                 a->tc_abuf.assign(cfg->L, nullptr); a->tc_wbuf.assign(cfg->L, nullptr);
                 for (int l = 0; l < cfg->L && st == GASR_OK; l++) {
@@ -592,15 +554,13 @@ int gasr_asr_create(gasr_ctx *ctx, const gasr_asr_config *cfg, const char *vocab
     }
     if (st == GASR_OK && a->chunk > 0 && a->use_tc) {
         // streaming envelope: whole blocks of 128 rows, the persistent recurrence's cluster budget, one output tile
-        int want_stream = 1;
-        if (const char *e = getenv("GASR_STREAM")) want_stream = atoi(e);
+        const int want_stream = ctx->opt.stream == 1;          // opt-in: persistent kernels that wait for each other
         const int N = cfg->N, L = cfg->L;
         if (want_stream && cfg->beam <= 32 && cfg->V <= 32 && N % 16 == 0 && 128 % N == 0 && L + 1 <= XS_MAX_TARGETS && L <= RS_MAX_LAYERS &&
             rnn_stream_supported(ctx, H, N, L) && H % 128 == 0 && ((size_t)cfg->T * N) % 128 == 0 && ctx->sm_count >= 132) {
             a->stream_fpb = 128 / N;
             a->stream_blocks = (int)(rows / 128);
-            a->stream_gemm_ctas = 24;
-            if (const char *e = getenv("GASR_STREAM_GEMM_CTAS")) a->stream_gemm_ctas = atoi(e);
+            a->stream_gemm_ctas = ctx->opt.stream_gemm_ctas;
             auto allocv = [&](void **p, size_t bytes) { if (st == GASR_OK) st = gasr_malloc_device(ctx, bytes, p); };
             allocv(&a->x_planes, xproj_tc_a_bytes((int)rows, cfg->in) + 1024);
             a->h_planes.assign(L, nullptr);
@@ -631,6 +591,7 @@ int gasr_asr_destroy(gasr_asr *a) {
     gasr_ctx *ctx = a->ctx;
     GASR_ENTER(ctx);
     cudaStreamSynchronize(ctx->stream);
+    wave_destroy(a);
     for (auto v : {&a->w_ih, &a->w_hh, &a->b_ih, &a->b_hh, &a->hiddens})
         for (float *p : *v) if (p) gasr_free_device(ctx, p);
     for (float *p : {a->fc_w, a->fc_b, a->x_dev, a->logp, a->xproj_all, a->bias_all}) if (p) gasr_free_device(ctx, p);
@@ -672,6 +633,11 @@ int gasr_asr_set_weights(gasr_asr *a, const float *const *w_ih, const float *con
             GASR_TRY(xproj_tc_prepare_weights(ctx, a->w_ih[l], l == 0 ? c.in : H, H, a->tc_wbuf[l], ctx->stream));
     GASR_TRY(gasr_memcpy_h2d(ctx, a->fc_w, fc_w, sizeof(float) * D * H * c.V));
     GASR_TRY(gasr_memcpy_h2d(ctx, a->fc_b, fc_b, sizeof(float) * c.V));
+    if (a->wave) {
+        GASR_TRY(wave_set_weights(a, fc_w, fc_b));
+        a->have_weights = true;
+        return GASR_OK;
+    }
     if (a->stream_ok) {
         // output layer as a 32-column GEMM target: W_fc padded to [H, 32] -> W^T hi/lo planes; bias padded with zeros
         std::vector<float> wpad((size_t)H * 32, 0.0f), bpad(32, 0.0f);
@@ -1055,6 +1021,10 @@ int gasr_asr_run_device(gasr_asr *a, const float *x_dev, char *out_paths, int *o
     GASR_ENTER(ctx);
     GASR_CHECK(a->have_weights, "gasr_asr_run: weights not set");
     GASR_CHECK(x_dev && out_paths && out_lens && out_scores, "gasr_asr_run: null argument");
+    if (a->wave) {
+        GASR_TRY(wave_submit(a, x_dev, nullptr));
+        return wave_collect(a, out_paths, out_lens, out_scores);
+    }
     if (a->stream_ok) {
         const int rc = asr_run_streaming(a, x_dev, nullptr, out_paths, out_lens, out_scores);
         if (rc == GASR_OK || getenv("GASR_STREAM_DEBUG")) return rc;
@@ -1072,6 +1042,10 @@ int gasr_asr_run_host(gasr_asr *a, const float *x_host, char *out_paths, int *ou
     const gasr_asr_config &c = a->cfg;
     GASR_CHECK(a->have_weights, "gasr_asr_run: weights not set");
     GASR_CHECK(out_paths && out_lens && out_scores, "gasr_asr_run: null argument");
+    if (a->wave) {
+        GASR_TRY(wave_submit(a, nullptr, x_host));
+        return wave_collect(a, out_paths, out_lens, out_scores);
+    }
     if (a->stream_ok) {
         const int rc = asr_run_streaming(a, a->x_dev, x_host, out_paths, out_lens, out_scores);
         if (rc == GASR_OK || getenv("GASR_STREAM_DEBUG")) return rc;
@@ -1084,6 +1058,7 @@ int gasr_asr_run_host(gasr_asr *a, const float *x_host, char *out_paths, int *ou
 
 int gasr_asr_logprobs(gasr_asr *a, const float **logp_dev, int *ldp) {
     GASR_CHECK(a && logp_dev && ldp, "gasr_asr_logprobs: null argument");
+    if (a->wave) { DeviceGuard guard(a->ctx->device); return wave_logprobs(a, logp_dev, ldp); }
     *logp_dev = a->logp;
     *ldp = a->ldp;
     return GASR_OK;
@@ -1098,7 +1073,43 @@ int gasr_asr_stage_times(gasr_asr *a, float *ms4) {
 int gasr_asr_stage_launches(gasr_asr *a, int *n4, int *chunk_frames) {
     GASR_CHECK(a && n4, "gasr_asr_stage_launches: null argument");
     for (int i = 0; i < 4; i++) n4[i] = a->stage_launches[i];
-    if (chunk_frames) *chunk_frames = a->stream_ok ? -1 : a->chunk;
+    if (chunk_frames) *chunk_frames = a->wave ? -2 : (a->stream_ok ? -1 : a->chunk);
+    return GASR_OK;
+}
+
+/* ---- asynchronous form + profiling (wave engine) -------------------------------------------------------------------- */
+int gasr_asr_submit_host(gasr_asr *a, const float *x_host) {
+    GASR_CHECK(a != nullptr && x_host != nullptr, "gasr_asr_submit_host: null argument");
+    GASR_ENTER(a->ctx);
+    GASR_CHECK(a->have_weights, "gasr_asr_submit: weights not set");
+    if (!a->wave) { set_error("gasr_asr_submit: this configuration runs outside the wave engine; use gasr_asr_run_host"); return GASR_ERR_UNSUPPORTED; }
+    return wave_submit(a, nullptr, x_host);
+}
+
+int gasr_asr_submit_device(gasr_asr *a, const float *x_dev) {
+    GASR_CHECK(a != nullptr && x_dev != nullptr, "gasr_asr_submit_device: null argument");
+    GASR_ENTER(a->ctx);
+    GASR_CHECK(a->have_weights, "gasr_asr_submit: weights not set");
+    if (!a->wave) { set_error("gasr_asr_submit: this configuration runs outside the wave engine; use gasr_asr_run_device"); return GASR_ERR_UNSUPPORTED; }
+    return wave_submit(a, x_dev, nullptr);
+}
+
+int gasr_asr_collect(gasr_asr *a, char *out_paths, int *out_lens, float *out_scores) {
+    GASR_CHECK(a != nullptr && out_paths && out_lens && out_scores, "gasr_asr_collect: null argument");
+    GASR_ENTER(a->ctx);
+    if (!a->wave) { set_error("gasr_asr_collect: nothing was submitted"); return GASR_ERR_INVALID; }
+    return wave_collect(a, out_paths, out_lens, out_scores);
+}
+
+int gasr_asr_profile(gasr_asr *a, int on) {
+    GASR_CHECK(a != nullptr, "null gasr_asr");
+    a->profile = on != 0;
+    return GASR_OK;
+}
+
+int gasr_asr_last_ms(gasr_asr *a, float *ms) {
+    GASR_CHECK(a != nullptr && ms != nullptr, "gasr_asr_last_ms: null argument");
+    *ms = wave_last_ms(a);
     return GASR_OK;
 }
 

@@ -124,7 +124,7 @@ int launch_linear(gasr_ctx *ctx, const float *x, int ldx, const float *W, const 
     GASR_CHECK(rows >= 0 && in >= 1 && out >= 1 && ldx >= in && ldy >= out, "linear: bad shape");
     GASR_CHECK(act == GASR_ACT_NONE || act == GASR_ACT_RELU || act == GASR_ACT_LOGSOFTMAX, "linear: unknown activation");
     if (rows == 0) return GASR_OK;
-    if (linear_tc_supported(rows, in, out, ldy, y, act))
+    if (!ctx->opt.linear_simt && linear_tc_supported(rows, in, out, ldy, y, act))
         return launch_linear_logsoftmax_tc(ctx, x, ldx, W, b, y, ldy, rows, in, out, st);
     const size_t smem = (size_t)in * 32 * sizeof(float);
     if (out <= 32 && smem <= (size_t)ctx->max_smem_optin - 1024) {

@@ -10,7 +10,7 @@
 //   * CTA r of the cluster keeps columns [64r, 64r+64) of W_hh resident in shared memory for the whole launch, as the
 //     K-major B operand (W_hh^T slice, bf16 hi + lo planes, 128-byte swizzle): H x 64 x 2 x 2 B = 128 KB at H = 512;
 //   * h_{t-1} of the group -- [128 x H] as bf16 hi/lo planes, exactly the array this kernel writes for the next layer's
-//     projection GEMM -- is the A operand.  It is pulled through a 3-stage ring by TMA ([128 x 64] boxes); with multicast the
+//     projection GEMM -- is the A operand.  It is pulled through a 2-stage ring by TMA ([128 x 64] boxes); with multicast the
 //     H/64 CTAs of the cluster each issue 1/(H/64) of the boxes and every box lands in all of them;
 //   * D[128 utterances x 64 columns] accumulates in TMEM (fp32); three MMA terms (hi*hi + hi*lo + lo*hi) give an fp32-grade
 //     product (same split as xproj_gemm_tc.cu);
@@ -36,12 +36,13 @@ namespace gasr {
 
 constexpr int RW_COLS = 64;                       // W_hh columns per CTA (UMMA N)
 constexpr int RW_U = 128;                         // utterances per group (UMMA M)
-constexpr int RW_STAGES = 3;
+constexpr int RW_STAGES = 2;                      // 2 x 32 KB in flight covers the TMA latency at the ~40 B/clk an SM ingests
 constexpr int RW_EPI_WARPS = 8;
 constexpr int RW_THREADS = 64 + 32 * RW_EPI_WARPS;   // TMA warp, MMA warp, epilogue warps
 constexpr int RW_A_TILE = RW_U * TC_BK * 2;       // 16 KB: [128 x 64] bf16
 constexpr int RW_STAGE_BYTES = 2 * RW_A_TILE;     // hi + lo
 constexpr int RW_W_TILE = RW_COLS * TC_BK * 2;    // 8 KB: [64 x 64] bf16
+constexpr int RW_EPI_STAGE = 4096;                // per epilogue warp: [32 rows x 64 B] hi + lo, to store whole 64-byte row segments
 constexpr unsigned long long RW_TIMEOUT_NS = 4000000000ull;
 
 struct RnnWideParams {
@@ -146,7 +147,8 @@ rnn_wide_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_const
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t w_smem = (raw + 1023u) & ~1023u;                         // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t ring = w_smem + (uint32_t)p.KB * 2u * RW_W_TILE;
-    const uint32_t bars = ring + RW_STAGES * RW_STAGE_BYTES;
+    const uint32_t epi_stage = ring + RW_STAGES * RW_STAGE_BYTES;
+    const uint32_t bars = epi_stage + RW_EPI_WARPS * RW_EPI_STAGE;
     const uint32_t full0 = bars, empty0 = bars + 8 * RW_STAGES, accf0 = bars + 16 * RW_STAGES, hrdy0 = accf0 + 16, wfull = hrdy0 + 16;
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem_raw + (wfull + 8 - raw));
 
@@ -264,15 +266,17 @@ rnn_wide_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_const
             for (int g = 0; g < ng; g++) {
                 const int u = (g0 + g) * RW_U + row;
                 const bool live = u < p.N;
-                // the projection values do not depend on the MMAs: request them before waiting for the accumulator
-                float4 x4[8];
-                if (live) {
-                    const float4 *xr = reinterpret_cast<const float4 *>(p.xp + ((size_t)t * p.xp_rpf + u) * p.ldxp + c0);
+                // The projection values do not depend on the MMAs: request them before waiting for the accumulator.  Coalesced:
+                // an instruction fetches 4 rows x 128 B of the warp's [32 rows x 32 columns] piece (a row-per-thread load
+                // touches 32 cache lines per instruction); the piece is transposed through shared memory below.
+                const int ubase = (g0 + g) * RW_U + q * 32;
+                const int lr = lane >> 3, lc = lane & 7;
+                float4 xg[8];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) x4[j] = __ldcs(xr + j);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; j++) x4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < 8; i++) {
+                    const int uu = ubase + 4 * i + lr;
+                    xg[i] = uu < p.N ? __ldcs(reinterpret_cast<const float4 *>(p.xp + ((size_t)t * p.xp_rpf + uu) * p.ldxp + c0) + lc)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 uint32_t v[32];
                 const bool stamp = g == 0 && warp == 2 && lane == 0;
@@ -289,6 +293,16 @@ rnn_wide_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_const
                     for (int j = 0; j < 32; j++) v[j] = 0u;
                 }
                 if (stamp) RW_STAMP(8);
+                float4 x4[8];
+                {
+                    float4 *sx = reinterpret_cast<float4 *>(smem_raw + (epi_stage - raw) + (uint32_t)(warp - 2) * RW_EPI_STAGE);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) { const int r = 4 * i + lr; sx[r * 8 + (lc ^ (r & 7))] = xg[i]; }
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; j++) x4[j] = sx[lane * 8 + (j ^ (lane & 7))];
+                    __syncwarp();
+                }
                 float h[32];
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
@@ -308,12 +322,27 @@ rnn_wide_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_const
                     ph[j] = *reinterpret_cast<const uint32_t *>(&th);
                     pl[j] = *reinterpret_cast<const uint32_t *>(&tl);
                 }
-                const size_t prow = ((size_t)t * p.Npad + u) * H + c0;
-                uint4 *dh = reinterpret_cast<uint4 *>(p.hi + prow), *dl = reinterpret_cast<uint4 *>(p.lo + prow);
+                // Stores: a thread-per-row store touches 32 cache lines per instruction (the epilogue was bound by exactly that).
+                // The warp's [32 rows x 64 B] pieces of both planes go through a swizzled shared-memory tile and leave as
+                // 8 rows x 64 contiguous bytes per instruction.
+                {
+                    uint4 *sw = reinterpret_cast<uint4 *>(smem_raw + (epi_stage - raw) + (uint32_t)(warp - 2) * RW_EPI_STAGE);
+                    const int xr = (lane >> 1) & 3;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    dh[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
-                    dl[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+                    for (int j = 0; j < 4; j++) {
+                        sw[lane * 4 + (j ^ xr)] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+                        sw[128 + lane * 4 + (j ^ xr)] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i2 = 0; i2 < 4; i2++) {
+                        const int r = 8 * i2 + (lane >> 2), c = lane & 3;
+                        const int sidx = r * 4 + (c ^ ((r >> 1) & 3));
+                        const size_t prow = ((size_t)t * p.Npad + ubase + r) * H + c0;
+                        reinterpret_cast<uint4 *>(p.hi + prow)[c] = sw[sidx];
+                        reinterpret_cast<uint4 *>(p.lo + prow)[c] = sw[128 + sidx];
+                    }
+                    __syncwarp();
                 }
                 if (p.out != nullptr && live) {
                     float4 *o = reinterpret_cast<float4 *>(p.out + ((size_t)t * p.out_rpf + u) * p.ldo + p.col0 + c0);
@@ -348,7 +377,7 @@ bool rnn_wide_supported(const gasr_ctx *ctx, int H) {
     return ctx->cluster_ok && (H == 64 || H == 128 || H == 256 || H == 512);
 }
 
-size_t rnn_wide_smem_bytes(int H) { return 1024 + (size_t)(H / 64) * 2 * RW_W_TILE + RW_STAGES * RW_STAGE_BYTES + 256; }
+size_t rnn_wide_smem_bytes(int H) { return 1024 + (size_t)(H / 64) * 2 * RW_W_TILE + RW_STAGES * RW_STAGE_BYTES + RW_EPI_WARPS * RW_EPI_STAGE + 256; }
 size_t rnn_wide_plane_bytes(int T, int Npad, int H) { return align_up((size_t)T * Npad * H * 2, 1024); }   // one plane (hi or lo)
 
 // W_hh -> W_hh^T bf16 hi/lo planes (xproj_tc_prepare_weights layout) + the four TMA descriptors of a layer

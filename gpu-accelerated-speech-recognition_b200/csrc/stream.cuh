@@ -25,6 +25,7 @@ struct XsTarget {
 
 struct XsParams {
     int M;                    // rows (T * N)
+    int row0;                 // first row of the A operand in its TMA descriptor (the wave engine runs one time chunk per launch)
     int n_blocks;             // ceil(M / 128)
     int n_targets;
     int *error;               // mapped host word: watchdog code

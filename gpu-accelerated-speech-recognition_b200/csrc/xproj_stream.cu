@@ -152,10 +152,10 @@ xproj_stream_kernel(const __grid_constant__ XsMaps maps, const XsParams p) {
                     if (!xs_wait(empty0 + 8 * s, ((it / TC_STAGES) & 1) ^ 1, abort_flag, p.abort)) break;
                     const uint32_t st = tiles + s * TC_STAGE_BYTES;
                     mbar_expect_tx(full0 + 8 * s, bytes);
-                    tma_load_2d(st, ma_hi, full0 + 8 * s, kb * TC_BK, blk * TC_BM);
+                    tma_load_2d(st, ma_hi, full0 + 8 * s, kb * TC_BK, p.row0 + blk * TC_BM);
                     tma_load_2d(st + 2 * TC_TILE_BYTES, mb_hi, full0 + 8 * s, kb * TC_BK, tile * t.bn);
                     if (t.terms == 3) {
-                        tma_load_2d(st + TC_TILE_BYTES, ma_lo, full0 + 8 * s, kb * TC_BK, blk * TC_BM);
+                        tma_load_2d(st + TC_TILE_BYTES, ma_lo, full0 + 8 * s, kb * TC_BK, p.row0 + blk * TC_BM);
                         tma_load_2d(st + 3 * TC_TILE_BYTES, mb_lo, full0 + 8 * s, kb * TC_BK, tile * t.bn);
                     }
                 }
@@ -325,7 +325,7 @@ int launch_xproj_stream(gasr_ctx *ctx, const XsMaps &maps, const XsParams &p, in
 // split, log-softmax in the epilogue.
 bool linear_tc_supported(int rows, int in, int out, int ldy, const float *y, int act) {
     return act == GASR_ACT_LOGSOFTMAX && out >= 1 && out <= 32 && in >= 1024 && rows >= 4096 && ldy >= 32 && ldy % 4 == 0 &&
-           (reinterpret_cast<uintptr_t>(y) & 15) == 0 && !getenv("GASR_LINEAR_SIMT");
+           (reinterpret_cast<uintptr_t>(y) & 15) == 0;
 }
 
 int launch_linear_logsoftmax_tc(gasr_ctx *ctx, const float *x, int ldx, const float *W, const float *b, float *y, int ldy,

@@ -55,6 +55,7 @@ EXPORTS = [
     "gasr_matmul", "gasr_matadd", "gasr_xproj_gemm", "gasr_linear_forward", "gasr_log_softmax", "gasr_rnn_cell_forward",
     "gasr_rnn_forward", "gasr_ctc_decode", "gasr_ctc_last_stats", "gasr_ctc_decode_host", "gasr_asr_create", "gasr_asr_destroy",
     "gasr_asr_set_weights", "gasr_asr_run_host", "gasr_asr_run_device", "gasr_asr_logprobs", "gasr_asr_stage_times", "gasr_asr_stage_launches",
+    "gasr_asr_submit_host", "gasr_asr_submit_device", "gasr_asr_collect", "gasr_asr_profile", "gasr_asr_last_ms",
 ]
 
 
@@ -450,6 +451,27 @@ class AsrPipeline:
                                         self._lens.ctypes.data_as(c_int_p), _fp(self._scores)))
         return self._result()
 
+    def submit_host(self, x_host):
+        assert x_host.dtype == np.float32 and x_host.flags["C_CONTIGUOUS"]
+        self._keep = x_host
+        _check(_lib.gasr_asr_submit_host(self._h, _fp(x_host)))
+
+    def submit_device(self, x_dev):
+        _check(_lib.gasr_asr_submit_device(self._h, x_dev))
+
+    def collect(self):
+        _check(_lib.gasr_asr_collect(self._h, self._paths.ctypes.data_as(ctypes.c_char_p),
+                                     self._lens.ctypes.data_as(c_int_p), _fp(self._scores)))
+        return self._result()
+
+    def profile(self, on=True):
+        _check(_lib.gasr_asr_profile(self._h, int(on)))
+
+    def last_ms(self):
+        ms = ctypes.c_float(0)
+        _check(_lib.gasr_asr_last_ms(self._h, ctypes.byref(ms)))
+        return ms.value
+
     def logprobs(self):
         p, ld = ctypes.c_void_p(), ctypes.c_int(0)
         _check(_lib.gasr_asr_logprobs(self._h, ctypes.byref(p), ctypes.byref(ld)))
@@ -507,6 +529,11 @@ def _declare():
     L.gasr_asr_logprobs.argtypes = [vp, c_void_pp, c_int_p]
     L.gasr_asr_stage_times.argtypes = [vp, c_float_p]
     L.gasr_asr_stage_launches.argtypes = [vp, c_int_p, c_int_p]
+    L.gasr_asr_submit_host.argtypes = [vp, c_float_p]
+    L.gasr_asr_submit_device.argtypes = [vp, vp]
+    L.gasr_asr_collect.argtypes = [vp, ctypes.c_char_p, c_int_p, c_float_p]
+    L.gasr_asr_profile.argtypes = [vp, ci]
+    L.gasr_asr_last_ms.argtypes = [vp, c_float_p]
 
 
 _declare()

@@ -159,10 +159,25 @@ int gasr_asr_stage_times(gasr_asr *asr, float *ms4);
  *   0   the stages ran back to back on one stream;
  *   >0  time chunks of that many frames flowed through the stages on concurrent streams (a stage time is the sum of
  *       its launches' durations);
- *   -1  streaming: one persistent kernel per stage (recurrence of all layers / projection + output-layer GEMM / decoder)
+ *   -2  wave engine (default wherever it applies: unidirectional tanh stacks, H in {128, 256, 512}, beam / vocabulary <= 32):
+ *       groups of 128 utterances, time chunks on per-stage streams ordered by events; a stage time is the sum of its launches'
+ *       durations (only with gasr_asr_profile on);
+ *   -1  streaming (opt-in, GASR_STREAM=1): one persistent kernel per stage (recurrence of all layers / projection + output-layer GEMM / decoder)
  *       ran concurrently for the whole sequence, coupled by progress counters in HBM; a stage time is the duration of
  *       its kernel and the Linear + log-softmax stage is part of the GEMM kernel (reported as 0).                  */
 int gasr_asr_stage_launches(gasr_asr *asr, int *n4, int *chunk_frames);
+/*
+ * Asynchronous form (wave engine; GASR_ERR_UNSUPPORTED for configurations outside it): submit enqueues one batch on the
+ * pipeline's streams and returns; collect waits for it and unpacks transcripts / lengths / scores.  One batch in flight
+ * per gasr_asr; several gasr_asr objects (each on its own gasr_ctx) overlap on one GPU -- gasr_job_* below does that.
+ */
+int gasr_asr_submit_host(gasr_asr *asr, const float *x_host);
+int gasr_asr_submit_device(gasr_asr *asr, const float *x_dev);
+int gasr_asr_collect(gasr_asr *asr, char *out_paths, int *out_lens, float *out_scores);
+/* Per-launch stage timing on/off (two event records per kernel launch; off by default) and the device time of the last
+ * batch, first kernel to last result copy, measured with CUDA events.                                                 */
+int gasr_asr_profile(gasr_asr *asr, int on);
+int gasr_asr_last_ms(gasr_asr *asr, float *ms);
 
 #ifdef __cplusplus
 }

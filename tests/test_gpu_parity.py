@@ -498,10 +498,12 @@ def test_pipeline_end_to_end(gasr, ctx, O, T, N, D, H, L, beam):
     pipe.close()
 
 
-def test_streaming_full_size_from_pageable_and_pinned_host_memory(gasr, ctx):
+def test_streaming_full_size_from_pageable_and_pinned_host_memory(gasr, monkeypatch):
     """cfg2-sized batch through gasr_asr_run_host from an ordinary (pageable) numpy array and from a pinned block: both must
-    stay in the streaming mode (no watchdog, no fallback) and return identical transcripts and scores."""
+    stay in the (opt-in, GASR_STREAM=1) streaming mode (no watchdog, no fallback) and return identical transcripts and scores."""
     import synth
+    monkeypatch.setenv("GASR_STREAM", "1")
+    ctx = gasr.Context(0)
     T, N, D, H, L, V, beam = 1000, 64, 161, 512, 3, 29, 16
     x = synth.spectrogram_batch(5, T, N, D)
     w = synth.rnn_weights(6, D, H, L)
@@ -517,9 +519,10 @@ def test_streaming_full_size_from_pageable_and_pinned_host_memory(gasr, ctx):
         res.append((paths, list(scores)))
     assert res[0] == res[1] == res[2]
     pipe.close()
+    ctx.close()
 
 
-def test_streaming_falls_back_to_chunked_when_a_producer_is_lost(gasr, ctx, O, monkeypatch):
+def test_streaming_falls_back_to_chunked_when_a_producer_is_lost(gasr, O, monkeypatch):
     """The streaming mode waits inside kernels for other kernels.  If one of them never runs (injected here), the in-kernel
     watchdogs end the step with an error word instead of a hang and the pipeline object drops to the time-chunked mode,
     which must give the same transcripts and scores."""
@@ -528,6 +531,8 @@ def test_streaming_falls_back_to_chunked_when_a_producer_is_lost(gasr, ctx, O, m
     x = synth.spectrogram_batch(5, T, N, D)
     w_ih, w_hh, b_ih, b_hh = synth.rnn_weights(6, D, H, L)
     fc_w, fc_b = synth.fc_weights(7, H, V)
+    monkeypatch.setenv("GASR_STREAM", "1")                     # the streaming (latency) mode is opt-in since round 2
+    ctx = gasr.Context(0)
     pipe = gasr.AsrPipeline(ctx, gasr.CELL_TANH, False, T, N, D, H, L, V, beam, 0, synth.VOCAB29)
     pipe.set_weights(w_ih, w_hh, b_ih, b_hh, fc_w, fc_b)
     good = pipe.run_host(x)
@@ -541,6 +546,7 @@ def test_streaming_falls_back_to_chunked_when_a_producer_is_lost(gasr, ctx, O, m
     assert again[0] == good[0]
     assert np.allclose(again[1], good[1], rtol=1e-5, atol=0)
     pipe.close()
+    ctx.close()
 
 
 def test_cpp_module_mirror(tmp_path):
