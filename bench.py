@@ -4,19 +4,24 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
 
-A "step" is one pass of the whole path over one batch of BASELINE.json configs[1] ("cfg2": 64 utterances x
-1000 frames x 161 bins, 3-layer tanh RNN H=512, Linear 512->29 + log-softmax, beam 16) on synthetic, seeded
-inputs and torch-default-initialised random weights.  Every rank owns its own batch (weak scaling, utterances are
-independent: no data-path collective); rank 0 prints ONE JSON line.
+Workload = BASELINE.json configs[4] ("cfg5", the configuration the RTFx-at-1/2/4/8-GPUs metric is quoted on): 8192 synthetic
+utterances of the cfg2 shape (T=1000 frames x 161 bins, 3-layer tanh RNN H=512, Linear 512->29 + log-softmax, beam 16),
+torch-default random weights.  The 8192 utterances are cut into batches of --wave utterances; rank r of N owns a CONTIGUOUS
+range of batches (strong scaling, utterances are independent: no data-path collective), runs them through gasr_job_*
+(several batches in flight per GPU) and the transcripts + scores are gathered on the host.  A "step" is one pass over all
+8192 utterances.  Rank 0 prints ONE JSON line.
 
-  value     RTFx with the batch already resident in HBM; transcripts + scores land in host memory inside the
-            timed region.  Device-timed (CUDA events on the library's stream), max over ranks.
-  e2e       the same through the host-buffer entry point gasr_asr_run_host: the batch is copied from pinned host
-            memory every step (h2d_bytes_per_step) and the results are read back (d2h_bytes_per_step).
-  roofline  the dominant kernel (the persistent recurrence kernel) against the measured HBM peak.
-  cpu_baseline / --impl reference: the CPU restatement of the reference (oracle/, "port": the reference ships no
-            runnable CPU implementation of this path -- CTCBeamSearch.cpp does not compile) on the
-            box's host cores, on a bounded sample of the same workload.
+  value     RTFx with every batch already resident in HBM; transcripts + scores land in host memory inside the timed
+            region.  Device-timed (CUDA events on the library's stream), max over ranks.
+  e2e       the same through the host-buffer entry point gasr_job_run_host: every batch is copied from pinned host memory
+            each step (h2d_bytes_per_step) and the results are read back (d2h_bytes_per_step).
+  roofline  the recurrence kernel (largest algorithmic byte count of the path) against the measured HBM peak, from per-launch
+            CUDA-event durations inside the running pipeline; stage_rooflines has every stage.
+  parity_checked / gather  oracle check of the benched computation (log-probs 1e-4, transcripts and scores bit-exact) and
+            bit-equality of the N-GPU gathered result with the same utterances decoded by rank 0 alone.
+  cpu_baseline / --impl reference: the CPU restatement of the reference (oracle/, "port": the reference ships no runnable
+            CPU implementation of this path -- CTCBeamSearch.cpp does not compile) on the box's host cores,
+            on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -34,9 +39,12 @@ sys.path.insert(0, ROOT)
 
 METRIC = "RTFx: audio-sec decoded/sec (RNN fwd + CTC beam) at 1/2/4/8 B200"
 UNIT = "audio-seconds per second"
-CFG = dict(T=1000, N=64, D=161, H=512, L=3, V=29, beam=16)   # BASELINE.json configs[1]
+CFG = dict(T=1000, D=161, H=512, L=3, V=29, beam=16)          # the cfg2 shape every utterance of cfg5 has
+UTTS, WAVE, LANES = 8192, 1024, 2                            # BASELINE.json configs[4]; utterances per batch; batches in flight
 SEED_X, SEED_W, SEED_FC = 1234, 4321, 99
 FRAME_SEC = 0.010
+WORKLOAD = ("cfg5: 8192 utt x T=1000 x D=161 sharded over the GPUs, 3-layer tanh RNN H=512, Linear 512->29 + log-softmax, "
+            "CTC beam 16")
 
 
 def measured_peaks():
@@ -54,23 +62,19 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def workload(rank):
+def weights():
     import synth
     c = CFG
-    x = synth.spectrogram_batch(SEED_X, c["T"], c["N"], c["D"], first_utt=rank * c["N"])
-    w = synth.rnn_weights(SEED_W, c["D"], c["H"], c["L"])
-    fc = synth.fc_weights(SEED_FC, c["H"], c["V"])
-    return x, w, fc
+    return synth.rnn_weights(SEED_W, c["D"], c["H"], c["L"]), synth.fc_weights(SEED_FC, c["H"], c["V"])
 
 
-def cpu_port_rtfx(n_utt, cores):
-    """The oracle port (CPU restatement of the reference path) over n_utt utterances of the cfg2 workload."""
+def cpu_port_rtfx(n_utt, cores, first_utt=0):
+    """The oracle port (CPU restatement of the reference path) over n_utt utterances of the workload."""
     import synth
     from oracle import oracle as O   # bench.py's cpu_baseline / reference leg: the one place it may run
     c = CFG
-    x = synth.spectrogram_batch(SEED_X, c["T"], n_utt, c["D"])
-    w = synth.rnn_weights(SEED_W, c["D"], c["H"], c["L"])
-    fc_w, fc_b = synth.fc_weights(SEED_FC, c["H"], c["V"])
+    x = synth.spectrogram_batch(SEED_X, c["T"], n_utt, c["D"], first_utt=first_utt)
+    w, (fc_w, fc_b) = weights()
     t0 = time.perf_counter()
     h = O.rnn_forward(x, c["T"], n_utt, *w, nthreads=cores)[-1]
     logp = O.linear(h, fc_w, fc_b, act="logsoftmax")
@@ -136,13 +140,12 @@ def run_reference(args, rank, world):
         t_total += dt
         audio += n_utt * c["T"] * FRAME_SEC
     value = audio / t_total
-    sample = f"{n_utt} utterances x T={c['T']} of cfg2 per step (of 64), {cores} host threads"
+    sample = f"{n_utt} utterances x T={c['T']} per step (of the {args.utts}), {cores} host threads, RTFx-normalised"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2: 64 utt x T=1000 x D=161, 3-layer tanh RNN H=512, Linear 512->29 + log-softmax, "
-                               "CTC beam 16", "sample": sample},
+        "config": {"workload": WORKLOAD, "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -150,13 +153,43 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def oracle_check(gasr, job, x_dev0, res0, n_check):
+    """The benched computation against the CPU oracle: utterances 0 .. n_check-1 of batch 0.  Log-probabilities within 1e-4
+    of the oracle's forward pass; transcripts and fp32 scores of the GPU decoder bit-exact against the oracle decoder run on
+    the GPU's own log-probabilities (the decoder contract, tests/test_gpu_parity.py)."""
+    import synth
+    from oracle import oracle as O   # checker only
+    c = CFG
+    paths, lens, scores = job.run_device([x_dev0])            # one batch -> lane 0
+    assert (paths == res0[0]).all() and (lens == res0[1]).all() and (scores.view(np.uint32) == res0[2].view(np.uint32)).all(), \
+        "batch 0 decoded alone differs from batch 0 inside the job"
+    logp = job.lane_logprobs(0).reshape(c["T"], args_wave(job), c["V"])[:, :n_check, :]
+    w, (fc_w, fc_b) = weights()
+    x = synth.spectrogram_batch(SEED_X, c["T"], n_check, c["D"], first_utt=0)
+    ref = O.linear(O.rnn_forward(x, c["T"], n_check, *w, nthreads=host_cores())[-1], fc_w, fc_b, act="logsoftmax")
+    err = float(np.abs(logp.reshape(-1, c["V"]) - ref).max())
+    op, os_ = O.ctc_decode(np.ascontiguousarray(logp), synth.VOCAB29, 0, c["beam"], domain="log", nthreads=host_cores())
+    gp, gs = gasr.unpack_results(paths[:n_check], lens[:n_check], scores[:n_check], job.cfg.max_len)
+    same = gp == op and all(np.float32(a).view(np.uint32) == np.float32(b).view(np.uint32) for a, b in zip(gs, os_))
+    return {"utterances": n_check, "frames": c["T"], "logprob_max_abs_err": err, "logprob_tol": 1e-4,
+            "transcripts_and_scores_bit_exact": bool(same), "ok": bool(err < 1e-4 and same)}
+
+
+def args_wave(job):
+    return job.cfg.N
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--utts", type=int, default=UTTS)
+    ap.add_argument("--wave", type=int, default=WAVE)
+    ap.add_argument("--lanes", type=int, default=LANES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-checks", action="store_true", help="skip the oracle / gather checks (timing only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -169,27 +202,42 @@ def main():
         return
 
     import gasr   # raises ImportError if libgasr.so is missing: no CPU fallback
-    dist = None
+    import shard
+    import synth
+    dist, host_group = None, None
     if world > 1:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        host_group = dist.new_group(backend="gloo")           # host-side gather of the results (no data-path collective)
 
     c = CFG
-    x, w, (fc_w, fc_b) = workload(rank)
-    import synth
-    ctx = gasr.Context(local)
-    pipe = gasr.AsrPipeline(ctx, gasr.CELL_TANH, False, c["T"], c["N"], c["D"], c["H"], c["L"], c["V"], c["beam"], 0,
-                            synth.VOCAB29)
-    pipe.set_weights(*w, fc_w, fc_b)
-    x_pinned = ctx.pinned(x.shape)
-    x_pinned[...] = x
-    x_dev = ctx.to_device(x)
-    audio_per_step = c["N"] * c["T"] * FRAME_SEC
+    assert args.utts % args.wave == 0, "--utts must be a multiple of --wave"
+    n_batches = args.utts // args.wave
+    b_lo, b_hi = shard.shard_range(n_batches, world, rank)    # contiguous batches of this rank
+    job = gasr.Job(local, c["T"], args.wave, c["D"], c["H"], c["L"], c["V"], c["beam"], 0, synth.VOCAB29, lanes=args.lanes)
+    w, (fc_w, fc_b) = weights()
+    job.set_weights(*w, fc_w, fc_b)
+    ctx0 = job.lane_context(0)
+    batch_bytes = c["T"] * args.wave * c["D"] * 4
+
+    def make_batch(b):
+        d = ctx0.malloc(batch_bytes)
+        ctx0.synth_spectrogram(d, SEED_X, c["T"], args.wave, c["D"], first_utt=b * args.wave)
+        return d
+
+    x_dev = [make_batch(b) for b in range(b_lo, b_hi)]
+    x_pin = []
+    for d in x_dev:
+        h = ctx0.pinned((c["T"] * args.wave, c["D"]))
+        ctx0.d2h_into(h, d)
+        x_pin.append(h)
+    ctx0.sync()
+    audio_per_step = args.utts * c["T"] * FRAME_SEC
 
     def barrier():
-        ctx.sync()
+        ctx0.sync()
         if dist is not None:
             import torch
             torch.cuda.synchronize()
@@ -197,10 +245,10 @@ def main():
 
     def timed(fn, steps):
         barrier()
-        ctx.timer_start()
+        ctx0.timer_start()
         for _ in range(steps):
             fn()
-        ms = ctx.timer_stop()
+        ms = ctx0.timer_stop()
         barrier()
         if dist is not None:
             import torch
@@ -209,111 +257,130 @@ def main():
             ms = float(t.item())
         return ms
 
+    ref = None
     for _ in range(args.warmup):
-        ref = pipe.run_device(x_dev)
-        pipe.run_host(x_pinned)
+        ref = job.run_device(x_dev)
+        job.run_host(x_pin)
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = ctx.launch_count()
-    stage_acc = np.zeros(4)
-
-    def step_dev():
-        pipe.run_device(x_dev)
-        stage_acc[:] += pipe.stage_times()
-
-    ms_dev = timed(step_dev, args.steps)
-    launches = ctx.launch_count() - launches0
-    ms_e2e = timed(lambda: pipe.run_host(x_pinned), args.steps)
+    launches0 = job.launch_count()
+    ms_dev = timed(lambda: job.run_device(x_dev), args.steps)
+    launches = job.launch_count() - launches0
+    ms_e2e = timed(lambda: job.run_host(x_pin), args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    last = pipe.run_device(x_dev)
-    assert last == ref, "results changed between runs"
+    last = job.run_device(x_dev)
+    assert all((a == b).all() for a, b in zip(last[:2], ref[:2])) and (last[2].view(np.uint32) == ref[2].view(np.uint32)).all(), \
+        "results changed between runs"
+
+    # per-stage launch durations inside the running pipeline (profiled pass, outside the timed loops)
+    job.profile(True)
+    job.run_device(x_dev)
+    stage_ms, stage_launches = job.stage_times()
+    job.profile(False)
+
+    # ---- gather (host side) and checks ------------------------------------------------------------------------------------
+    gathered = None
+    if dist is not None:
+        bucket = [None] * world if rank == 0 else None
+        dist.gather_object((last[0], last[1], last[2]), bucket, dst=0, group=host_group)
+        if rank == 0:
+            gathered = tuple(np.concatenate([b[i] for b in bucket]) for i in range(3))   # rank order == utterance order
+    else:
+        gathered = last
 
     if rank == 0:
+        checks = {}
+        if not args.no_checks:
+            checks["parity_checked"] = oracle_check(gasr, job, x_dev[0], tuple(a[: args.wave] for a in last), 4)
+            if world > 1:
+                # the same 8192 utterances decoded by this GPU alone must equal the gathered N-GPU result bit for bit
+                extra = [make_batch(b) for b in range(b_hi, n_batches)]
+                alone = job.run_device(x_dev + extra)
+                for d in extra:
+                    ctx0.free(d)
+                eq = bool((alone[0] == gathered[0]).all() and (alone[1] == gathered[1]).all()
+                          and (alone[2].view(np.uint32) == gathered[2].view(np.uint32)).all())
+                checks["gather"] = {"utterances": int(gathered[1].shape[0]), "ranks": world,
+                                    "equals_single_gpu_result_bit_for_bit": eq}
+            else:
+                checks["gather"] = {"utterances": int(gathered[1].shape[0]), "ranks": 1, "equals_single_gpu_result_bit_for_bit": True,
+                                    "note": "single rank: the result IS the single-GPU result"}
         hbm_peak, tc_peak, peak_kind = measured_peaks()
-        stage_ms = stage_acc / args.steps                      # proj, recurrence, linear, decode (per step)
-        rows = c["T"] * c["N"]
-        rec_bytes = rows * c["H"] * 4 * 2                      # per layer: read xproj (fp32) + write h (4 B/element)
-        launches_per_stage, chunk_frames = pipe.stage_launches()
-        streaming = chunk_frames < 0
-        n_rec = max(launches_per_stage[1], 1)
-        rec_bytes = rec_bytes * c["L"] // n_rec                # algorithmic bytes of ONE launch
+        local_rows = (b_hi - b_lo) * args.wave * c["T"]        # frame-utterances this rank processes per step
+        n_rec = max(stage_launches[1], 1)
+        rec_bytes_total = local_rows * c["H"] * 4 * 2 * c["L"]  # per layer: read xproj (fp32) + write h (4 B/element), SURVEY.md 8d
         rec_ms_per_launch = stage_ms[1] / n_rec
-        achieved = rec_bytes / (rec_ms_per_launch * 1e-3) / 1e9
-        if streaming:
-            rec_kernel = ("rnn_stream_kernel<512> (persistent recurrence of all 3 layers, ONE launch per step; its duration "
-                          "includes waiting for the projection GEMM that runs concurrently)")
-            mode = {"mode": "streaming", "note": "three persistent kernels (recurrence of all layers / tcgen05 projection + "
-                    "output-layer GEMM / decoder) run concurrently for the whole sequence and hand 128-row blocks to each "
-                    "other through counters in HBM; stage times are whole-kernel durations and overlap; Linear + "
-                    "log-softmax is a target of the GEMM kernel", "launches_per_stage": launches_per_stage}
-        else:
-            rec_kernel = "rnn_tanh_mma_kernel (recurrence, one launch per layer and time chunk)"
-            mode = {"mode": "chunked" if chunk_frames > 0 else "sequential", "chunk_frames": chunk_frames,
-                    "launches_per_stage": launches_per_stage,
-                    "note": "chunk_frames > 0: stages overlap on separate streams; stage times are sums of per-launch "
-                            "durations and may exceed ms_per_step"}
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "rnn_stream_traffic.json")
-        if streaming and os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")   # ncu --set full capture of the same kernel and shape
-        proj_flop = 2.0 * rows * (c["D"] * c["H"] + (c["L"] - 1) * c["H"] * c["H"])
-        if streaming:
-            proj_flop += 2.0 * rows * c["H"] * c["V"]          # the output layer is a target of the same GEMM kernel
-        lin_bytes = rows * (c["H"] * 4 + c["V"] * 4)
-        dec_bytes = rows * c["V"] * 4
-        value = world * audio_per_step * args.steps / (ms_dev * 1e-3)
-        e2e = world * audio_per_step * args.steps / (ms_e2e * 1e-3)
+        achieved = rec_bytes_total / n_rec / (rec_ms_per_launch * 1e-3) / 1e9
+        proj_flop = 2.0 * local_rows * (c["D"] * c["H"] + (c["L"] - 1) * c["H"] * c["H"])
+        lin_bytes = local_rows * (c["H"] * 4 + c["V"] * 4)
+        dec_bytes = local_rows * c["V"] * 4
+        value = audio_per_step * args.steps / (ms_dev * 1e-3)
+        e2e = audio_per_step * args.steps / (ms_e2e * 1e-3)
+        step_ms = ms_dev / args.steps
+        whole = local_rows * 25452 / (step_ms * 1e-3) / 1e9   # 25 452 compulsory bytes per frame and utterance
+
+        def rl(bound, work, ms, peak, unit, scale):
+            if ms <= 0:
+                return None
+            a = work / (ms * 1e-3) / scale
+            return {"bound": bound, "achieved": a, "peak": peak, "unit": unit, "frac": a / peak, "ms_sum_of_launches": ms}
+
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg2: 64 utt x T=1000 x D=161, 3-layer tanh RNN H=512, Linear 512->29 + "
-                                   "log-softmax, CTC beam 16 (per GPU)",
-                       "l2": "per-step working set ~0.57 GB (x, xproj, 3 hidden sequences) exceeds the 126 MB L2",
-                       "init": "weights U(+-1/sqrt(H)) seed 4321, inputs U[0,1) seed 1234 (splitmix64)"},
+            "config": {"workload": WORKLOAD, "utterances": args.utts, "utterances_per_batch": args.wave,
+                       "batches_in_flight_per_gpu": args.lanes, "batches_per_gpu": b_hi - b_lo,
+                       "l2": "per-batch working set ~16 GB (x, xproj, hidden planes of 1024 utterances x 1000 frames) exceeds the "
+                             "126 MB L2 many times over",
+                       "init": "weights U(+-1/sqrt(H)) seed 4321, inputs U[0,1) seed 1234 (splitmix64, generated on the device, "
+                               "bit-identical to synth.py)"},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(x.nbytes), "d2h_bytes_per_step": int(c["N"] * (c["T"] + 1 + 8))},
+                    "h2d_bytes_per_step": int(args.utts * c["T"] * c["D"] * 4),
+                    "d2h_bytes_per_step": int(args.utts * (c["T"] + 1 + 8))},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": rec_kernel, "bound": "hbm",
-                         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": traffic, "peak_source": peak_kind,
-                         "algorithmic_bytes_per_launch": rec_bytes, "ms_per_launch": rec_ms_per_launch,
+            "roofline": {"kernel": "rnn_wide_kernel (tcgen05 recurrence, one launch per layer and 50-frame chunk of a batch; "
+                                   "durations measured inside the running pipeline, where it shares the GPU with the GEMM and decoder kernels)",
+                         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "peak_source": peak_kind,
+                         "algorithmic_bytes_per_launch": rec_bytes_total / n_rec, "ms_per_launch": rec_ms_per_launch,
                          "launches_per_step": n_rec},
-            "decode_prune": dict(zip(("fallback_utt_frames", "survivors_total"), ctx.ctc_last_stats())),
-            "pipeline": mode,
-            "stages_ms_per_step": {"projection_gemm": stage_ms[0], "recurrence": stage_ms[1],
-                                   "linear_logsoftmax": stage_ms[2], "ctc_decode": stage_ms[3]},
+            "whole_path_hbm": {"achieved": whole, "peak": hbm_peak, "unit": "GB/s", "frac": whole / hbm_peak,
+                               "note": "25 452 compulsory bytes per frame and utterance (SURVEY.md 8d) over the whole step"},
+            "pipeline": {"mode": "wave", "chunk_frames": 50, "launches_per_stage_per_step": stage_launches,
+                         "note": "stages overlap on separate streams; stage times are sums of per-launch durations (profiled pass) "
+                                 "and exceed ms_per_step"},
+            "stages_ms_sum_of_launches": {"projection_gemm": stage_ms[0], "recurrence": stage_ms[1],
+                                          "linear_logsoftmax": stage_ms[2], "ctc_decode": stage_ms[3]},
             "stage_rooflines": {
-                "projection_gemm": {"bound": "tensor", "achieved": proj_flop / (stage_ms[0] * 1e-3) / 1e12,
-                                    "peak": tc_peak, "unit": "TFLOP/s",
-                                    "frac": proj_flop / (stage_ms[0] * 1e-3) / 1e12 / tc_peak},
-                "linear_logsoftmax": (None if stage_ms[2] <= 0 else
-                                      {"bound": "hbm", "achieved": lin_bytes / (stage_ms[2] * 1e-3) / 1e9,
-                                       "peak": hbm_peak, "unit": "GB/s",
-                                       "frac": lin_bytes / (stage_ms[2] * 1e-3) / 1e9 / hbm_peak}),
-                "ctc_decode": {"bound": "hbm", "achieved": dec_bytes / (stage_ms[3] * 1e-3) / 1e9, "peak": hbm_peak,
-                               "unit": "GB/s", "frac": dec_bytes / (stage_ms[3] * 1e-3) / 1e9 / hbm_peak},
+                "projection_gemm": rl("tensor", proj_flop, stage_ms[0], tc_peak, "TFLOP/s", 1e12),
+                "linear_logsoftmax": rl("hbm", lin_bytes, stage_ms[2], hbm_peak, "GB/s", 1e9),
+                "ctc_decode": rl("hbm", dec_bytes, stage_ms[3], hbm_peak, "GB/s", 1e9),
             },
         }
+        line.update(checks)
         if world == 1 and not args.no_cpu_baseline:
-            # bounded sample: whole cfg2 batches (64 utterances) on all host threads until ~10 s of CPU work are spent
+            # bounded sample: batches of 64 utterances on all host threads until ~10 s of CPU work are spent
             cores = host_cores()
-            n_utt, total_s, reps = c["N"], 0.0, 0
+            n_utt, total_s, reps = 64, 0.0, 0
             while total_s < 10.0 and reps < 12:
-                _, dt = cpu_port_rtfx(n_utt, cores)
+                _, dt = cpu_port_rtfx(n_utt, cores, first_utt=reps * n_utt)
                 total_s += dt
                 reps += 1
             v = reps * n_utt * c["T"] * FRAME_SEC / total_s
+            v1, _ = cpu_port_rtfx(2, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "seconds": total_s,
-                                    "sample": f"{reps} x the full cfg2 batch ({n_utt} utterances x T={c['T']}), "
-                                              f"{cores} host threads, oracle port (forward + CTC-REF decode)"}
+                                    "single_thread_value": v1,
+                                    "sample": f"{reps} x 64 utterances x T={c['T']} of the {args.utts}, {cores} host threads, "
+                                              f"oracle port (forward + CTC-REF decode); single thread: 2 utterances"}
         print(json.dumps(line), flush=True)
 
-    pipe.close()
-    ctx.close()
+    for d in x_dev:
+        ctx0.free(d)
+    job.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -12,8 +12,9 @@
 //   * h_{t-1} of the group -- [128 x H] as bf16 hi/lo planes, exactly the array this kernel writes for the next layer's
 //     projection GEMM -- is the A operand.  It is pulled through a 2-stage ring by TMA ([128 x 64] boxes); with multicast the
 //     H/64 CTAs of the cluster each issue 1/(H/64) of the boxes and every box lands in all of them;
-//   * D[128 utterances x 64 columns] accumulates in TMEM (fp32); three MMA terms (hi*hi + hi*lo + lo*hi) give an fp32-grade
-//     product (same split as xproj_gemm_tc.cu);
+//   * D accumulates in TMEM (fp32); the three terms hi*hi + hi*lo + lo*hi of the fp32-grade split (xproj_gemm_tc.cu) are two
+//     instructions per K step: h_hi * [W_hi | W_lo] (N = 128) and h_lo * W_hi (N = 64) -- operand reads from shared memory,
+//     not the tensor pipe, pace MMAs this narrow, so the A tile is read twice instead of three times;
 //   * eight epilogue warps (thread = utterance row of the accumulator, 32 columns each) add xp, apply tanh, split h_t into
 //     its bf16 hi/lo planes and store them (plus, optionally, the fp32 row the C ABI returns), then release the step to the
 //     TMA producers of ALL CTAs of the cluster with one remote mbarrier arrive per warp -- no cluster-wide barrier;
@@ -167,7 +168,7 @@ rnn_wide_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)), "n"(128) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)), "n"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -220,15 +221,16 @@ rnn_wide_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_const
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            // instruction descriptor: D = f32, A = B = bf16, both K-major, N = 64, M = 128
-            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(RW_COLS >> 3) << 17) | ((uint32_t)(RW_U >> 4) << 24);
+            // instruction descriptors: D = f32, A = B = bf16, both K-major, M = 128; N = 128 ([W_hi ; W_lo] rows) and N = 64
+            constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(2 * RW_COLS >> 3) << 17) | ((uint32_t)(RW_U >> 4) << 24);
+            constexpr uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(RW_COLS >> 3) << 17) | ((uint32_t)(RW_U >> 4) << 24);
             rw_wait(wfull, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             int it = 0;
             for (int t = p.s0; t < p.s1; t++) {
                 if (t == 0) continue;
                 for (int g = 0; g < ng; g++) {
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(g * RW_COLS);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(g * 2 * RW_COLS);
                     for (int kb = 0; kb < p.KB; kb++, it++) {
                         const int s = it % RW_STAGES;
                         rw_wait(full0 + 8 * s, (uint32_t)(it / RW_STAGES) & 1u);
@@ -237,14 +239,16 @@ rnn_wide_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_const
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t st = ring + (uint32_t)s * RW_STAGE_BYTES;
                         const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + RW_A_TILE);
-                        const uint64_t b_hi = umma_desc_sw128(w_smem + (uint32_t)(2 * kb) * RW_W_TILE);
-                        const uint64_t b_lo = umma_desc_sw128(w_smem + (uint32_t)(2 * kb + 1) * RW_W_TILE);
+                        // The hi and lo tiles of a k-block are adjacent: together they are ONE [128 x 64] B tile [W_hi ; W_lo].
+                        // h_hi * [W_hi | W_lo] is a single N = 128 instruction (columns 0-63: hi*hi, 64-127: hi*lo, summed in
+                        // the epilogue) and h_lo * W_hi accumulates onto columns 0-63: the A tile is read twice instead of
+                        // three times -- with N = 64 the operand reads from shared memory, not the tensor pipe, set the pace.
+                        const uint64_t b_hl = umma_desc_sw128(w_smem + (uint32_t)(2 * kb) * RW_W_TILE);
 #pragma unroll
                         for (int k4 = 0; k4 < TC_BK / 16; k4++) {
                             const uint64_t adv = (uint64_t)(k4 * 32 >> 4);   // 16 bf16 = 32 bytes along K inside the swizzle atom
-                            umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb | k4) != 0);
-                            umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
-                            umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1);
+                            umma_bf16(d_tmem, a_hi + adv, b_hl + adv, idesc2, (kb | k4) != 0);
+                            umma_bf16(d_tmem, a_lo + adv, b_hl + adv, idesc1, 1);
                         }
                         if (MC) rw_commit_mc(empty0 + 8 * s, mc_mask);       // the stage is free once EVERY CTA's MMAs have read it
                         else umma_commit(empty0 + 8 * s);
@@ -285,8 +289,12 @@ rnn_wide_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_const
                     rw_wait(accf0 + 8 * g, (uint32_t)(t - t_first) & 1u);
                     if (stamp) RW_STAMP(7);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    rw_tmem_ld32(v, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * RW_COLS + half * 32));
+                    uint32_t v2[32];
+                    rw_tmem_ld32(v, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 2 * RW_COLS + half * 32));
+                    rw_tmem_ld32(v2, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 2 * RW_COLS + RW_COLS + half * 32));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // the next step's MMAs overwrite the accumulator
                 } else {
 #pragma unroll
@@ -314,12 +322,12 @@ rnn_wide_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_const
                 // bf16 hi / lo planes of h_t: the next step's A operand and the next layer's GEMM operand
                 uint32_t ph[16], pl[16];
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const __nv_bfloat16 h0 = __float2bfloat16_rn(h[2 * j]), h1 = __float2bfloat16_rn(h[2 * j + 1]);
-                    const __nv_bfloat16 l0 = __float2bfloat16_rn(h[2 * j] - __bfloat162float(h0));
-                    const __nv_bfloat16 l1 = __float2bfloat16_rn(h[2 * j + 1] - __bfloat162float(h1));
-                    const __nv_bfloat162 th = __halves2bfloat162(h0, h1), tl = __halves2bfloat162(l0, l1);
-                    ph[j] = *reinterpret_cast<const uint32_t *>(&th);
+                for (int j = 0; j < 16; j++) {                               // packed conversions: one cvt.rn.bf16x2.f32 per pair
+                    const __nv_bfloat162 th = __floats2bfloat162_rn(h[2 * j], h[2 * j + 1]);
+                    const uint32_t hb = *reinterpret_cast<const uint32_t *>(&th);
+                    const float f0 = __uint_as_float(hb << 16), f1 = __uint_as_float(hb & 0xffff0000u);
+                    const __nv_bfloat162 tl = __floats2bfloat162_rn(h[2 * j] - f0, h[2 * j + 1] - f1);
+                    ph[j] = hb;
                     pl[j] = *reinterpret_cast<const uint32_t *>(&tl);
                 }
                 // Stores: a thread-per-row store touches 32 cache lines per instruction (the epilogue was bound by exactly that).
@@ -367,7 +375,7 @@ rnn_wide_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_const
     rw_cluster_sync();                       // no CTA leaves while a peer may still arrive on its barriers
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(128) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
     }
 }
 

@@ -56,6 +56,8 @@ EXPORTS = [
     "gasr_rnn_forward", "gasr_ctc_decode", "gasr_ctc_last_stats", "gasr_ctc_decode_host", "gasr_asr_create", "gasr_asr_destroy",
     "gasr_asr_set_weights", "gasr_asr_run_host", "gasr_asr_run_device", "gasr_asr_logprobs", "gasr_asr_stage_times", "gasr_asr_stage_launches",
     "gasr_asr_submit_host", "gasr_asr_submit_device", "gasr_asr_collect", "gasr_asr_profile", "gasr_asr_last_ms",
+    "gasr_job_create", "gasr_job_destroy", "gasr_job_set_weights", "gasr_job_run_host", "gasr_job_run_device", "gasr_job_last_ms",
+    "gasr_job_launch_count", "gasr_job_lane", "gasr_job_profile", "gasr_job_stage_times", "gasr_synth_spectrogram",
 ]
 
 
@@ -86,10 +88,16 @@ class Context:
         _check(_lib.gasr_ctx_create(int(device), ctypes.byref(self._h)))
         self.device = device
 
+    _borrowed = False
+
     def close(self):
-        if self._h:
+        if self._h and not self._borrowed:
             _lib.gasr_ctx_destroy(self._h)
-            self._h = ctypes.c_void_p()
+        self._h = ctypes.c_void_p()
+
+    def synth_spectrogram(self, dptr, seed, T, N, D, first_utt=0):
+        """Fill dptr[T*N, D] on the device with the same values synth.spectrogram_batch produces on the host."""
+        _check(_lib.gasr_synth_spectrogram(self._h, dptr, int(seed), T, N, D, int(first_utt)))
 
     def __del__(self):
         try:
@@ -128,6 +136,10 @@ class Context:
     def h2d_async(self, dptr, arr):
         _check(_lib.gasr_memcpy_h2d_async(self._h, dptr, arr.ctypes.data_as(ctypes.c_void_p),
                                           ctypes.c_size_t(arr.nbytes)))
+
+    def d2h_into(self, arr, dptr):
+        """Blocking device -> host copy into an existing C-contiguous array (e.g. a pinned block)."""
+        _check(_lib.gasr_memcpy_d2h(self._h, arr.ctypes.data_as(ctypes.c_void_p), dptr, ctypes.c_size_t(arr.nbytes)))
 
     def to_host(self, dptr, shape, dtype=np.float32):
         out = np.empty(shape, dtype=dtype)
@@ -490,6 +502,86 @@ class AsrPipeline:
         return list(n), chunk.value
 
 
+class Job:
+    """gasr_job: many batches of cfg.N utterances on one GPU, `lanes` of them in flight (BASELINE.json cfg5)."""
+
+    def __init__(self, device, T, N, in_, H, L, V, beam, blank, vocab, lanes=2, precision=PREC_FP32, nbest=1, max_len=None):
+        self.cfg = AsrConfig(CELL_TANH, 0, T, N, in_, H, L, V, beam, blank, precision, nbest, T + 1 if max_len is None else max_len)
+        self._h = ctypes.c_void_p()
+        _check(_lib.gasr_job_create(device, ctypes.byref(self.cfg), bytes(vocab), lanes, ctypes.byref(self._h)))
+        self.lanes = lanes
+
+    def close(self):
+        if self._h:
+            _lib.gasr_job_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def set_weights(self, w_ih, w_hh, b_ih, b_hh, fc_w, fc_b):
+        keep = [[_f32(a) for a in lst] for lst in (w_ih, w_hh, b_ih, b_hh)]
+        arrs = [(c_float_p * len(lst))(*[_fp(a) for a in lst]) for lst in keep]
+        fw, fb = _f32(fc_w), _f32(fc_b)
+        _check(_lib.gasr_job_set_weights(self._h, arrs[0], arrs[1], arrs[2], arrs[3], _fp(fw), _fp(fb)))
+
+    def lane_context(self, lane=0):
+        """A borrowed Context view of a lane (allocation / copies on the job's device); do not close it."""
+        c = ctypes.c_void_p()
+        _check(_lib.gasr_job_lane(self._h, lane, ctypes.byref(c), None))
+        ctx = Context.__new__(Context)
+        ctx._h = c
+        ctx._borrowed = True
+        return ctx
+
+    def _run(self, fn, ptrs):
+        n = len(ptrs)
+        per = self.cfg.N * self.cfg.nbest
+        ml = max(self.cfg.max_len, 1)
+        paths = np.zeros((n * per, ml), dtype=np.uint8)
+        lens = np.zeros((n * per,), dtype=np.int32)
+        scores = np.zeros((n * per,), dtype=np.float32)
+        arr = (ctypes.c_void_p * n)(*ptrs)
+        _check(fn(self._h, arr, n, paths.ctypes.data_as(ctypes.c_char_p), lens.ctypes.data_as(c_int_p), _fp(scores)))
+        return paths, lens, scores
+
+    def run_host(self, batches):
+        """batches: list of C-contiguous float32 arrays [T*N, in] (or raw host addresses)."""
+        ptrs = [b if isinstance(b, int) else b.ctypes.data for b in batches]
+        return self._run(_lib.gasr_job_run_host, ptrs)
+
+    def run_device(self, dev_ptrs):
+        ptrs = [p.value if isinstance(p, ctypes.c_void_p) else int(p) for p in dev_ptrs]
+        return self._run(_lib.gasr_job_run_device, ptrs)
+
+    def last_ms(self):
+        ms = ctypes.c_float(0)
+        _check(_lib.gasr_job_last_ms(self._h, ctypes.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = ctypes.c_longlong(0)
+        _check(_lib.gasr_job_launch_count(self._h, ctypes.byref(n)))
+        return n.value
+
+    def profile(self, on=True):
+        _check(_lib.gasr_job_profile(self._h, int(on)))
+
+    def stage_times(self):
+        ms, n = (ctypes.c_float * 4)(), (ctypes.c_int * 4)()
+        _check(_lib.gasr_job_stage_times(self._h, ms, n))
+        return list(ms), list(n)
+
+    def lane_logprobs(self, lane=0):
+        """Log-probabilities [T*N, V] of the last batch that ran on a lane."""
+        c, a = ctypes.c_void_p(), ctypes.c_void_p()
+        _check(_lib.gasr_job_lane(self._h, lane, ctypes.byref(c), ctypes.byref(a)))
+        p, ld = ctypes.c_void_p(), ctypes.c_int(0)
+        _check(_lib.gasr_asr_logprobs(a, ctypes.byref(p), ctypes.byref(ld)))
+        return self.lane_context(lane).to_host(p, (self.cfg.T * self.cfg.N, ld.value))[:, : self.cfg.V]
+
+
+def unpack_results(paths, lens, scores, max_len):
+    return ([bytes(paths[i, : min(int(lens[i]), max_len)]) for i in range(paths.shape[0])], [float(s) for s in scores])
+
+
 def _declare():
     vp, sz, ci, cf = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_float
     L = _lib
@@ -534,6 +626,17 @@ def _declare():
     L.gasr_asr_collect.argtypes = [vp, ctypes.c_char_p, c_int_p, c_float_p]
     L.gasr_asr_profile.argtypes = [vp, ci]
     L.gasr_asr_last_ms.argtypes = [vp, c_float_p]
+    L.gasr_job_create.argtypes = [ci, ctypes.POINTER(AsrConfig), ctypes.c_char_p, ci, c_void_pp]
+    L.gasr_job_destroy.argtypes = [vp]
+    L.gasr_job_set_weights.argtypes = [vp, vp, vp, vp, vp, c_float_p, c_float_p]
+    L.gasr_job_run_host.argtypes = [vp, c_void_pp, ci, ctypes.c_char_p, c_int_p, c_float_p]
+    L.gasr_job_run_device.argtypes = [vp, c_void_pp, ci, ctypes.c_char_p, c_int_p, c_float_p]
+    L.gasr_job_last_ms.argtypes = [vp, c_float_p]
+    L.gasr_job_launch_count.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong)]
+    L.gasr_job_lane.argtypes = [vp, ci, c_void_pp, c_void_pp]
+    L.gasr_job_profile.argtypes = [vp, ci]
+    L.gasr_job_stage_times.argtypes = [vp, c_float_p, c_int_p]
+    L.gasr_synth_spectrogram.argtypes = [vp, vp, ctypes.c_ulonglong, ci, ci, ci, ctypes.c_longlong]
 
 
 _declare()

@@ -179,6 +179,37 @@ int gasr_asr_collect(gasr_asr *asr, char *out_paths, int *out_lens, float *out_s
 int gasr_asr_profile(gasr_asr *asr, int on);
 int gasr_asr_last_ms(gasr_asr *asr, float *ms);
 
+/* ---- jobs: many batches of utterances on one GPU, several in flight (BASELINE.json cfg5) ------------------------------- */
+/*
+ * A job owns `lanes` complete pipelines of cfg->N utterances each; batch b runs on lane b % lanes, so consecutive batches
+ * overlap on the GPU.  x[b] is batch b in the reference's layout (time-major [T*N, in], RNN.cu:17), in host memory (pinned
+ * for the copies to overlap) or device memory; results are written in batch order: out_paths [n_batches*N, nbest, max_len],
+ * out_lens / out_scores [n_batches*N, nbest].  Configurations outside the wave engine are GASR_ERR_UNSUPPORTED.  The
+ * multi-GPU layer gives every process / GPU a contiguous range of batches and gathers the results on the host
+ * (utterances are independent: RNN.cu:15-27, CTCBeamSearch.cu:416 -- no collective on the data path).
+ */
+typedef struct gasr_job gasr_job;
+int gasr_job_create(int device, const gasr_asr_config *cfg, const char *vocab, int lanes, gasr_job **job);
+int gasr_job_destroy(gasr_job *job);
+int gasr_job_set_weights(gasr_job *job, const float *const *w_ih, const float *const *w_hh, const float *const *b_ih,
+                         const float *const *b_hh, const float *fc_w, const float *fc_b);
+int gasr_job_run_host(gasr_job *job, const float *const *x_host, int n_batches, char *out_paths, int *out_lens,
+                      float *out_scores);
+int gasr_job_run_device(gasr_job *job, const float *const *x_dev, int n_batches, char *out_paths, int *out_lens,
+                        float *out_scores);
+int gasr_job_last_ms(gasr_job *job, float *ms);                 /* device time of the last run (CUDA events)            */
+int gasr_job_launch_count(gasr_job *job, long long *launches);  /* kernels launched by all lanes since creation         */
+int gasr_job_lane(gasr_job *job, int lane, gasr_ctx **ctx, gasr_asr **asr);   /* borrowed handles (allocation, log-probs) */
+/* Per-launch stage timing for every lane; stage_times = sums over all batches of the last run (projection, recurrence,
+ * linear + log-softmax, decode) and the launch counts.                                                              */
+int gasr_job_profile(gasr_job *job, int on);
+int gasr_job_stage_times(gasr_job *job, float *ms4, int *n4);
+
+/* ---- synthetic inputs (counter-based RNG reproducible on host and device) --------------------------------- */
+/* x_dev[T*N, D] time-major: element (t, d) of utterance first_utt + n = top 24 bits of
+ * splitmix64((u*T*D + t*D + d) ^ splitmix64(seed)) / 2^24, like the torch.rand input of baseline/main.py:39.            */
+int gasr_synth_spectrogram(gasr_ctx *ctx, float *x_dev, unsigned long long seed, int T, int N, int D, long long first_utt);
+
 #ifdef __cplusplus
 }
 #endif
