@@ -40,7 +40,7 @@ sys.path.insert(0, ROOT)
 METRIC = "RTFx: audio-sec decoded/sec (RNN fwd + CTC beam) at 1/2/4/8 B200"
 UNIT = "audio-seconds per second"
 CFG = dict(T=1000, D=161, H=512, L=3, V=29, beam=16)          # the cfg2 shape every utterance of cfg5 has
-UTTS, WAVE, LANES = 8192, 1024, 2                            # BASELINE.json configs[4]; utterances per batch; batches in flight
+UTTS, WAVE_MAX, LANES = 8192, 2048, 2                        # BASELINE.json configs[4]; largest batch; batches in flight per GPU
 SEED_X, SEED_W, SEED_FC = 1234, 4321, 99
 FRAME_SEC = 0.010
 WORKLOAD = ("cfg5: 8192 utt x T=1000 x D=161 sharded over the GPUs, 3-layer tanh RNN H=512, Linear 512->29 + log-softmax, "
@@ -179,6 +179,96 @@ def args_wave(job):
     return job.cfg.N
 
 
+def other_configs(gasr, device):
+    """The other BASELINE.json configs, each bounded to a few seconds: cfg1 (baseline/config.json hot path), cfg2 (ONE batch of
+    64 utterances: a latency case), cfg3 (bidirectional GRU stack, bf16 projection), cfg4 (decode-only, T = 4000, beam sweep).
+    Parity at these sizes is enforced by tests/test_gpu_sizes.py; here cfg1 and cfg4 are re-checked live (oracle / golden)."""
+    import synth
+    from oracle import oracle as O   # checker only
+    out = {}
+    ctx = gasr.Context(device)
+
+    def time_pipe(pipe, xd, reps):
+        pipe.run_device(xd)
+        best = 1e30
+        for _ in range(reps):
+            ctx.sync(); ctx.timer_start()
+            res = pipe.run_device(xd)
+            best = min(best, ctx.timer_stop())
+        return best, res
+
+    # cfg1: T=200, N=1, 2048 -> tanh RNN 2048 -> Linear 47 + log-softmax, beam 100 (> V)
+    T, N, D, H, L, V, beam = 200, 1, 2048, 2048, 1, 47, 100
+    vocab = bytes(range(1, V + 1))
+    x = synth.spectrogram_batch(101, T, N, D)
+    w = synth.rnn_weights(102, D, H, L)
+    fc = synth.fc_weights(103, H, V)
+    pipe = gasr.AsrPipeline(ctx, gasr.CELL_TANH, False, T, N, D, H, L, V, beam, 0, vocab)
+    pipe.set_weights(*w, *fc)
+    xd = ctx.to_device(x)
+    ms, (paths, scores) = time_pipe(pipe, xd, 3)
+    logp = pipe.logprobs()
+    ref = O.linear(O.rnn_forward(x, T, N, *w, nthreads=host_cores())[-1], *fc, act="logsoftmax")
+    op, os_ = O.ctc_decode(logp.reshape(T, N, V), vocab, 0, beam, domain="log")
+    out["cfg1"] = {"shape": "T=200 N=1 in=2048 H=2048 V=47 beam=100", "ms": ms, "rtfx": N * T * FRAME_SEC / (ms * 1e-3),
+                   "stages_ms": pipe.stage_times(),
+                   "parity": {"logprob_max_abs_err": float(np.abs(logp - ref).max()),
+                              "decode_bit_exact": bool(paths == op and np.float32(scores[0]).view(np.uint32) == np.float32(os_[0]).view(np.uint32))}}
+    pipe.close(); ctx.free(xd)
+
+    # cfg2: one batch of 64 utterances (what round 1 benched): latency of a single small batch through the wave engine
+    c = CFG
+    x = synth.spectrogram_batch(SEED_X, c["T"], 64, c["D"])
+    w, fc = weights()
+    pipe = gasr.AsrPipeline(ctx, gasr.CELL_TANH, False, c["T"], 64, c["D"], c["H"], c["L"], c["V"], c["beam"], 0, synth.VOCAB29)
+    pipe.set_weights(*w, *fc)
+    xd = ctx.to_device(x)
+    ms, _ = time_pipe(pipe, xd, 5)
+    out["cfg2_single_batch"] = {"shape": "T=1000 N=64 D=161 H=512 L=3 V=29 beam=16", "ms": ms, "rtfx": 64 * c["T"] * FRAME_SEC / (ms * 1e-3),
+                                "parity": "tests/test_gpu_sizes.py::test_cfg2_full_size_pipeline_vs_oracle (whole batch vs oracle)"}
+    pipe.close(); ctx.free(xd)
+
+    # cfg3: 5-layer bidirectional GRU H=800, N=256, T=1000, beam 32, bf16 projection
+    T, N, D, H, L, V, beam = 1000, 256, 161, 800, 5, 29, 32
+    w = synth.rnn_weights(2, D, H, L, cell_gates=3, bidir=True)
+    fc = synth.fc_weights(3, 2 * H, V)
+    pipe = gasr.AsrPipeline(ctx, gasr.CELL_GRU, True, T, N, D, H, L, V, beam, 0, synth.VOCAB29, precision=gasr.PREC_BF16)
+    pipe.set_weights(*w, *fc)
+    xd = ctx.malloc(T * N * D * 4)
+    ctx.synth_spectrogram(xd, 1, T, N, D)
+    ms, _ = time_pipe(pipe, xd, 1)
+    out["cfg3"] = {"shape": "5-layer bidirectional GRU H=800, N=256, T=1000, beam 32, bf16 projection", "ms": ms,
+                   "rtfx": N * T * FRAME_SEC / (ms * 1e-3), "stages_ms": pipe.stage_times(),
+                   "recurrence_hbm_frac": (N * T * 128000 / (max(pipe.stage_times()[1], 1e-9) * 1e-3) / 1e9) / measured_peaks()[0],
+                   "parity": "tests/test_gpu_sizes.py::test_cfg3_gru_at_batch_256 (layer outputs vs oracle at N=256), "
+                             "test_gpu_parity.py::test_pipeline_cfg3_style_gru_bf16_projection (2e-2 + unchanged transcripts)"}
+    pipe.close(); ctx.free(xd)
+
+    # cfg4: decode only, T=4000, N=64, beam 8 / 32 / 128 (random-init-like log-probs); one utterance re-checked against the golden
+    T, N, V = 4000, 64, 29
+    lp = synth.random_logprobs(1, T, N, V)
+    d = ctx.to_device(lp)
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "ctc_cfg4.json")))
+    g_lp = synth.random_logprobs(77, T, 1, V)
+    cfg4 = {}
+    for beam in (8, 32, 128):
+        best = 1e30
+        for _ in range(2):
+            ctx.sync(); ctx.timer_start()
+            ctx.ctc_decode(d, gasr.DOMAIN_LOG, T, N, V, V, beam, 0, synth.VOCAB29)
+            best = min(best, ctx.timer_stop())
+        gp, gs = ctx.ctc_decode_host(g_lp, gasr.DOMAIN_LOG, beam, 0, synth.VOCAB29)
+        case = [k for k in gold["cases"] if k["kind"] == "random" and k["beam"] == beam][0]
+        cfg4[f"beam{beam}"] = {"ms": best, "us_per_frame": 1e3 * best / T, "rtfx": N * T * FRAME_SEC / (best * 1e-3),
+                               "hbm_frac": (N * T * 116 / (best * 1e-3) / 1e9) / measured_peaks()[0],
+                               "golden_bit_exact": bool(gp[0].hex() == case["path_hex"] and
+                                                        int(np.float32(gs[0]).view(np.uint32)) == case["score_bits"])}
+    out["cfg4"] = {"shape": "decode only, T=4000 N=64 V=29", **cfg4}
+    ctx.free(d)
+    ctx.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -186,7 +276,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--utts", type=int, default=UTTS)
-    ap.add_argument("--wave", type=int, default=WAVE)
+    ap.add_argument("--wave", type=int, default=0, help="utterances per batch (0: min(2048, this rank's share))")
     ap.add_argument("--lanes", type=int, default=LANES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-checks", action="store_true", help="skip the oracle / gather checks (timing only)")
@@ -213,9 +303,17 @@ def main():
         host_group = dist.new_group(backend="gloo")           # host-side gather of the results (no data-path collective)
 
     c = CFG
-    assert args.utts % args.wave == 0, "--utts must be a multiple of --wave"
+    # Contiguous shard of utterances per rank, cut into batches of `wave` utterances.  Rows of a batch never interact
+    # (RNN.cu:15-27, CTCBeamSearch.cu:416), so every utterance's result is independent of the batch it travels in: ranks may
+    # use different batch sizes and the gathered result still equals the single-GPU one bit for bit (checked below).
+    assert args.utts % world == 0, "--utts must be a multiple of the number of ranks"
+    share = args.utts // world
+    if args.wave <= 0:
+        args.wave = min(WAVE_MAX, share)
+    assert share % args.wave == 0, "this rank's share must be a multiple of --wave"
     n_batches = args.utts // args.wave
-    b_lo, b_hi = shard.shard_range(n_batches, world, rank)    # contiguous batches of this rank
+    u_lo, u_hi = shard.shard_range(args.utts, world, rank)    # contiguous utterances of this rank
+    b_lo, b_hi = u_lo // args.wave, u_hi // args.wave
     job = gasr.Job(local, c["T"], args.wave, c["D"], c["H"], c["L"], c["V"], c["beam"], 0, synth.VOCAB29, lanes=args.lanes)
     w, (fc_w, fc_b) = weights()
     job.set_weights(*w, fc_w, fc_b)
@@ -333,8 +431,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "utterances": args.utts, "utterances_per_batch": args.wave,
                        "batches_in_flight_per_gpu": args.lanes, "batches_per_gpu": b_hi - b_lo,
-                       "l2": "per-batch working set ~16 GB (x, xproj, hidden planes of 1024 utterances x 1000 frames) exceeds the "
-                             "126 MB L2 many times over",
+                       "l2": "per-batch working set (x, xproj, hidden planes: ~16 MB per utterance) exceeds the 126 MB L2 many times over",
                        "init": "weights U(+-1/sqrt(H)) seed 4321, inputs U[0,1) seed 1234 (splitmix64, generated on the device, "
                                "bit-identical to synth.py)"},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
@@ -362,6 +459,10 @@ def main():
             },
         }
         line.update(checks)
+        if world == 1 and not args.no_checks:
+            job.close()                                      # free the job's buffers before the other configs allocate theirs
+            job = None
+            line["other_configs"] = other_configs(gasr, local)
         if world == 1 and not args.no_cpu_baseline:
             # bounded sample: batches of 64 utterances on all host threads until ~10 s of CPU work are spent
             cores = host_cores()
@@ -378,9 +479,10 @@ def main():
                                               f"oracle port (forward + CTC-REF decode); single thread: 2 utterances"}
         print(json.dumps(line), flush=True)
 
-    for d in x_dev:
-        ctx0.free(d)
-    job.close()
+    if job is not None:
+        for d in x_dev:
+            ctx0.free(d)
+        job.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -52,7 +52,7 @@ struct WaveState {
     std::vector<int> tag;
     size_t n_timed = 0;
     CtcArgs ca = {};
-    bool pending = false;
+    bool pending = false, serial = false;
     float last_ms = 0.0f;
 };
 
@@ -118,9 +118,17 @@ int wave_create(gasr_asr *a) {
     GASR_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     const int prio_mid = prio_hi < prio_lo ? prio_hi + 1 : prio_lo;
     auto mk = [&](cudaStream_t *s, int prio) { if (st == GASR_OK && cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, prio) != cudaSuccess) st = GASR_ERR_CUDA; };
-    mk(&w->st_in, prio_mid); mk(&w->st_fc, prio_mid); mk(&w->st_dec, prio_lo);
     w->st_g.assign(L, nullptr); w->st_r.assign(L, nullptr);
-    for (int l = 0; l < L; l++) { mk(&w->st_g[l], prio_mid); mk(&w->st_r[l], prio_hi); }
+    if (ctx->opt.wave_serial) {
+        // diagnostic: every stage on ONE stream, nothing overlaps -- the profiled stage sums are then the stages' costs alone
+        mk(&w->st_in, prio_mid);
+        w->st_fc = w->st_dec = w->st_in;
+        for (int l = 0; l < L; l++) w->st_g[l] = w->st_r[l] = w->st_in;
+        w->serial = true;
+    } else {
+        mk(&w->st_in, prio_mid); mk(&w->st_fc, prio_mid); mk(&w->st_dec, prio_lo);
+        for (int l = 0; l < L; l++) { mk(&w->st_g[l], prio_mid); mk(&w->st_r[l], prio_hi); }
+    }
     auto mkev = [&](cudaEvent_t *e, bool timing) {
         if (st == GASR_OK && cudaEventCreateWithFlags(e, timing ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess) st = GASR_ERR_CUDA;
     };
@@ -147,6 +155,7 @@ int wave_create(gasr_asr *a) {
     CtcArgs &ca = w->ca;
     ca.scores = w->logp; ca.domain = GASR_DOMAIN_LOG; ca.T = c.T; ca.N = c.N; ca.V = c.V; ca.ld = 32; ca.beam = c.beam; ca.blank = c.blank;
     ca.vocab_host = a->vocab.data(); ca.max_len = c.max_len; ca.nbest = c.nbest; ca.frame_rows = w->Npad;
+    ca.warps_per_cta = ctx->opt.ctc_warps;
     GASR_TRY(ctc_decode_reserve(ctx, ca));
     GASR_TRY(ctc_decode_upload_vocab(ctx, ca, ctx->stream));
     ca.vocab_resident = true;
@@ -165,9 +174,13 @@ void wave_destroy(gasr_asr *a) {
     for (float *p : w->xp) if (p) gasr_free_device(ctx, p);
     for (void *p : {w->x_planes, w->fc_wbuf, (void *)w->fc_b_pad, (void *)w->bias_all, (void *)w->logp, (void *)w->logp_dense, (void *)w->flags})
         if (p) gasr_free_device(ctx, p);
-    for (cudaStream_t s : {w->st_in, w->st_fc, w->st_dec}) if (s) cudaStreamDestroy(s);
-    for (cudaStream_t s : w->st_g) if (s) cudaStreamDestroy(s);
-    for (cudaStream_t s : w->st_r) if (s) cudaStreamDestroy(s);
+    if (w->serial) {
+        if (w->st_in) cudaStreamDestroy(w->st_in);
+    } else {
+        for (cudaStream_t s : {w->st_in, w->st_fc, w->st_dec}) if (s) cudaStreamDestroy(s);
+        for (cudaStream_t s : w->st_g) if (s) cudaStreamDestroy(s);
+        for (cudaStream_t s : w->st_r) if (s) cudaStreamDestroy(s);
+    }
     for (cudaEvent_t e : w->ev_in) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : w->ev_fc) if (e) cudaEventDestroy(e);
     for (auto &v : w->ev_g) for (cudaEvent_t e : v) if (e) cudaEventDestroy(e);
@@ -201,8 +214,9 @@ int wave_set_weights(gasr_asr *a, const float *fc_w, const float *fc_b) {
         memset(&m, 0, sizeof(m));
         GASR_TRY(tc_make_map(&m.m[0], ab, (int)w->rows_p, Kp, TC_BM));
         GASR_TRY(tc_make_map(&m.m[1], ab + a_half, (int)w->rows_p, Kp, TC_BM));
-        GASR_TRY(tc_make_map(&m.m[2], wb, H, Kp, TC_BN));
-        GASR_TRY(tc_make_map(&m.m[3], wb + xproj_tc_w_bytes(K, H) / 2, H, Kp, TC_BN));
+        const int bn = (ctx->opt.gemm_bn == 256 && H % 256 == 0) ? 256 : TC_BN;
+        GASR_TRY(tc_make_map(&m.m[2], wb, H, Kp, bn));
+        GASR_TRY(tc_make_map(&m.m[3], wb + xproj_tc_w_bytes(K, H) / 2, H, Kp, bn));
     }
     {
         // output layer as a 32-column target: W_fc padded to [H, 32] -> W^T hi/lo planes; bias padded with zeros
@@ -234,13 +248,16 @@ static int wave_gemm(gasr_asr *a, int target, int row0, int rows, cudaStream_t s
     const int L = c.L, H = c.H;
     XsParams p = {};
     p.M = rows; p.row0 = row0; p.n_blocks = ceil_div(rows, TC_BM); p.n_targets = 1;
+    p.stages = ctx->opt.gemm_stages;
     p.abort = w->flags + 2 * (size_t)w->max_blocks; p.error = nullptr;
     XsTarget &t = p.target[0];
     t.src_done = w->flags; t.src_need = 1; t.dst_ready = w->flags + w->max_blocks;
     t.cta0 = 0;
     if (target < L) {
         const int K = target == 0 ? c.in : H;
-        t.kind = XS_KIND_XPROJ; t.n_tiles = H / TC_BN; t.bn = TC_BN; t.V = 0;
+        const int bn = (ctx->opt.gemm_bn == 256 && H % 256 == 0) ? 256 : TC_BN;   // 256-column tiles: the A block is read once per 256 outputs
+        p.wide = bn == 256;
+        t.kind = XS_KIND_XPROJ; t.n_tiles = H / bn; t.bn = bn; t.V = 0;
         t.kblocks = ceil_div(K, TC_BK); t.terms = c.precision == GASR_PREC_BF16 ? 1 : 3;
         t.C = w->xp[target] + (size_t)row0 * H; t.ldc = H; t.bias = w->bias_all + (size_t)target * H;
     } else {

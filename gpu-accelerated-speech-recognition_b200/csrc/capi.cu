@@ -119,6 +119,8 @@ int gasr_ctx_create(int device, gasr_ctx **out) {
         o.bidir_serial = getenv("GASR_BIDIR_SERIAL") != nullptr; o.linear_simt = getenv("GASR_LINEAR_SIMT") != nullptr;
         o.xproj = chr("GASR_XPROJ"); o.chunk = num("GASR_CHUNK", -1); o.stream = num("GASR_STREAM", -1); o.wave = num("GASR_WAVE", -1);
         o.stream_gemm_ctas = num("GASR_STREAM_GEMM_CTAS", 24); o.rnn_nsub = num("GASR_RNN_NSUB", -1);
+        o.gemm_stages = num("GASR_GEMM_STAGES", 3); o.ctc_warps = num("GASR_CTC_WARPS", 8); o.gemm_bn = num("GASR_GEMM_BN", 256);
+        o.wave_serial = getenv("GASR_WAVE_SERIAL") != nullptr;
     }
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
@@ -254,14 +256,6 @@ int gasr_free_host(gasr_ctx *ctx, void *ptr) {
     return GASR_OK;
 }
 
-int gasr_matrix_alloc(gasr_ctx *ctx, int rows, int cols, int elem_bytes, void **dev, int *ld) {
-    GASR_CHECK(rows >= 0 && cols >= 0 && (elem_bytes == 1 || elem_bytes == 2 || elem_bytes == 4 || elem_bytes == 8) &&
-                   dev != nullptr && ld != nullptr, "gasr_matrix_alloc: bad arguments");
-    const int per16 = 16 / elem_bytes;
-    *ld = (cols + per16 - 1) / per16 * per16;
-    return gasr_malloc_device(ctx, (size_t)rows * (size_t)*ld * elem_bytes, dev);
-}
-
 int gasr_memcpy_h2d(gasr_ctx *ctx, void *dst, const void *src, size_t bytes) {
     GASR_ENTER(ctx);
     GASR_CHECK(bytes == 0 || (dst && src), "gasr_memcpy_h2d: null pointer");
@@ -285,6 +279,15 @@ int gasr_memcpy_h2d_async(gasr_ctx *ctx, void *dst, const void *src, size_t byte
     GASR_CHECK(bytes == 0 || (dst && src), "gasr_memcpy_h2d_async: null pointer");
     if (bytes == 0) return GASR_OK;
     GASR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return GASR_OK;
+}
+
+int gasr_memcpy_h2d_on_stream(gasr_ctx *ctx, void *dst, const void *src, size_t bytes, void *cuda_stream) {
+    GASR_ENTER(ctx);
+    GASR_CHECK(bytes == 0 || (dst && src), "gasr_memcpy_h2d_on_stream: null pointer");
+    if (bytes == 0) return GASR_OK;
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    GASR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
     return GASR_OK;
 }
 

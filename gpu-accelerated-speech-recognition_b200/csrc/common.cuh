@@ -62,6 +62,10 @@ struct gasr_options {
     int wave = -1;           // GASR_WAVE (-1: default): throughput (wave) engine on/off
     int stream_gemm_ctas = 24;
     int rnn_nsub = -1;
+    int gemm_stages = 3;     // GASR_GEMM_STAGES: ring depth of the wave engine's GEMM launches (2 or 3)
+    int gemm_bn = 256;       // GASR_GEMM_BN: tile width of the wave engine's projection GEMMs (128 or 256)
+    bool wave_serial = false; // GASR_WAVE_SERIAL: diagnostic, all stages of the wave engine on one stream
+    int ctc_warps = 8;       // GASR_CTC_WARPS: utterances (warps) per decoder CTA in the wave engine
 };
 
 struct gasr_ctx {
@@ -118,11 +122,11 @@ int xproj_tc_split_rows(gasr_ctx *ctx, const float *A, int lda, int M, int K, vo
 struct XprojTcPlan { CUtensorMap maps[4]; int M, K, N; void *abuf; };
 int xproj_tc_plan(XprojTcPlan &pl, int M, int K, int N, const void *wbuf, void *abuf);
 int xproj_tc_run(gasr_ctx *ctx, const XprojTcPlan &pl, const float *A, int lda, const float *bias, float *C, int ldc,
-                 int precision, cudaStream_t st);
+                 int precision, cudaStream_t st, int relu = 0);
 int xproj_tc_split_rows_range(gasr_ctx *ctx, const float *A, int lda, int M_total, int row0, int nrows, int K, void *abuf,
                               cudaStream_t st);
 int launch_xproj_tc(gasr_ctx *ctx, const float *A, int lda, int M, int K, int N, const void *wbuf, void *abuf,
-                    const float *bias, float *C, int ldc, int precision, cudaStream_t st);
+                    const float *bias, float *C, int ldc, int precision, cudaStream_t st, int relu = 0);
 
 // fused GRU timestep (gru_tc.cu): permuted W_hh^T planes + ping-pong bf16 planes of h, TMA descriptors built once
 struct GruTcPlan { CUtensorMap maps[2][2]; CUtensorMap wmaps[2]; void *plane[2][2]; int N, H, Kp; };
@@ -159,6 +163,7 @@ struct CtcArgs {
     const unsigned *lp_ready = nullptr; int lp_need = 0, lp_fpb = 1; int *error = nullptr; volatile unsigned *abort = nullptr;
     bool vocab_resident = false;   // the vocabulary was uploaded by ctc_decode_upload_vocab
     int frame_rows = 0;            // rows of `scores` per frame (0: N)
+    int warps_per_cta = 0;         // warp kernel: utterances per CTA (0: automatic)
 };
 int ctc_decode_reserve(gasr_ctx *ctx, const CtcArgs &a);                  // allocations only (device-synchronising)
 int ctc_decode_upload_vocab(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st);

@@ -1295,6 +1295,7 @@ __global__ void __launch_bounds__(128) ctc_beam_cta_kernel(const CtcParams p) {
                 } while (v < (unsigned)p.lp_need);
             }
             ready_frames = (blk + 1) * p.lp_fpb;
+            __threadfence();                             // acquire side of the counter: the rows are read after this fence
             flag_next = 0;
             if (ready_frames < p.T && lane == 0) flag_next = lpr[blk + 1];
         }
@@ -1787,6 +1788,7 @@ __global__ void __launch_bounds__(MW * 32 + 64) ctc_beam_cta2_kernel(const CtcPa
                     }
                 } while (v < (unsigned)p.lp_need);
                 ready_frames = (blk + 1) * p.lp_fpb;
+                __threadfence();                         // acquire side of the counter: the rows are read after this fence
             }
             const float lpv = active ? __ldcg(S + (size_t)t * frame_stride + lane) : 0.0f;
             const unsigned mine = active ? f2ord(lpv) : 0u;
@@ -2442,6 +2444,7 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
         // warp-per-utterance fast path; few warps per CTA when utterances are scarce (latency), 8 when plentiful
         int W = ceil_div(a.N, ctx->sm_count);
         if (W > 8) W = 8;
+        if (a.warps_per_cta >= 1 && a.warps_per_cta <= 8) W = a.warps_per_cta;
         const int blocks = ceil_div(a.N, W);
 #define GASR_CTCW_LAUNCH(DOM, BM)                                                                                \
     do {                                                                                                          \

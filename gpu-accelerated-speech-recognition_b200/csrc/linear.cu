@@ -126,6 +126,17 @@ int launch_linear(gasr_ctx *ctx, const float *x, int ldx, const float *W, const 
     if (rows == 0) return GASR_OK;
     if (!ctx->opt.linear_simt && linear_tc_supported(rows, in, out, ldy, y, act))
         return launch_linear_logsoftmax_tc(ctx, x, ldx, W, b, y, ldy, rows, in, out, st);
+    // Wide layers (the DeepSpeech FC front / back layers, main.cpp:31-45, baseline/model.py:22-35): the tcgen05 tile engine
+    // with bias + ReLU in its epilogue -- fp32-grade (3-term bf16 split), one GEMM launch instead of FFMA GEMM + activation.
+    if (!ctx->opt.linear_simt && act != GASR_ACT_LOGSOFTMAX && rows >= 32 && xproj_tc_supported(rows, in, out) && ldy % 4 == 0 &&
+        (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+        const size_t wb = xproj_tc_w_bytes(in, out), ab = xproj_tc_a_bytes(rows, in);
+        GASR_TRY(ws_reserve(ctx, ctx->ws_lin, wb + ab + 2048));
+        unsigned char *base = static_cast<unsigned char *>(ctx->ws_lin.ptr);
+        GASR_TRY(xproj_tc_prepare_weights(ctx, W, in, out, base, st));
+        return launch_xproj_tc(ctx, x, ldx, rows, in, out, base, base + align_up(wb, 1024), b, y, ldy, GASR_PREC_FP32, st,
+                               act == GASR_ACT_RELU ? 1 : 0);
+    }
     const size_t smem = (size_t)in * 32 * sizeof(float);
     if (out <= 32 && smem <= (size_t)ctx->max_smem_optin - 1024) {
         const int tiles = ceil_div(rows, LIN_ROWS * 8);

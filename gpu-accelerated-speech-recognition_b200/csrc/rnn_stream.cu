@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_stream_kernel(const RnnStre
     unsigned flag_next = 0;
     auto sample_flag = [&]() { if (lane == 0) flag_next = xr[ready_blocks]; };
     auto advance_blocks = [&](int t) {                   // make sure the xproj rows of frame t are complete
+        const int before = ready_blocks;
         // opportunistic: last step's sample of the next block's counter
         if (__shfl_sync(0xffffffffu, flag_next, 0) >= (unsigned)p.xp_need) ready_blocks++;
         const int need = (fsh >= 0 ? (t >> fsh) : t / fpb) + 1;
@@ -223,6 +224,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_stream_kernel(const RnnStre
             } while (v < (unsigned)p.xp_need);
             ready_blocks++;
         }
+        if (ready_blocks != before) __threadfence();     // acquire side of the counters: the xproj rows are read after this fence
         flag_next = 0;
         if (ready_blocks < nblocks) sample_flag();       // issued BEFORE this step's xproj loads
     };
@@ -448,6 +450,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_stream2_kernel(const RnnStr
     int ready_blocks = xr == nullptr ? nblocks : 0;
     unsigned flag_next = 0;
     auto advance_blocks = [&](int t) {
+        const int before = ready_blocks;
         if (__shfl_sync(0xffffffffu, flag_next, 0) >= (unsigned)p.xp_need) ready_blocks++;
         const int need = (fsh >= 0 ? (t >> fsh) : t / fpb) + 1;
         while (ready_blocks < need) {
@@ -468,6 +471,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_stream2_kernel(const RnnStr
             } while (v < (unsigned)p.xp_need);
             ready_blocks++;
         }
+        if (ready_blocks != before) __threadfence();     // acquire side of the counters
         flag_next = 0;
         if (ready_blocks < nblocks && lane == 0) flag_next = xr[ready_blocks];
     };

@@ -28,6 +28,8 @@ struct XsParams {
     int row0;                 // first row of the A operand in its TMA descriptor (the wave engine runs one time chunk per launch)
     int n_blocks;             // ceil(M / 128)
     int n_targets;
+    int stages;               // shared-memory ring depth (0 = default 3)
+    int wide;                 // 1: targets may use 256-column tiles (96 KB stages, two of them; 2 x 256 TMEM columns)
     int *error;               // mapped host word: watchdog code
     volatile unsigned *abort; // device word: any persistent kernel of the pipeline gave up -> everybody stops waiting
     XsTarget target[XS_MAX_TARGETS];

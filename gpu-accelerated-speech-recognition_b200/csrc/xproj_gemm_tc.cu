@@ -31,6 +31,7 @@ struct TcParams {
     int M, N, kblocks, terms;     // terms = 3 (fp32-grade) or 1 (bf16)
     float *C; int ldc;
     const float *bias;
+    int relu;                     // epilogue: max(. + bias, 0)  (Linear.cu:3-10)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -138,6 +139,7 @@ xproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                     o.y = __uint_as_float(v[j + 1]) + (bsrc ? bsrc[j + 1] : 0.0f);
                     o.z = __uint_as_float(v[j + 2]) + (bsrc ? bsrc[j + 2] : 0.0f);
                     o.w = __uint_as_float(v[j + 3]) + (bsrc ? bsrc[j + 3] : 0.0f);
+                    if (p.relu) { o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f); }
                     *reinterpret_cast<float4 *>(dst + j) = o;
                 }
             }
@@ -273,12 +275,12 @@ int xproj_tc_plan(XprojTcPlan &pl, int M, int K, int N, const void *wbuf, void *
 
 // C[M, N] = A[M, K] * W + bias through a plan: split A into the plan's bf16 planes, then the tcgen05 GEMM
 int xproj_tc_run(gasr_ctx *ctx, const XprojTcPlan &pl, const float *A, int lda, const float *bias, float *C, int ldc,
-                 int precision, cudaStream_t st) {
+                 int precision, cudaStream_t st, int relu) {
     GASR_CHECK(ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0, "xproj_tc: output must be 16-byte aligned");
     GASR_TRY(xproj_tc_split_rows(ctx, A, lda, pl.M, pl.K, pl.abuf, st));
     TcParams p;
     p.M = pl.M; p.N = pl.N; p.kblocks = ceil_div(pl.K, TC_BK); p.terms = precision == GASR_PREC_BF16 ? 1 : 3;
-    p.C = C; p.ldc = ldc; p.bias = bias;
+    p.C = C; p.ldc = ldc; p.bias = bias; p.relu = relu;
     if (!(ctx->attr_mask & 1024u)) {
         GASR_CUDA(cudaFuncSetAttribute(xproj_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         ctx->attr_mask |= 1024u;
@@ -293,10 +295,10 @@ int xproj_tc_run(gasr_ctx *ctx, const XprojTcPlan &pl, const float *A, int lda, 
 
 // C[M, N] = A[M, K] * W + bias with W prepared by xproj_tc_prepare_weights; abuf is scratch of xproj_tc_a_bytes(M, K).
 int launch_xproj_tc(gasr_ctx *ctx, const float *A, int lda, int M, int K, int N, const void *wbuf, void *abuf,
-                    const float *bias, float *C, int ldc, int precision, cudaStream_t st) {
+                    const float *bias, float *C, int ldc, int precision, cudaStream_t st, int relu) {
     XprojTcPlan pl;
     GASR_TRY(xproj_tc_plan(pl, M, K, N, wbuf, abuf));
-    return xproj_tc_run(ctx, pl, A, lda, bias, C, ldc, precision, st);
+    return xproj_tc_run(ctx, pl, A, lda, bias, C, ldc, precision, st, relu);
 }
 
 }  // namespace gasr

@@ -22,7 +22,10 @@
 
 namespace gasr {
 
-constexpr int XS_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/ + 4 * 32 * 36 * 4 /*epilogue staging*/;
+constexpr int XS_SMEM_EXTRA = 1024 /*alignment slack*/ + 128 /*barriers*/ + 4 * 32 * 36 * 4 /*epilogue staging*/;
+constexpr int XS_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + XS_SMEM_EXTRA;
+static inline int xs_stage_bytes(int wide) { return wide ? 2 * TC_TILE_BYTES + 2 * 256 * TC_BK * 2 : TC_STAGE_BYTES; }   // A hi/lo + B hi/lo (B up to 256 rows)
+static inline int xs_smem_bytes(int stages, int wide) { return stages * xs_stage_bytes(wide) + XS_SMEM_EXTRA; }
 constexpr unsigned long long XS_TIMEOUT_NS = 2000000000ull;
 
 __device__ __forceinline__ bool xs_mbar_try(uint32_t bar, uint32_t parity) {
@@ -98,12 +101,16 @@ xproj_stream_kernel(const __grid_constant__ XsMaps maps, const XsParams p) {
     __shared__ int abort_s;
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles = (raw + 1023u) & ~1023u;
-    const uint32_t bars = tiles + TC_STAGES * TC_STAGE_BYTES;            // full[S], empty[S], tfull[2], tempty[2], tmem slot
+    const int NS = p.stages;                                             // ring depth: 3, or 2 (the wave engine: leaves shared memory for decoder CTAs on the same SM)
+    const uint32_t SB = p.wide ? (uint32_t)(2 * TC_TILE_BYTES + 2 * 256 * TC_BK * 2) : (uint32_t)TC_STAGE_BYTES;   // stage bytes
+    const uint32_t OFF_BLO = 2 * TC_TILE_BYTES + (p.wide ? 256u : 128u) * TC_BK * 2;                                  // B lo inside a stage
+    const uint32_t ACC = p.wide ? 256u : (uint32_t)TC_BN;                                                             // TMEM columns per accumulator
+    const uint32_t bars = tiles + NS * SB;                               // full[S], empty[S], tfull[2], tempty[2], tmem slot
     const uint32_t full0 = bars, empty0 = bars + 8 * TC_STAGES, tfull0 = bars + 16 * TC_STAGES, tempty0 = tfull0 + 16;
     unsigned char *gen_tiles = smem_raw + (tiles - raw);
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen_tiles + TC_STAGES * TC_STAGE_BYTES + 16 * TC_STAGES + 32);
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen_tiles + NS * SB + 16 * TC_STAGES + 32);
     volatile int *abort_flag = &abort_s;
-    float *epi_stage = reinterpret_cast<float *>(gen_tiles + TC_STAGES * TC_STAGE_BYTES + 128);     // [4 warps][32][36] floats
+    float *epi_stage = reinterpret_cast<float *>(gen_tiles + NS * SB + 128);     // [4 warps][32][36] floats
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -114,7 +121,8 @@ xproj_stream_kernel(const __grid_constant__ XsMaps maps, const XsParams p) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)), "n"(2 * TC_BN) : "memory");
+        if (p.wide) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)), "n"(512) : "memory");
+        else asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)), "n"(2 * TC_BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -148,15 +156,15 @@ xproj_stream_kernel(const __grid_constant__ XsMaps maps, const XsParams p) {
                 const uint32_t btile = (uint32_t)t.bn * TC_BK * 2;
                 const uint32_t bytes = (t.terms == 3 ? 2u : 1u) * (TC_TILE_BYTES + btile);
                 for (int kb = 0; kb < t.kblocks; kb++, it++) {
-                    const int s = it % TC_STAGES;
-                    if (!xs_wait(empty0 + 8 * s, ((it / TC_STAGES) & 1) ^ 1, abort_flag, p.abort)) break;
-                    const uint32_t st = tiles + s * TC_STAGE_BYTES;
+                    const int s = it % NS;
+                    if (!xs_wait(empty0 + 8 * s, ((it / NS) & 1) ^ 1, abort_flag, p.abort)) break;
+                    const uint32_t st = tiles + s * SB;
                     mbar_expect_tx(full0 + 8 * s, bytes);
                     tma_load_2d(st, ma_hi, full0 + 8 * s, kb * TC_BK, p.row0 + blk * TC_BM);
                     tma_load_2d(st + 2 * TC_TILE_BYTES, mb_hi, full0 + 8 * s, kb * TC_BK, tile * t.bn);
                     if (t.terms == 3) {
                         tma_load_2d(st + TC_TILE_BYTES, ma_lo, full0 + 8 * s, kb * TC_BK, p.row0 + blk * TC_BM);
-                        tma_load_2d(st + 3 * TC_TILE_BYTES, mb_lo, full0 + 8 * s, kb * TC_BK, tile * t.bn);
+                        tma_load_2d(st + OFF_BLO, mb_lo, full0 + 8 * s, kb * TC_BK, tile * t.bn);
                     }
                 }
             }
@@ -174,15 +182,15 @@ xproj_stream_kernel(const __grid_constant__ XsMaps maps, const XsParams p) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 // instruction descriptor: D = f32, A = B = bf16, both K-major, N = bn, M = 128
                 const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(t.bn >> 3) << 17) | ((TC_BM >> 4) << 24);
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_BN);
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * ACC;
                 bool ok = true;
                 for (int kb = 0; kb < t.kblocks; kb++, it++) {
-                    const int s = it % TC_STAGES;
-                    if (!xs_wait(full0 + 8 * s, (it / TC_STAGES) & 1, abort_flag, p.abort)) { ok = false; break; }
+                    const int s = it % NS;
+                    if (!xs_wait(full0 + 8 * s, (it / NS) & 1, abort_flag, p.abort)) { ok = false; break; }
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t st = tiles + s * TC_STAGE_BYTES;
+                    const uint32_t st = tiles + s * SB;
                     const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + TC_TILE_BYTES);
-                    const uint64_t b_hi = umma_desc_sw128(st + 2 * TC_TILE_BYTES), b_lo = umma_desc_sw128(st + 3 * TC_TILE_BYTES);
+                    const uint64_t b_hi = umma_desc_sw128(st + 2 * TC_TILE_BYTES), b_lo = umma_desc_sw128(st + OFF_BLO);
 #pragma unroll
                     for (int k4 = 0; k4 < TC_BK / 16; k4++) {
                         const uint64_t adv = (uint64_t)(k4 * 32 >> 4);
@@ -221,7 +229,7 @@ xproj_stream_kernel(const __grid_constant__ XsMaps maps, const XsParams p) {
             const int n0 = tile * t.bn;
             const int nchunks = t.bn / 32;
             uint32_t v[32];
-            xs_tmem_ld32(v, tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * TC_BN));
+            xs_tmem_ld32(v, tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)acc * ACC);
             if (pend) {
                 if (lane == 0) { __threadfence(); atomicAdd(pend, 1u); }
                 pend = nullptr;
@@ -266,7 +274,7 @@ xproj_stream_kernel(const __grid_constant__ XsMaps maps, const XsParams p) {
                 }
                 // the registers are staged: fetch the next 32 columns while this chunk is being stored
                 if (c + 1 < nchunks)
-                    xs_tmem_ld32(v, tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * TC_BN + (c + 1) * 32));
+                    xs_tmem_ld32(v, tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)acc * ACC + (uint32_t)((c + 1) * 32));
                 __syncwarp();
                 if (!(t.kind & 16)) {
                     const int c4 = lane & 7, rsub = lane >> 3;                   // this lane: columns 4*c4..+3 of rows rsub + 4i
@@ -293,7 +301,8 @@ xproj_stream_kernel(const __grid_constant__ XsMaps maps, const XsParams p) {
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * TC_BN) : "memory");
+        if (p.wide) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * TC_BN) : "memory");
     }
 }
 
@@ -301,18 +310,22 @@ int launch_xproj_stream(gasr_ctx *ctx, const XsMaps &maps, const XsParams &p, in
     GASR_CHECK(ctas >= 0 && p.n_targets >= 1 && p.n_targets <= XS_MAX_TARGETS, "xproj_stream: bad parameters");
     for (int i = 0; i < p.n_targets; i++) {
         const XsTarget &t = p.target[i];
-        GASR_CHECK(t.C && t.src_done && t.dst_ready && t.kblocks >= 1 && (t.bn == 128 || t.bn == 32) && (t.terms == 1 || t.terms == 3),
+        GASR_CHECK(t.C && t.src_done && t.dst_ready && t.kblocks >= 1 && (t.bn == 128 || t.bn == 32 || (t.bn == 256 && p.wide)) && (t.terms == 1 || t.terms == 3),
                    "xproj_stream: bad target %d", i);
         GASR_CHECK((t.kind & 15) == XS_KIND_XPROJ || (t.bn == 32 && t.n_tiles == 1 && t.V >= 1 && t.V <= 32), "xproj_stream: bad output-layer target");
         GASR_CHECK(ctas == 0 || (t.nctas >= 1 && t.cta0 >= 0 && t.cta0 + t.nctas <= ctas), "xproj_stream: bad CTA range of target %d", i);
         GASR_CHECK(t.ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(t.C) & 15) == 0, "xproj_stream: output must be 16-byte aligned");
     }
     if (!(ctx->attr_mask & 8u)) {       // once per context, never while the pipeline's other kernels are running
-        GASR_CUDA(cudaFuncSetAttribute(xproj_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XS_SMEM_BYTES));
+        GASR_CUDA(cudaFuncSetAttribute(xproj_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, xs_smem_bytes(2, 1) > XS_SMEM_BYTES ? xs_smem_bytes(2, 1) : XS_SMEM_BYTES));
         ctx->attr_mask |= 8u;
     }
     if (ctas == 0) return GASR_OK;      // preparation call
-    xproj_stream_kernel<<<ctas, TC_THREADS, XS_SMEM_BYTES, st>>>(maps, p);
+    GASR_CHECK(p.stages == 0 || p.stages == 2 || p.stages == 3, "xproj_stream: ring depth must be 2 or 3");
+    XsParams q = p;
+    if (q.stages == 0) q.stages = TC_STAGES;
+    if (q.wide) q.stages = 2;              // 96 KB stages: two fit
+    xproj_stream_kernel<<<ctas, TC_THREADS, xs_smem_bytes(q.stages, q.wide), st>>>(maps, q);
     GASR_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return GASR_OK;

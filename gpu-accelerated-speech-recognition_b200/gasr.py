@@ -50,7 +50,7 @@ _lib.gasr_last_error.restype = ctypes.c_char_p
 EXPORTS = [
     "gasr_version", "gasr_last_error", "gasr_device_count", "gasr_ctx_create", "gasr_ctx_destroy", "gasr_ctx_sync",
     "gasr_ctx_sm_count", "gasr_timer_start", "gasr_timer_stop", "gasr_ctx_launch_count", "gasr_malloc_device",
-    "gasr_free_device", "gasr_malloc_host", "gasr_free_host", "gasr_matrix_alloc", "gasr_memcpy_h2d",
+    "gasr_free_device", "gasr_malloc_host", "gasr_free_host", "gasr_memcpy_h2d_on_stream", "gasr_memcpy_h2d",
     "gasr_memcpy_d2h", "gasr_memcpy_h2d_async", "gasr_memcpy_d2h_async", "gasr_memset_device", "gasr_memory_stats",
     "gasr_matmul", "gasr_matadd", "gasr_xproj_gemm", "gasr_linear_forward", "gasr_log_softmax", "gasr_rnn_cell_forward",
     "gasr_rnn_forward", "gasr_ctc_decode", "gasr_ctc_last_stats", "gasr_ctc_decode_host", "gasr_asr_create", "gasr_asr_destroy",
@@ -597,7 +597,7 @@ def _declare():
     L.gasr_free_device.argtypes = [vp, vp]
     L.gasr_malloc_host.argtypes = [vp, sz, c_void_pp]
     L.gasr_free_host.argtypes = [vp, vp]
-    L.gasr_matrix_alloc.argtypes = [vp, ci, ci, ci, c_void_pp, c_int_p]
+    L.gasr_memcpy_h2d_on_stream.argtypes = [vp, vp, vp, sz, vp]
     for f in (L.gasr_memcpy_h2d, L.gasr_memcpy_d2h, L.gasr_memcpy_h2d_async, L.gasr_memcpy_d2h_async):
         f.argtypes = [vp, vp, vp, sz]
     L.gasr_memset_device.argtypes = [vp, vp, ci, sz]

@@ -13,6 +13,11 @@
 #include "MemoryMonitor.h"
 #include "gasr_cxx.h"
 
+/* the CUDA runtime's opaque stream handle, declared here so that callers need no CUDA headers (an identical typedef in
+ * <driver_types.h> is a legal redeclaration) */
+struct CUstream_st;
+typedef struct CUstream_st *cudaStream_t;
+
 template <class T>
 class cuMatrix {
 public:
@@ -59,12 +64,15 @@ public:
         mallocDev(); mallocHost();
         gasr_cxx::check(gasr_memcpy_h2d(gasr_cxx::ctx(), devData, hostData, bytes()), "cuMatrix::toGPU data upload failed");
     }
-    /* asynchronous upload on the context's stream (the reference takes a cudaStream_t, cuMatrix.h:108-115) */
-    void toGpuAsync() {
+    /* asynchronous upload on a caller's stream (reference cuMatrix.h:108-115 takes a cudaStream_t); the handle is passed to
+     * the library as an opaque pointer, so a caller needs no CUDA headers unless it creates streams itself */
+    void toGpu(cudaStream_t stream) {
         if (isShallow) { printf("Error: attempting to manipulate memory of a shallow copy."); return; }
         mallocDev(); mallocHost();
-        gasr_cxx::check(gasr_memcpy_h2d_async(gasr_cxx::ctx(), devData, hostData, bytes()), "cuMatrix::toGpu(stream)");
+        gasr_cxx::check(gasr_memcpy_h2d_on_stream(gasr_cxx::ctx(), devData, hostData, bytes(), (void *)stream), "cuMatrix::toGpu(stream)");
     }
+    /* the same on the context's own stream */
+    void toGpuAsync() { toGpu((cudaStream_t)0); }
     void gpuClear() {
         if (isShallow) { printf("Error: attempting to manipulate memory of a shallow copy."); return; }
         mallocDev();

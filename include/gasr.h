@@ -61,12 +61,13 @@ int gasr_malloc_device(gasr_ctx *ctx, size_t bytes, void **ptr);
 int gasr_free_device(gasr_ctx *ctx, void *ptr);
 int gasr_malloc_host(gasr_ctx *ctx, size_t bytes, void **ptr);     /* pinned, zero-filled           */
 int gasr_free_host(gasr_ctx *ctx, void *ptr);
-/* Row-pitched matrix: ld = cols rounded up so every row starts 16-byte aligned (TMA / float4).      */
-int gasr_matrix_alloc(gasr_ctx *ctx, int rows, int cols, int elem_bytes, void **dev, int *ld);
 int gasr_memcpy_h2d(gasr_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);  /* toGpu  */
 int gasr_memcpy_d2h(gasr_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);  /* toCpu  */
 int gasr_memcpy_h2d_async(gasr_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
 int gasr_memcpy_d2h_async(gasr_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+/* cuMatrix::toGpu(cudaStream_t) (cuMatrix.h:108-115): upload on the caller's stream; cuda_stream is a cudaStream_t passed
+ * as an opaque pointer (NULL = the ctx's own stream).                                                              */
+int gasr_memcpy_h2d_on_stream(gasr_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, void *cuda_stream);
 int gasr_memset_device(gasr_ctx *ctx, void *dst_dev, int value, size_t bytes);           /* gpuClear */
 int gasr_memory_stats(gasr_ctx *ctx, size_t *device_bytes, size_t *host_bytes);  /* print*Memory   */
 

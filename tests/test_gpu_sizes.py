@@ -80,6 +80,23 @@ def test_cfg1_baseline_config_hot_path(gasr, ctx, O):
     pipe.close()
 
 
+def test_wide_linear_relu_on_tensor_cores(gasr, ctx, O):
+    """The DeepSpeech FC layers (main.cpp:31-45, baseline/model.py:22-35: 2048-wide Linear + ReLU) run on the tcgen05 tile
+    engine with bias + ReLU in the epilogue (Linear.cu:3-10,42-49 semantics), fp32-grade."""
+    rng = np.random.default_rng(5)
+    for rows, in_, out, act in ((200, 78, 2048, "relu"), (256, 2048, 2048, "relu"), (1000, 2048, 2048, "none")):
+        x = rng.normal(size=(rows, in_)).astype(np.float32)
+        W = (rng.normal(size=(in_, out)) / np.sqrt(in_)).astype(np.float32)
+        b = rng.normal(size=(out,)).astype(np.float32)
+        ref = O.linear(x, W, b, act=act)
+        dx, dW, db, dy = ctx.to_device(x), ctx.to_device(W), ctx.to_device(b), ctx.malloc(rows * out * 4)
+        ctx.linear(dx, in_, dW, db, dy, out, rows, in_, out, gasr.ACT_RELU if act == "relu" else gasr.ACT_NONE)
+        got = ctx.to_host(dy, (rows, out))
+        for q in (dx, dW, db, dy):
+            ctx.free(q)
+        assert np.abs(got - ref).max() < AM_TOL, (rows, in_, out, act)
+
+
 # ------------------------------------------------------------------------------------------------ cfg2
 def test_cfg2_full_size_pipeline_vs_oracle(gasr, ctx, O):
     """The whole cfg2 batch (64 utterances x 1000 frames, 3 layers H = 512, beam 16) end to end against the oracle: every
