@@ -52,7 +52,7 @@ struct WaveState {
     std::vector<int> tag;
     size_t n_timed = 0;
     CtcArgs ca = {};
-    bool pending = false, serial = false;
+    bool pending = false, serial = false, pair = false;
     float last_ms = 0.0f;
 };
 
@@ -78,7 +78,7 @@ __global__ void wave_split_kernel(const float *__restrict__ x, int ldx, int N, i
 bool wave_supported(const gasr_ctx *ctx, const gasr_asr_config &c) {
     return c.cell == GASR_CELL_TANH && !c.bidirectional && (c.H == 128 || c.H == 256 || c.H == 512) && c.beam <= 32 && c.V <= 32 &&
            ctx->cluster_ok && rnn_wide_supported(ctx, c.H) &&
-           (long long)c.T * (ceil_div(c.N, 128) * 128) < (1ll << 31) / 64;
+           (long long)c.T * (ceil_div(c.N, 256) * 256) < (1ll << 31) / 64;
 }
 
 static size_t planes_bytes(size_t rows, int Kp) { return 2 * align_up(rows * (size_t)Kp * 2, 1024); }
@@ -89,7 +89,8 @@ int wave_create(gasr_asr *a) {
     WaveState *w = new WaveState();
     a->wave = w;
     const int L = c.L, H = c.H;
-    w->Npad = ceil_div(c.N, 128) * 128;
+    w->pair = ctx->opt.rnn_pair && rnn_wide2_supported(ctx, c.H) && c.N > 128;   // CTA-pair recurrence: groups of 256 utterances
+    w->Npad = w->pair ? ceil_div(c.N, 256) * 256 : ceil_div(c.N, 128) * 128;
     w->Tc = ctx->opt.chunk > 0 ? ctx->opt.chunk : 50;
     if (w->Tc > c.T) w->Tc = c.T;
     w->C = ceil_div(c.T, w->Tc);
@@ -142,6 +143,7 @@ int wave_create(gasr_asr *a) {
     if (st != GASR_OK) { set_error("wave engine: stream / event creation failed"); return st; }
     // function attributes and the decoder's workspaces now (both may synchronise the device), never between launches
     GASR_TRY(rnn_wide_prepare(ctx, H));
+    if (w->pair) GASR_TRY(rnn_wide2_prepare(ctx));
     {
         XsParams prep = {};
         XsMaps none;
@@ -206,7 +208,7 @@ int wave_set_weights(gasr_asr *a, const float *fc_w, const float *fc_b) {
         const int K = l == 0 ? c.in : H, Kp = l == 0 ? w->Kp0 : H;
         GASR_TRY(xproj_tc_prepare_weights(ctx, a->w_ih[l], K, H, w->wih[l], st));
         GASR_TRY(launch_matadd(ctx, a->b_ih[l], H, a->b_hh[l], H, w->bias_all + (size_t)l * H, H, 1, H, 1.0f, st));
-        GASR_TRY(rnn_wide_plan(ctx, w->rec[l], a->w_hh[l], c.T, c.N, H, w->whh[l], w->h_planes[l], st));
+        GASR_TRY(rnn_wide_plan(ctx, w->rec[l], a->w_hh[l], c.T, c.N, H, w->whh[l], w->h_planes[l], st, w->pair ? 256 : 128));
         unsigned char *ab = static_cast<unsigned char *>(l == 0 ? w->x_planes : w->h_planes[l - 1]);
         const size_t a_half = l == 0 ? planes_bytes(w->rows_p, Kp) / 2 : rnn_wide_plane_bytes(c.T, w->Npad, H);
         unsigned char *wb = static_cast<unsigned char *>(w->wih[l]);
@@ -333,7 +335,7 @@ int wave_submit(gasr_asr *a, const float *x_dev, const float *x_host) {
             r.s0 = f0; r.s1 = f1; r.xp = w->xp[l]; r.ldxp = c.H; r.xp_rows_per_frame = Npad;
             r.out = nullptr; r.groups_per_cluster = ctx->opt.rnn_groups; r.multicast = ctx->opt.rnn_mc;
             GASR_TRY(timed_begin(1, w->st_r[l]));
-            GASR_TRY(launch_rnn_wide(ctx, w->rec[l], r, w->st_r[l]));
+            GASR_TRY(w->pair ? launch_rnn_wide2(ctx, w->rec[l], r, w->st_r[l]) : launch_rnn_wide(ctx, w->rec[l], r, w->st_r[l]));
             GASR_TRY(timed_end(w->st_r[l]));
             GASR_CUDA(cudaEventRecord(w->ev_r[l][ci], w->st_r[l]));
         }

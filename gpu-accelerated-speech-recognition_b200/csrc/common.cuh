@@ -50,7 +50,8 @@ struct Workspace {
 struct gasr_options {
     char rnn = 0;            // GASR_RNN: w = wide tcgen05 recurrence, f / m / ... = the round-1 kernels (first letter)
     int rnn_mc = 1;          // GASR_RNN_MC: TMA multicast of the h boxes in the wide recurrence
-    int rnn_groups = 2;      // GASR_RNN_G: groups of 128 utterances per cluster (1 or 2)
+    int rnn_groups = 2;      // GASR_RNN_G: groups of utterances per cluster (1 or 2)
+    int rnn_pair = 1;        // GASR_RNN_PAIR: CTA-pair recurrence (tcgen05.mma.cta_group::2, groups of 256 utterances)
     char ctc_kernel = 0;     // GASR_CTC_KERNEL
     int ctc_mw = 8;          // GASR_CTC_MW
     int ctc_pad = 0;         // GASR_CTC_PAD

@@ -433,17 +433,19 @@ int launch_rnn_recurrence(gasr_ctx *ctx, const RnnLayerArgs &a, cudaStream_t st)
         const bool whole = a.s0 == 0 && (a.s1 == 0 || a.s1 == a.T);
         const bool want = force ? force == 'w' : a.N >= 96;
         if (want && whole && a.cell == GASR_CELL_TANH && !a.reverse && rnn_wide_supported(ctx, a.H) && cluster_kernel_supported(ctx, a)) {
-            const int Npad = ceil_div(a.N, 128) * 128;
+            const bool pair = ctx->opt.rnn_pair && rnn_wide2_supported(ctx, a.H) && a.N > 128;   // CTA pairs: groups of 256
+            const int unit = pair ? 256 : 128;
+            const int Npad = ceil_div(a.N, unit) * unit;
             const size_t pb = rnn_wide_plane_bytes(a.T, Npad, a.H), wb = xproj_tc_w_bytes(a.H, a.H);
             GASR_TRY(ws_reserve(ctx, ctx->ws_wide, 2 * pb + wb + 2048));
             unsigned char *base = static_cast<unsigned char *>(ctx->ws_wide.ptr);
             RnnWidePlan pl;
-            GASR_TRY(rnn_wide_plan(ctx, pl, a.w_hh, a.T, a.N, a.H, base + 2 * pb, base, st));
+            GASR_TRY(rnn_wide_plan(ctx, pl, a.w_hh, a.T, a.N, a.H, base + 2 * pb, base, st, unit));
             RnnWideRun r = {};
             r.s0 = 0; r.s1 = a.T; r.xp = a.xproj; r.ldxp = a.ldxp; r.xp_rows_per_frame = a.N;
             r.out = a.out; r.ldo = a.ldo; r.col0 = a.col0; r.out_rows_per_frame = a.N;
             r.groups_per_cluster = ctx->opt.rnn_groups; r.multicast = ctx->opt.rnn_mc;
-            return launch_rnn_wide(ctx, pl, r, st);
+            return pair ? launch_rnn_wide2(ctx, pl, r, st) : launch_rnn_wide(ctx, pl, r, st);
         }
     }
     if (cluster_kernel_supported(ctx, a)) {

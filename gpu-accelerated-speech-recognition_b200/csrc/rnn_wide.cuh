@@ -31,7 +31,11 @@ size_t rnn_wide_smem_bytes(int H);
 size_t rnn_wide_plane_bytes(int T, int Npad, int H);       // bytes of ONE plane; the planes buffer holds hi then lo
 int rnn_wide_prepare(gasr_ctx *ctx, int H);                // function attributes (call before concurrent kernels run)
 int rnn_wide_plan(gasr_ctx *ctx, RnnWidePlan &pl, const float *w_hh, int T, int N, int H, void *wbuf, void *planes,
-                  cudaStream_t st);
+                  cudaStream_t st, int pad_to = 128);
 int launch_rnn_wide(gasr_ctx *ctx, const RnnWidePlan &pl, const RnnWideRun &r, cudaStream_t st);
+// CTA-pair variant (rnn_wide2.cu, tcgen05.mma.cta_group::2): groups of 256 utterances, plan padded to 256
+bool rnn_wide2_supported(const gasr_ctx *ctx, int H);
+int rnn_wide2_prepare(gasr_ctx *ctx);
+int launch_rnn_wide2(gasr_ctx *ctx, const RnnWidePlan &pl, const RnnWideRun &r, cudaStream_t st);
 
 }  // namespace gasr

@@ -56,3 +56,23 @@ def test_wide_recurrence_vs_oracle(gasr, O, monkeypatch, mc, groups, H, N, T, L)
     for l in range(L):
         err = np.abs(out[l] - ref[l]).max()
         assert err < AM_TOL, f"layer {l}: {err}"
+
+
+@pytest.mark.parametrize("groups", [1, 2])
+@pytest.mark.parametrize("H,N,T,L", [(512, 256, 20, 1), (512, 700, 13, 2), (256, 512, 16, 1), (128, 300, 11, 2)])
+def test_wide_recurrence_cta_pairs_vs_oracle(gasr, O, monkeypatch, groups, H, N, T, L):
+    """rnn_wide2.cu: tcgen05.mma.cta_group::2, groups of 256 utterances (GASR_RNN_PAIR=1)."""
+    import synth
+    monkeypatch.setenv("GASR_RNN", "w")
+    monkeypatch.setenv("GASR_RNN_PAIR", "1")
+    monkeypatch.setenv("GASR_RNN_G", str(groups))
+    ctx = gasr.Context(0)
+    D = 37
+    x = synth.spectrogram_batch(H + N, T, N, D)
+    w_ih, w_hh, b_ih, b_hh = synth.rnn_weights(H * 3 + 1, D, H, L)
+    out = _rnn(gasr, ctx, T, N, D, H, L, x, w_ih, w_hh, b_ih, b_hh)
+    ctx.close()
+    ref = O.rnn_forward(x, T, N, w_ih, w_hh, b_ih, b_hh, nthreads=8)
+    for l in range(L):
+        err = np.abs(out[l] - ref[l]).max()
+        assert err < AM_TOL, f"layer {l}: {err}"
