@@ -25,6 +25,7 @@
 
 #include "asr.cuh"
 #include "common.cuh"
+#include "gemm_pair.cuh"
 #include "rnn_wide.cuh"
 #include "stream.cuh"
 #include "tc_common.cuh"
@@ -43,6 +44,7 @@ struct WaveState {
     int max_blocks = 0;
     std::vector<RnnWidePlan> rec;
     std::vector<XsMaps> maps;                            // per layer + output layer
+    std::vector<XsMaps> pmaps;                           // per layer: the same operands with 128-row W^T boxes (CTA-pair GEMM)
     cudaStream_t st_in = nullptr, st_fc = nullptr, st_dec = nullptr;
     std::vector<cudaStream_t> st_g, st_r;
     std::vector<cudaEvent_t> ev_in, ev_fc;
@@ -144,6 +146,7 @@ int wave_create(gasr_asr *a) {
     // function attributes and the decoder's workspaces now (both may synchronise the device), never between launches
     GASR_TRY(rnn_wide_prepare(ctx, H));
     if (w->pair) GASR_TRY(rnn_wide2_prepare(ctx));
+    GASR_TRY(gemm_pair_prepare(ctx));
     {
         XsParams prep = {};
         XsMaps none;
@@ -204,6 +207,7 @@ int wave_set_weights(gasr_asr *a, const float *fc_w, const float *fc_b) {
     cudaStream_t st = ctx->stream;
     w->rec.resize(L);
     w->maps.resize(L + 1);
+    w->pmaps.resize(L);
     for (int l = 0; l < L; l++) {
         const int K = l == 0 ? c.in : H, Kp = l == 0 ? w->Kp0 : H;
         GASR_TRY(xproj_tc_prepare_weights(ctx, a->w_ih[l], K, H, w->wih[l], st));
@@ -219,6 +223,11 @@ int wave_set_weights(gasr_asr *a, const float *fc_w, const float *fc_b) {
         const int bn = (ctx->opt.gemm_bn == 256 && H % 256 == 0) ? 256 : TC_BN;
         GASR_TRY(tc_make_map(&m.m[2], wb, H, Kp, bn));
         GASR_TRY(tc_make_map(&m.m[3], wb + xproj_tc_w_bytes(K, H) / 2, H, Kp, bn));
+        XsMaps &pm = w->pmaps[l];
+        memset(&pm, 0, sizeof(pm));
+        pm.m[0] = m.m[0]; pm.m[1] = m.m[1];
+        GASR_TRY(tc_make_map(&pm.m[2], wb, H, Kp, TC_BN));
+        GASR_TRY(tc_make_map(&pm.m[3], wb + xproj_tc_w_bytes(K, H) / 2, H, Kp, TC_BN));
     }
     {
         // output layer as a 32-column target: W_fc padded to [H, 32] -> W^T hi/lo planes; bias padded with zeros
@@ -248,6 +257,9 @@ static int wave_gemm(gasr_asr *a, int target, int row0, int rows, cudaStream_t s
     WaveState *w = a->wave;
     const gasr_asr_config &c = a->cfg;
     const int L = c.L, H = c.H;
+    if (target < L && ctx->opt.gemm_pair && gemm_pair_supported(ctx, rows, H))
+        return launch_gemm_pair(ctx, w->pmaps[target].m, row0, rows, target == 0 ? c.in : H, H, w->xp[target] + (size_t)row0 * H, H,
+                                w->bias_all + (size_t)target * H, c.precision, st);
     XsParams p = {};
     p.M = rows; p.row0 = row0; p.n_blocks = ceil_div(rows, TC_BM); p.n_targets = 1;
     p.stages = ctx->opt.gemm_stages;

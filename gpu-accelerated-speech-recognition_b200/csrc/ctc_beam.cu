@@ -2442,7 +2442,13 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
         }
     } else if (fast) {
         // warp-per-utterance fast path; few warps per CTA when utterances are scarce (latency), 8 when plentiful
-        int W = ceil_div(a.N, ctx->sm_count);
+        // utterances (warps) per CTA: the smallest k whole CTAs per SM that keeps a CTA at <= 8 warps, so that every SM gets the
+        // same number of warps (2048 utterances on 148 SMs: 293 CTAs of 7 warps = 2 per SM, not 256 of 8 = 1 or 2 per SM)
+        int W = 8;
+        for (int k = 1; k <= 64; k++) {
+            W = ceil_div(a.N, ctx->sm_count * k);
+            if (W <= 8) break;
+        }
         if (W > 8) W = 8;
         if (a.warps_per_cta >= 1 && a.warps_per_cta <= 8) W = a.warps_per_cta;
         const int blocks = ceil_div(a.N, W);
