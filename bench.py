@@ -40,7 +40,7 @@ sys.path.insert(0, ROOT)
 METRIC = "RTFx: audio-sec decoded/sec (RNN fwd + CTC beam) at 1/2/4/8 B200"
 UNIT = "audio-seconds per second"
 CFG = dict(T=1000, D=161, H=512, L=3, V=29, beam=16)          # the cfg2 shape every utterance of cfg5 has
-UTTS, WAVE_MAX, LANES = 8192, 2048, 2                        # BASELINE.json configs[4]; largest batch; batches in flight per GPU
+UTTS, WAVE_MAX, LANES = 8192, 4096, 2                        # BASELINE.json configs[4]; largest batch; batches in flight per GPU
 SEED_X, SEED_W, SEED_FC = 1234, 4321, 99
 FRAME_SEC = 0.010
 WORKLOAD = ("cfg5: 8192 utt x T=1000 x D=161 sharded over the GPUs, 3-layer tanh RNN H=512, Linear 512->29 + log-softmax, "
@@ -302,6 +302,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         host_group = dist.new_group(backend="gloo")           # host-side gather of the results (no data-path collective)
 
+    def note(msg):
+        if os.environ.get("GASR_BENCH_VERBOSE"):
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     c = CFG
     # Contiguous shard of utterances per rank, cut into batches of `wave` utterances.  Rows of a batch never interact
     # (RNN.cu:15-27, CTCBeamSearch.cu:416), so every utterance's result is independent of the batch it travels in: ranks may
@@ -317,6 +321,7 @@ def main():
     job = gasr.Job(local, c["T"], args.wave, c["D"], c["H"], c["L"], c["V"], c["beam"], 0, synth.VOCAB29, lanes=args.lanes)
     w, (fc_w, fc_b) = weights()
     job.set_weights(*w, fc_w, fc_b)
+    note("job created, weights set")
     ctx0 = job.lane_context(0)
     batch_bytes = c["T"] * args.wave * c["D"] * 4
 
@@ -332,6 +337,7 @@ def main():
         ctx0.d2h_into(h, d)
         x_pin.append(h)
     ctx0.sync()
+    note("inputs generated")
     audio_per_step = args.utts * c["T"] * FRAME_SEC
 
     def barrier():
@@ -356,15 +362,18 @@ def main():
         return ms
 
     ref = None
-    for _ in range(args.warmup):
+    for i in range(args.warmup):
         ref = job.run_device(x_dev)
+        note(f"warm-up {i}: run_device done ({job.last_ms():.1f} ms)")
         job.run_host(x_pin)
+        note(f"warm-up {i}: run_host done ({job.last_ms():.1f} ms)")
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = job.launch_count()
     ms_dev = timed(lambda: job.run_device(x_dev), args.steps)
+    note(f"timed device-resident loop done: {ms_dev / args.steps:.1f} ms per step")
     launches = job.launch_count() - launches0
     ms_e2e = timed(lambda: job.run_host(x_pin), args.steps)
     clocks = sampler.stop() if rank == 0 else None

@@ -21,6 +21,9 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <chrono>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "asr.cuh"
@@ -33,11 +36,11 @@
 namespace gasr {
 
 struct WaveState {
-    int Npad = 0, Tc = 0, C = 0, Kp0 = 0;
+    int Npad = 0, Tc = 0, C = 0, Kp0 = 0, xp_slots = 1;
     size_t rows_p = 0;                                   // T * Npad
     void *x_planes = nullptr;                            // [rows_p, Kp0] hi, then lo
     std::vector<void *> h_planes, wih, whh;              // per layer: hidden planes (hi, lo), W_ih^T planes, W_hh^T planes
-    std::vector<float *> xp;                             // per layer: [rows_p, H] fp32
+    std::vector<float *> xp;                             // per layer: ring of xp_slots chunks, [xp_slots * Tc * Npad, H] fp32
     void *fc_wbuf = nullptr;
     float *fc_b_pad = nullptr, *bias_all = nullptr, *logp = nullptr, *logp_dense = nullptr;
     unsigned *flags = nullptr;                           // [ones: max blocks][sink: max blocks][misc 16]
@@ -99,6 +102,8 @@ int wave_create(gasr_asr *a) {
     w->Kp0 = ceil_div(c.in, TC_BK) * TC_BK;
     w->rows_p = (size_t)c.T * w->Npad;
     w->max_blocks = ceil_div(w->Tc * w->Npad, TC_BM);
+    // xproj only lives from a chunk's GEMM to the same chunk's recurrence: a ring of chunk slots instead of the whole sequence
+    w->xp_slots = w->C < 4 ? w->C : 4;
     int st = GASR_OK;
     auto allocv = [&](void **p, size_t bytes) { if (st == GASR_OK) st = gasr_malloc_device(ctx, bytes, p); };
     allocv(&w->x_planes, planes_bytes(w->rows_p, w->Kp0));
@@ -107,7 +112,7 @@ int wave_create(gasr_asr *a) {
         allocv(&w->h_planes[l], 2 * rnn_wide_plane_bytes(c.T, w->Npad, H));
         allocv(&w->wih[l], xproj_tc_w_bytes(l == 0 ? c.in : H, H) + 1024);
         allocv(&w->whh[l], xproj_tc_w_bytes(H, H) + 1024);
-        allocv((void **)&w->xp[l], sizeof(float) * w->rows_p * H);
+        allocv((void **)&w->xp[l], sizeof(float) * (size_t)w->xp_slots * w->Tc * w->Npad * H);
     }
     allocv(&w->fc_wbuf, xproj_tc_w_bytes(H, 32) + 1024);
     allocv((void **)&w->fc_b_pad, sizeof(float) * 32);
@@ -252,13 +257,14 @@ int wave_set_weights(gasr_asr *a, const float *fc_w, const float *fc_b) {
 }
 
 // one launch of the persistent tile engine over the rows [row0, row0 + rows) of a layer's A planes
-static int wave_gemm(gasr_asr *a, int target, int row0, int rows, cudaStream_t st) {
+static int wave_gemm(gasr_asr *a, int target, int ci, int row0, int rows, cudaStream_t st) {
     gasr_ctx *ctx = a->ctx;
     WaveState *w = a->wave;
     const gasr_asr_config &c = a->cfg;
     const int L = c.L, H = c.H;
     if (target < L && ctx->opt.gemm_pair && gemm_pair_supported(ctx, rows, H))
-        return launch_gemm_pair(ctx, w->pmaps[target].m, row0, rows, target == 0 ? c.in : H, H, w->xp[target] + (size_t)row0 * H, H,
+        return launch_gemm_pair(ctx, w->pmaps[target].m, row0, rows, target == 0 ? c.in : H, H,
+                                w->xp[target] + (size_t)(ci % w->xp_slots) * w->Tc * w->Npad * H, H,
                                 w->bias_all + (size_t)target * H, c.precision, st);
     XsParams p = {};
     p.M = rows; p.row0 = row0; p.n_blocks = ceil_div(rows, TC_BM); p.n_targets = 1;
@@ -273,7 +279,7 @@ static int wave_gemm(gasr_asr *a, int target, int row0, int rows, cudaStream_t s
         p.wide = bn == 256;
         t.kind = XS_KIND_XPROJ; t.n_tiles = H / bn; t.bn = bn; t.V = 0;
         t.kblocks = ceil_div(K, TC_BK); t.terms = c.precision == GASR_PREC_BF16 ? 1 : 3;
-        t.C = w->xp[target] + (size_t)row0 * H; t.ldc = H; t.bias = w->bias_all + (size_t)target * H;
+        t.C = w->xp[target] + (size_t)(ci % w->xp_slots) * w->Tc * w->Npad * H; t.ldc = H; t.bias = w->bias_all + (size_t)target * H;
     } else {
         t.kind = XS_KIND_LOGSOFTMAX; t.n_tiles = 1; t.bn = 32; t.V = c.V; t.kblocks = H / TC_BK; t.terms = 3;
         t.C = w->logp + (size_t)row0 * 32; t.ldc = 32; t.bias = w->fc_b_pad;
@@ -338,13 +344,16 @@ int wave_submit(gasr_asr *a, const float *x_dev, const float *x_host) {
         // ---- layers: projection GEMM, then the recurrence ---------------------------------------------------------------
         for (int l = 0; l < L; l++) {
             GASR_CUDA(cudaStreamWaitEvent(w->st_g[l], l == 0 ? w->ev_in[ci] : w->ev_r[l - 1][ci], 0));
+            if (ci >= w->xp_slots) GASR_CUDA(cudaStreamWaitEvent(w->st_g[l], w->ev_r[l][ci - w->xp_slots], 0));   // the xproj slot is free again
             GASR_TRY(timed_begin(0, w->st_g[l]));
-            GASR_TRY(wave_gemm(a, l, row0, rows, w->st_g[l]));
+            GASR_TRY(wave_gemm(a, l, ci, row0, rows, w->st_g[l]));
             GASR_TRY(timed_end(w->st_g[l]));
             GASR_CUDA(cudaEventRecord(w->ev_g[l][ci], w->st_g[l]));
             GASR_CUDA(cudaStreamWaitEvent(w->st_r[l], w->ev_g[l][ci], 0));
             RnnWideRun r = {};
-            r.s0 = f0; r.s1 = f1; r.xp = w->xp[l]; r.ldxp = c.H; r.xp_rows_per_frame = Npad;
+            // the kernels address xproj as row t * Npad + n: bias the slot's base so that frame f0 lands on its first row
+            r.s0 = f0; r.s1 = f1; r.ldxp = c.H; r.xp_rows_per_frame = Npad;
+            r.xp = w->xp[l] + ((ptrdiff_t)(ci % w->xp_slots) * w->Tc - (ptrdiff_t)f0) * (ptrdiff_t)Npad * c.H;
             r.out = nullptr; r.groups_per_cluster = ctx->opt.rnn_groups; r.multicast = ctx->opt.rnn_mc;
             GASR_TRY(timed_begin(1, w->st_r[l]));
             GASR_TRY(w->pair ? launch_rnn_wide2(ctx, w->rec[l], r, w->st_r[l]) : launch_rnn_wide(ctx, w->rec[l], r, w->st_r[l]));
@@ -354,7 +363,7 @@ int wave_submit(gasr_asr *a, const float *x_dev, const float *x_host) {
         // ---- output layer + log-softmax, decode ---------------------------------------------------------------------------
         GASR_CUDA(cudaStreamWaitEvent(w->st_fc, w->ev_r[L - 1][ci], 0));
         GASR_TRY(timed_begin(2, w->st_fc));
-        GASR_TRY(wave_gemm(a, L, row0, rows, w->st_fc));
+        GASR_TRY(wave_gemm(a, L, ci, row0, rows, w->st_fc));
         GASR_TRY(timed_end(w->st_fc));
         GASR_CUDA(cudaEventRecord(w->ev_fc[ci], w->st_fc));
         GASR_CUDA(cudaStreamWaitEvent(w->st_dec, w->ev_fc[ci], 0));
@@ -375,6 +384,34 @@ int wave_collect(gasr_asr *a, char *out_paths, int *out_lens, float *out_scores)
     WaveState *w = a->wave;
     GASR_CHECK(w->pending, "gasr_asr: no batch in flight");
     w->pending = false;
+    {
+        // Bounded wait: a pipeline that stops making progress becomes an error that names the stuck stages, not a hung process.
+        const auto t_begin = std::chrono::steady_clock::now();
+        const double limit_s = ctx->opt.wave_timeout_s;
+        cudaError_t q;
+        unsigned spins = 0;
+        while ((q = cudaEventQuery(w->ev_t1)) == cudaErrorNotReady) {
+            if ((++spins & 63u) == 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count() > limit_s) {
+                std::string busy;
+                auto probe = [&](const char *name, int l, cudaStream_t s) {
+                    if (cudaStreamQuery(s) == cudaErrorNotReady) { busy += name; if (l >= 0) busy += std::to_string(l); busy += ' '; }
+                };
+                probe("input", -1, w->st_in);
+                for (int l = 0; l < a->cfg.L; l++) { probe("gemm", l, w->st_g[l]); probe("recurrence", l, w->st_r[l]); }
+                probe("output-layer", -1, w->st_fc); probe("decoder", -1, w->st_dec);
+                // first chunk whose event has not completed, per stage: the op that is stuck (or waiting for the stuck one)
+                auto first_open = [&](const std::vector<cudaEvent_t> &ev) { int ci = 0; while (ci < (int)ev.size() && cudaEventQuery(ev[ci]) == cudaSuccess) ci++; return ci; };
+                busy += "| first incomplete chunk: input " + std::to_string(first_open(w->ev_in));
+                for (int l = 0; l < a->cfg.L; l++)
+                    busy += " gemm" + std::to_string(l) + " " + std::to_string(first_open(w->ev_g[l])) + " recurrence" + std::to_string(l) + " " + std::to_string(first_open(w->ev_r[l]));
+                busy += " output-layer " + std::to_string(first_open(w->ev_fc)) + " of " + std::to_string(w->C);
+                set_error("wave engine: no completion after %.0f s; streams still busy: %s", limit_s, busy.c_str());
+                return GASR_ERR_CUDA;
+            }
+            if (spins > 256) std::this_thread::sleep_for(std::chrono::microseconds(50));
+        }
+        if (q != cudaSuccess) { set_error("wave engine: %s", cudaGetErrorString(q)); return GASR_ERR_CUDA; }
+    }
     GASR_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&w->last_ms, w->ev_t0, w->ev_t1);
     for (int i = 0; i < 4; i++) { a->stage_ms[i] = 0.0f; a->stage_launches[i] = 0; }

@@ -64,8 +64,9 @@ struct gasr_options {
     int stream_gemm_ctas = 24;
     int rnn_nsub = -1;
     int gemm_stages = 3;     // GASR_GEMM_STAGES: ring depth of the wave engine's GEMM launches (2 or 3)
-    int gemm_pair = 1;       // GASR_GEMM_PAIR: projection GEMMs on CTA pairs (256 x 256 tiles) when the chunk has whole tiles
+    int gemm_pair = 0;       // GASR_GEMM_PAIR: projection GEMMs on CTA pairs (256 x 256 tiles); opt-in, see DESIGN.md 4.2
     int gemm_bn = 256;       // GASR_GEMM_BN: tile width of the wave engine's projection GEMMs (128 or 256)
+    int wave_timeout_s = 60;  // GASR_WAVE_TIMEOUT_S: a batch that has not completed after this many seconds is reported as an error
     bool wave_serial = false; // GASR_WAVE_SERIAL: diagnostic, all stages of the wave engine on one stream
     int ctc_warps = 8;       // GASR_CTC_WARPS: utterances (warps) per decoder CTA in the wave engine (0: balanced automatically)
 };

@@ -713,8 +713,9 @@ struct WarpBeam {
     float pairmm[BMAX / 2][32];   // merged scores of twin pairs (X,0)+(X,1), [pair][vocab id]
     int pair_i[BMAX / 2], pair_tw[BMAX / 2];
     int order[32];            // order[j] = vocab id with the j-th largest score this frame
-    unsigned surv_key[64];    // prune survivors (candidates >= the lower bound), in candidate-index order
+    unsigned surv_key[68];    // prune survivors (candidates >= the lower bound), in candidate-index order (+ zero padding)
     int surv_iv[64];          // parent rank << 8 | vocab id
+    int pad_[3];              // keeps sizeof a multiple of 16 (the beam is parked with int4 copies)
 };
 
 // the character at 0-based position pos of the label string of trie node nd (depth(nd) > pos); rare path
@@ -996,6 +997,7 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
             if (sv && pos < 64) { wb.surv_key[pos] = key; wb.surv_iv[pos] = (i << 8) | lane; }
             ns += __popc(mask);
         }
+        if (lane < 4 && ns <= 64) wb.surv_key[ns + lane] = 0u;   // pad for the four-at-a-time ranking below
         __syncwarp();
         stat_surv += ns;
         stat_fallback += ns > 64;
@@ -1009,16 +1011,23 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
                     const int iv = wb.surv_iv[sidx];
                     const int mi = iv >> 8, mv = iv & 0xff;
                     const int ms = cand_suffix_id(mv, blank, pk[mi]);
+                    // four keys per iteration (the list is zero-padded to a multiple of four: real keys are > 0); an exact tie
+                    // (rare) takes the raw-string order from the relation matrix
                     int rank = 0;
-                    for (int o = 0; o < ns; o++) {
-                        const unsigned ok = wb.surv_key[o];
-                        if (ok > key) rank++;
-                        else if (ok == key && o != sidx) {
-                            if (t == 0) rank += o < sidx;
-                            else {
-                                const int oiv = wb.surv_iv[o];
-                                const int oi = oiv >> 8, ov = oiv & 0xff;
-                                rank += cand_less_rel(rel[oi][mi], cand_suffix_id(ov, blank, pk[oi]), ms, vch) ? 1 : 0;
+                    for (int o = 0; o < ns; o += 4) {
+                        const uint4 k4 = *reinterpret_cast<const uint4 *>(&wb.surv_key[o]);
+                        rank += (k4.x > key) + (k4.y > key) + (k4.z > key) + (k4.w > key);
+                        if (k4.x == key || k4.y == key || k4.z == key || k4.w == key) {
+                            const unsigned kk[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                if (kk[j] != key || o + j == sidx || o + j >= ns) continue;
+                                if (t == 0) rank += o + j < sidx;
+                                else {
+                                    const int oiv = wb.surv_iv[o + j];
+                                    const int oi = oiv >> 8, ov = oiv & 0xff;
+                                    rank += cand_less_rel(rel[oi][mi], cand_suffix_id(ov, blank, pk[oi]), ms, vch) ? 1 : 0;
+                                }
                             }
                         }
                     }
@@ -1098,9 +1107,13 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
             }
         }
         // ---- prefix relations of the new kept states from the old ones ----------------------------------------
-        for (int e = lane; e < BMAX * BMAX; e += 32) {
-            const int r = e / BMAX, q = e % BMAX;
-            if (r >= m || q >= m) continue;
+        // The relation is antisymmetric (rel[q][r] = mirror of rel[r][q]): every unordered pair is evaluated once -- pair
+        // (r, (r + d) mod BMAX) for d = 1 .. BMAX/2 (d = BMAX/2 only from the lower half) -- and written to both cells.
+        if (lane < m) wb.rel[nxt][lane][lane] = REL_EQ;
+        for (int e = lane; e < BMAX * (BMAX / 2); e += 32) {
+            const int r = e / (BMAX / 2), d = e % (BMAX / 2) + 1;
+            const int q = (r + d) & (BMAX - 1);
+            if (r >= m || q >= m || (d == BMAX / 2 && r >= BMAX / 2)) continue;
             const int ar = wb.seli[r], aq = wb.seli[q];
             const int er = cand_ext_id(wb.selv[r], blank, pk[ar]);
             const int eq2 = cand_ext_id(wb.selv[q], blank, pk[aq]);
@@ -1129,6 +1142,7 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
                 else out = REL_RPFX + trie_char_at(parent, meta, node[ar], dB + 1);
             }
             wb.rel[nxt][r][q] = (unsigned char)out;
+            wb.rel[nxt][q][r] = (unsigned char)(out < REL_PFX ? (out == REL_EQ ? REL_EQ : (REL_LT + REL_GT) - out) : (out < REL_RPFX ? out + 32 : out - 32));
         }
         kept = m;
         cur = nxt;
@@ -2442,13 +2456,7 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
         }
     } else if (fast) {
         // warp-per-utterance fast path; few warps per CTA when utterances are scarce (latency), 8 when plentiful
-        // utterances (warps) per CTA: the smallest k whole CTAs per SM that keeps a CTA at <= 8 warps, so that every SM gets the
-        // same number of warps (2048 utterances on 148 SMs: 293 CTAs of 7 warps = 2 per SM, not 256 of 8 = 1 or 2 per SM)
-        int W = 8;
-        for (int k = 1; k <= 64; k++) {
-            W = ceil_div(a.N, ctx->sm_count * k);
-            if (W <= 8) break;
-        }
+        int W = ceil_div(a.N, ctx->sm_count);
         if (W > 8) W = 8;
         if (a.warps_per_cta >= 1 && a.warps_per_cta <= 8) W = a.warps_per_cta;
         const int blocks = ceil_div(a.N, W);

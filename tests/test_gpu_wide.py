@@ -76,3 +76,33 @@ def test_wide_recurrence_cta_pairs_vs_oracle(gasr, O, monkeypatch, groups, H, N,
     for l in range(L):
         err = np.abs(out[l] - ref[l]).max()
         assert err < AM_TOL, f"layer {l}: {err}"
+
+
+def _same(gp, gs, op, os_):
+    assert gp == op
+    a, b = np.array(gs, dtype=np.float32), np.array(os_, dtype=np.float32)
+    assert (a.view(np.uint32) == b.view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("V,beam,T,N", [(29, 16, 120, 40), (29, 32, 60, 24), (29, 8, 200, 33), (5, 3, 90, 16), (32, 32, 40, 12),
+                                        (29, 1, 50, 8), (4, 9, 30, 8)])
+def test_warp_decoder_vs_oracle(gasr, O, monkeypatch, V, beam, T, N):
+    """The throughput decoder (one warp per utterance: what batches of > 296 utterances use) forced on small batches:
+    random log-probabilities, heavily quantised ones (exact score ties every frame -> raw-string tie-breaks through the
+    prefix-relation matrix) and the probability domain; transcripts and fp32 scores bit-exact against the oracle."""
+    import synth
+    monkeypatch.setenv("GASR_CTC_KERNEL", "w")
+    ctx = gasr.Context(0)
+    vocab = synth.VOCAB29 if V == 29 else bytes(range(1, V + 1))
+    rng = np.random.default_rng(V * 100 + beam)
+    logits = rng.normal(size=(T, N, V)).astype(np.float32) * 2.0
+    lp = (logits - np.log(np.exp(logits.astype(np.float64)).sum(-1, keepdims=True))).astype(np.float32)
+    cases = [("log", lp), ("log", (np.round(lp * 2.0) / 2.0).astype(np.float32))]          # second: many exact ties
+    p = np.exp(lp[:24].astype(np.float64)); p = (p / p.sum(-1, keepdims=True)).astype(np.float32)
+    cases.append(("prob", p))
+    for dom, x in cases:
+        x = np.ascontiguousarray(x)
+        gp, gs = ctx.ctc_decode_host(x, gasr.DOMAIN_LOG if dom == "log" else gasr.DOMAIN_PROB, beam, 0, vocab)
+        op, os_ = O.ctc_decode(x, vocab, 0, beam, domain=dom, nthreads=8)
+        _same(gp, gs, op, os_)
+    ctx.close()
