@@ -64,6 +64,11 @@ struct gasr_asr {
     // wave engine (asr_wave.cu): throughput mode, stream-ordered time chunks over groups of 128 utterances
     gasr::WaveState *wave = nullptr;
     bool profile = false;                       // per-launch stage timing (adds two event records per launch)
+    // decoder options of baseline/main.py:45-46 (decoder.decode(output, out_lens) -> ..., timesteps, out_seq_len)
+    int *lens_dev = nullptr;                    // frames per utterance [N] (null: every utterance has T frames)
+    bool want_ts = false;                       // per-token timesteps
+    std::vector<int> ts_host;                   // [N, nbest, max_len] of the last run
+    void decode_extras(gasr::CtcArgs &ca) { ca.lens_dev = lens_dev; ca.out_timesteps = want_ts ? ts_host.data() : nullptr; }
 };
 
 namespace gasr {
@@ -76,6 +81,7 @@ int wave_set_weights(gasr_asr *a, const float *fc_w_host, const float *fc_b_host
 int wave_submit(gasr_asr *a, const float *x_dev, const float *x_host);   // enqueue one batch; returns without waiting
 int wave_collect(gasr_asr *a, char *out_paths, int *out_lens, float *out_scores);   // wait + unpack the results
 int wave_logprobs(gasr_asr *a, const float **logp_dev, int *ldp);
+int wave_refresh_decoder(gasr_asr *a);           // decoder workspaces after lengths / timesteps were switched on
 int wave_chunk_frames(const gasr_asr *a);
 float wave_last_ms(const gasr_asr *a);
 

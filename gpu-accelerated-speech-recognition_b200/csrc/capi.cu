@@ -113,7 +113,7 @@ int gasr_ctx_create(int device, gasr_ctx **out) {
         gasr_options &o = ctx->opt;
         auto chr = [](const char *n) -> char { const char *e = getenv(n); return e ? e[0] : (char)0; };
         auto num = [](const char *n, int dflt) -> int { const char *e = getenv(n); return e ? atoi(e) : dflt; };
-        o.rnn = chr("GASR_RNN"); o.rnn_mc = num("GASR_RNN_MC", 1); o.rnn_groups = num("GASR_RNN_G", 2); o.rnn_pair = num("GASR_RNN_PAIR", 1);
+        o.rnn = chr("GASR_RNN"); o.rnn_mc = num("GASR_RNN_MC", 1); o.rnn_groups = num("GASR_RNN_G", 0); o.rnn_pair = num("GASR_RNN_PAIR", 1);
         o.ctc_kernel = chr("GASR_CTC_KERNEL"); o.ctc_mw = num("GASR_CTC_MW", 8); o.ctc_pad = num("GASR_CTC_PAD", 0);
         o.gru = chr("GASR_GRU"); o.gru_no_pdl = getenv("GASR_GRU_NO_PDL") != nullptr; o.no_graph = getenv("GASR_NO_GRAPH") != nullptr;
         o.bidir_serial = getenv("GASR_BIDIR_SERIAL") != nullptr; o.linear_simt = getenv("GASR_LINEAR_SIMT") != nullptr;
@@ -144,7 +144,7 @@ int gasr_ctx_destroy(gasr_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->dev_blocks) cudaFree(kv.first);
     for (auto &kv : ctx->host_blocks) cudaFreeHost(kv.first);
-    Workspace *wss[] = {&ctx->ws_ctc, &ctx->ws_rnn, &ctx->ws_misc, &ctx->ws_out, &ctx->ws_gru, &ctx->ws_lin, &ctx->ws_rnn_b, &ctx->ws_misc_b, &ctx->ws_gru_b, &ctx->ws_wide};
+    Workspace *wss[] = {&ctx->ws_ctc, &ctx->ws_rnn, &ctx->ws_misc, &ctx->ws_out, &ctx->ws_gru, &ctx->ws_lin, &ctx->ws_lens, &ctx->ws_rnn_b, &ctx->ws_misc_b, &ctx->ws_gru_b, &ctx->ws_wide};
     for (cudaEvent_t e : ctx->ev_bi) if (e) cudaEventDestroy(e);
     for (auto &g : ctx->step_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (Workspace *w : wss) if (w->ptr) cudaFree(w->ptr);
@@ -458,15 +458,30 @@ int gasr_rnn_forward(gasr_ctx *ctx, int cell, int bidirectional, int T, int N, i
                             ctx->stream);
 }
 
-int gasr_ctc_decode(gasr_ctx *ctx, const float *scores, int domain, int T, int N, int V, int ld, int beam, int blank,
-                    const char *vocab, int max_len, int nbest, char *out_paths, int *out_lens, float *out_scores,
-                    int *out_counts) {
+int gasr_ctc_decode_ex(gasr_ctx *ctx, const float *scores, int domain, int T, int N, int V, int ld, int beam, int blank,
+                       const char *vocab, int max_len, int nbest, const int *lens_host, char *out_paths, int *out_lens,
+                       float *out_scores, int *out_counts, int *out_timesteps) {
     GASR_ENTER(ctx);
     GASR_CHECK(out_paths && out_lens && out_scores, "ctc_decode: null output buffer");
     CtcArgs a = {scores, domain, T, N, V, ld, beam, blank, vocab, max_len, nbest, out_paths, out_lens, out_scores, out_counts};
+    a.out_timesteps = out_timesteps;
+    if (lens_host != nullptr && N > 0) {
+        for (int n = 0; n < N; n++)
+            GASR_CHECK(lens_host[n] >= 1 && lens_host[n] <= T, "ctc_decode: length %d of utterance %d outside 1..T=%d", lens_host[n], n, T);
+        GASR_TRY(ws_reserve(ctx, ctx->ws_lens, sizeof(int) * (size_t)N));
+        GASR_CUDA(cudaMemcpyAsync(ctx->ws_lens.ptr, lens_host, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+        a.lens_dev = static_cast<const int *>(ctx->ws_lens.ptr);
+    }
     GASR_TRY(ctc_decode_launch(ctx, a, ctx->stream));
     GASR_CUDA(cudaStreamSynchronize(ctx->stream));
     return ctc_decode_finish(ctx, a);
+}
+
+int gasr_ctc_decode(gasr_ctx *ctx, const float *scores, int domain, int T, int N, int V, int ld, int beam, int blank,
+                    const char *vocab, int max_len, int nbest, char *out_paths, int *out_lens, float *out_scores,
+                    int *out_counts) {
+    return gasr_ctc_decode_ex(ctx, scores, domain, T, N, V, ld, beam, blank, vocab, max_len, nbest, nullptr, out_paths, out_lens,
+                              out_scores, out_counts, nullptr);
 }
 
 int gasr_ctc_decode_host(gasr_ctx *ctx, const float *scores_host, int domain, int T, int N, int V, int beam, int blank,
@@ -598,6 +613,7 @@ int gasr_asr_destroy(gasr_asr *a) {
     for (auto v : {&a->w_ih, &a->w_hh, &a->b_ih, &a->b_hh, &a->hiddens})
         for (float *p : *v) if (p) gasr_free_device(ctx, p);
     for (float *p : {a->fc_w, a->fc_b, a->x_dev, a->logp, a->xproj_all, a->bias_all}) if (p) gasr_free_device(ctx, p);
+    if (a->lens_dev) gasr_free_device(ctx, a->lens_dev);
     for (void *p : a->tc_abuf) if (p) gasr_free_device(ctx, p);
     for (void *p : a->tc_wbuf) if (p) gasr_free_device(ctx, p);
     for (void *p : a->h_planes) if (p) gasr_free_device(ctx, p);
@@ -684,6 +700,7 @@ static int asr_run_sequential(gasr_asr *a, const float *x_dev, char *out_paths, 
     GASR_TRY(a->prof.mark(2, st));
     CtcArgs ca = {a->logp, GASR_DOMAIN_LOG, c.T, c.N, c.V, a->ldp, c.beam, c.blank, a->vocab.data(), c.max_len,
                   c.nbest, out_paths, out_lens, out_scores, nullptr};
+    a->decode_extras(ca);
     GASR_TRY(ctc_decode_launch(ctx, ca, st));
     GASR_TRY(a->prof.mark(3, st));
     GASR_CUDA(cudaStreamSynchronize(st));
@@ -734,6 +751,7 @@ static int asr_run_pipelined(gasr_asr *a, const float *x_dev, char *out_paths, i
         GASR_TRY(launch_matadd(ctx, a->b_ih[l], H, a->b_hh[l], H, a->bias_all + (size_t)l * H, H, 1, H, 1.0f, layer_stream(l)));
     CtcArgs ca = {a->logp, GASR_DOMAIN_LOG, T, N, c.V, a->ldp, c.beam, c.blank, a->vocab.data(), c.max_len,
                   c.nbest, out_paths, out_lens, out_scores, nullptr};
+    a->decode_extras(ca);
     for (int ci = 0; ci < C; ci++) {
         const int f0 = ci * Tc, f1 = (ci + 1) * Tc < T ? (ci + 1) * Tc : T;
         const size_t row0 = (size_t)f0 * N;
@@ -811,6 +829,7 @@ static int asr_run_streaming(gasr_asr *a, const float *x_dev, const float *x_hos
     // kernel starts: once they run they wait for each other, not for the host
     CtcArgs ca = {a->logp, GASR_DOMAIN_LOG, T, N, c.V, a->ldp, c.beam, c.blank, a->vocab.data(), c.max_len,
                   c.nbest, out_paths, out_lens, out_scores, nullptr};
+    a->decode_extras(ca);
     GASR_TRY(ctc_decode_reserve(ctx, ca));
     {
         XsParams prep = {};
@@ -1102,6 +1121,42 @@ int gasr_asr_collect(gasr_asr *a, char *out_paths, int *out_lens, float *out_sco
     GASR_ENTER(a->ctx);
     if (!a->wave) { set_error("gasr_asr_collect: nothing was submitted"); return GASR_ERR_INVALID; }
     return wave_collect(a, out_paths, out_lens, out_scores);
+}
+
+int gasr_asr_set_lengths(gasr_asr *a, const int *lens_host) {
+    GASR_CHECK(a != nullptr, "null gasr_asr");
+    gasr_ctx *ctx = a->ctx;
+    GASR_ENTER(ctx);
+    const gasr_asr_config &c = a->cfg;
+    if (lens_host == nullptr) {
+        if (a->lens_dev) { GASR_CUDA(cudaStreamSynchronize(ctx->stream)); gasr_free_device(ctx, a->lens_dev); a->lens_dev = nullptr; }
+        return GASR_OK;
+    }
+    GASR_CHECK(!c.bidirectional, "gasr_asr_set_lengths: a bidirectional stack would read the padding frames (pack the batch by length instead)");
+    for (int n = 0; n < c.N; n++)
+        GASR_CHECK(lens_host[n] >= 1 && lens_host[n] <= c.T, "gasr_asr_set_lengths: length %d of utterance %d outside 1..T=%d", lens_host[n], n, c.T);
+    if (!a->lens_dev) GASR_TRY(gasr_malloc_device(ctx, sizeof(int) * (size_t)c.N, (void **)&a->lens_dev));
+    GASR_CUDA(cudaMemcpyAsync(a->lens_dev, lens_host, sizeof(int) * (size_t)c.N, cudaMemcpyHostToDevice, ctx->stream));
+    GASR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GASR_OK;
+}
+
+int gasr_asr_enable_timesteps(gasr_asr *a, int on) {
+    GASR_CHECK(a != nullptr, "null gasr_asr");
+    gasr_ctx *ctx = a->ctx;
+    GASR_ENTER(ctx);
+    const gasr_asr_config &c = a->cfg;
+    a->want_ts = on != 0;
+    if (a->want_ts) a->ts_host.assign((size_t)c.N * c.nbest * c.max_len, 0);
+    if (a->wave) GASR_TRY(wave_refresh_decoder(a));
+    return GASR_OK;
+}
+
+int gasr_asr_timesteps(gasr_asr *a, int *out_timesteps) {
+    GASR_CHECK(a != nullptr && out_timesteps != nullptr, "gasr_asr_timesteps: null argument");
+    GASR_CHECK(a->want_ts, "gasr_asr_timesteps: call gasr_asr_enable_timesteps(asr, 1) before the run");
+    memcpy(out_timesteps, a->ts_host.data(), sizeof(int) * a->ts_host.size());
+    return GASR_OK;
 }
 
 int gasr_asr_profile(gasr_asr *a, int on) {

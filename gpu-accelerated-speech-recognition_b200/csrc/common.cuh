@@ -50,7 +50,7 @@ struct Workspace {
 struct gasr_options {
     char rnn = 0;            // GASR_RNN: w = wide tcgen05 recurrence, f / m / ... = the round-1 kernels (first letter)
     int rnn_mc = 1;          // GASR_RNN_MC: TMA multicast of the h boxes in the wide recurrence
-    int rnn_groups = 2;      // GASR_RNN_G: groups of utterances per cluster (1 or 2)
+    int rnn_groups = 0;      // GASR_RNN_G: groups of utterances per cluster (1 or 2; 0 = by batch size)
     int rnn_pair = 1;        // GASR_RNN_PAIR: CTA-pair recurrence (tcgen05.mma.cta_group::2, groups of 256 utterances)
     char ctc_kernel = 0;     // GASR_CTC_KERNEL
     int ctc_mw = 8;          // GASR_CTC_MW
@@ -83,7 +83,7 @@ struct gasr_ctx {
     long long launches = 0;
     size_t device_bytes = 0, host_bytes = 0;
     std::map<void *, size_t> dev_blocks, host_blocks;
-    gasr::Workspace ws_ctc, ws_rnn, ws_misc, ws_out, ws_gru, ws_lin;
+    gasr::Workspace ws_ctc, ws_rnn, ws_misc, ws_out, ws_gru, ws_lin, ws_lens;
     gasr::Workspace ws_wide;             // planes + W_hh^T planes of the wide recurrence (C-ABI path)
     gasr::Workspace ws_rnn_b, ws_misc_b, ws_gru_b;   // second set: the backward direction of a bidirectional layer runs concurrently
     int ws_sel = 0;                      // which set the recurrent-layer helpers use (0 / 1)
@@ -167,6 +167,8 @@ struct CtcArgs {
     bool vocab_resident = false;   // the vocabulary was uploaded by ctc_decode_upload_vocab
     int frame_rows = 0;            // rows of `scores` per frame (0: N)
     int warps_per_cta = 0;         // warp kernel: utterances per CTA (0: automatic)
+    const int *lens_dev = nullptr; // frames per utterance (device, N ints; null: all T) -- baseline/main.py:45-46 out_lens
+    int *out_timesteps = nullptr;  // host [N, nbest, max_len]: frame at which each output token's prefix first entered the beam (null: not wanted)
 };
 int ctc_decode_reserve(gasr_ctx *ctx, const CtcArgs &a);                  // allocations only (device-synchronising)
 int ctc_decode_upload_vocab(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st);

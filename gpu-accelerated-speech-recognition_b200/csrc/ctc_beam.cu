@@ -106,6 +106,9 @@ struct CtcParams {
     const float *scores;
     int T, N, V, ld, beam, blank;
     int frame_rows; // rows of `scores` per frame (>= N; the wave engine pads the batch to whole groups of 128)
+    int *born;       // [N, cap] frame at which a trie node was created (null: per-token timesteps not wanted)
+    int *out_ts;     // [N, nbest, max_len] frame at which each output token's prefix first entered the beam (null: not wanted)
+    const int *lens; // per-utterance frame counts (device, N entries, clamped to 1..T); null = every utterance has T frames
     int Vp;        // child-table row pitch (ints)
     int n_pad;     // power of two >= beam * V
     int cap;       // trie nodes per utterance
@@ -133,6 +136,14 @@ struct CtcParams {
     int *error;
     volatile unsigned *abort;
 };
+
+// frames of utterance `utt` (baseline/main.py:45-46 passes out_lens to its decoder): decoding stops after Tu frames and the
+// last-frame rule (trailing blank stripped, CTCBeamSearch.cu:452-456) applies at frame Tu - 1
+__device__ __forceinline__ int utt_frames(const CtcParams &p, int utt) {
+    if (p.lens == nullptr) return p.T;
+    const int n = p.lens[utt];
+    return n < 1 ? 1 : (n > p.T ? p.T : n);
+}
 
 constexpr int kNone = -1;
 constexpr uint16_t kNoRedir = 0xffffu;
@@ -274,6 +285,7 @@ __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
 
     int *parent = p.parent + (size_t)utt * p.cap;
     int *meta = p.meta + (size_t)utt * p.cap;
+    int *born = p.born ? p.born + (size_t)utt * p.cap : nullptr;
     int *child = p.child + (size_t)utt * p.cap * Vp;
     const float *S = p.scores + (size_t)utt * p.ld;
     const size_t frame_stride = (size_t)p.frame_rows * p.ld;
@@ -295,16 +307,17 @@ __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
     __syncthreads();
 
     int cur = 0;
-    for (int t = 0; t < p.T; t++) {
+    const int Tu = utt_frames(p, utt);
+    for (int t = 0; t < Tu; t++) {
         const BeamView st = beam_view(cur), nx = beam_view(cur ^ 1);
         const int k = s_kept;
         const int ncand = k * V;
-        const bool last_frame = (t == p.T - 1) && (t > 0);
+        const bool last_frame = (t == Tu - 1) && (t > 0);
 
         // ---- A: this frame's scores to smem, prefetch the next row, beam-level relations ----------------
         if (tid < V) {
             lp[tid] = next_lp;
-            if (t + 1 < p.T) next_lp = S[(size_t)(t + 1) * frame_stride + tid];
+            if (t + 1 < Tu) next_lp = S[(size_t)(t + 1) * frame_stride + tid];
         }
         for (int c = tid; c < ncand; c += NT) { redir0[c] = kNoRedir; redir1[c] = kNoRedir; }
         if (tid == 0) { s_m = 0; s_lo = 0xffffffffu; s_hi = 0u; s_nv = 0u; }
@@ -643,6 +656,7 @@ __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
                 const int pn = st.node[my_i];
                 parent[nd] = pn;
                 meta[nd] = (((meta[pn] >> 8) + 1) << 8) | my_v;
+                if (born) born[nd] = t;
                 child[(size_t)pn * Vp + my_v] = nd;
                 int4 *row = reinterpret_cast<int4 *>(child + (size_t)nd * Vp);
                 for (int q = 0; q < Vp / 4; q++) row[q] = make_int4(0, 0, 0, 0);
@@ -661,6 +675,7 @@ __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
     if (tid == 0 && p.out_counts) p.out_counts[utt] = kept;
     for (int r = tid; r < p.nbest; r += NT) {
         char *out = p.out_paths + ((size_t)utt * p.nbest + r) * p.max_len;
+        int *ts = p.out_ts ? p.out_ts + ((size_t)utt * p.nbest + r) * p.max_len : nullptr;
         int len = 0;
         float sc = 0.0f;
         if (r < kept) {
@@ -668,9 +683,9 @@ __global__ void __launch_bounds__(MAXT) ctc_beam_kernel(const CtcParams p) {
             const int depth = meta[nd] >> 8;
             len = depth;
             // T == 1: the reference returns the initial path as is, blank included
-            if (p.T == 1 && st.eb[r]) { if (len < p.max_len) out[len] = vch[blank]; len += 1; }
+            if (Tu == 1 && st.eb[r]) { if (len < p.max_len) { out[len] = vch[blank]; if (ts) ts[len] = 0; } len += 1; }
             for (int pos = depth - 1; pos >= 0; pos--) {
-                if (pos < p.max_len) out[pos] = vch[meta[nd] & 0xff];
+                if (pos < p.max_len) { out[pos] = vch[meta[nd] & 0xff]; if (ts) ts[pos] = born[nd]; }
                 nd = parent[nd];
             }
             sc = st.score[r];
@@ -773,6 +788,7 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
 
     int *parent = p.parent + (size_t)utt * p.cap;
     int *meta = p.meta + (size_t)utt * p.cap;
+    int *born = p.born ? p.born + (size_t)utt * p.cap : nullptr;
     int *child = p.child + (size_t)utt * p.cap * Vp;
     const float *S = p.scores + (size_t)utt * p.ld;
     const size_t frame_stride = (size_t)p.frame_rows * p.ld;
@@ -784,6 +800,9 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
     int stat_surv = 0, stat_fallback = 0;
     int4 *gstate = reinterpret_cast<int4 *>(p.state + (size_t)utt * p.state_stride);
     constexpr int kStateVec = (int)(sizeof(WarpBeam<BMAX>) / sizeof(int4));
+    const int Tu = utt_frames(p, utt);
+    if (p.t0 > 0 && p.t0 >= Tu) return;                  // this utterance ended in an earlier chunk (its result is written)
+    const int t_end = p.t1 < Tu ? p.t1 : Tu;
     if (p.t0 == 0) {
         if (lane < Vp) child[lane] = 0;
         if (lane == 0) {
@@ -802,10 +821,10 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
     float lp_next = active ? S[(size_t)p.t0 * frame_stride + lane] : 0.0f;
     __syncwarp();
 
-    for (int t = p.t0; t < p.t1; t++) {
+    for (int t = p.t0; t < t_end; t++) {
         const float lp = lp_next;
-        if (t + 1 < p.t1 && active) lp_next = S[(size_t)(t + 1) * frame_stride + lane];
-        const bool last_frame = (t == p.T - 1) && (t > 0);
+        if (t + 1 < t_end && active) lp_next = S[(size_t)(t + 1) * frame_stride + lane];
+        const bool last_frame = (t == Tu - 1) && (t > 0);
         const int k = kept;
         const float *sc = wb.sc[cur];
         const int *node = wb.node[cur], *pk = wb.pk[cur], *depth = wb.depth[cur];
@@ -1096,6 +1115,7 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
                 nd = nodes + __popc(nb & ((1u << lane) - 1u));
                 parent[nd] = pn;
                 meta[nd] = (dp << 8) | v;
+                if (born) born[nd] = t;
                 child[(size_t)pn * Vp + v] = nd;
                 int4 *row = reinterpret_cast<int4 *>(child + (size_t)nd * Vp);
                 for (int q = 0; q < Vp / 4; q++) row[q] = make_int4(0, 0, 0, 0);
@@ -1149,7 +1169,7 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
         __syncwarp();
     }
 
-    if (p.t1 < p.T) {
+    if (p.t1 < Tu) {
         // more chunks follow: park the beam in HBM
         const int4 *src = reinterpret_cast<const int4 *>(&wb);
         for (int i = lane; i < kStateVec; i += 32) gstate[i] = src[i];
@@ -1168,15 +1188,16 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
     if (lane == 0 && p.out_counts) p.out_counts[utt] = kept;
     for (int r = lane; r < p.nbest; r += 32) {
         char *out = p.out_paths + ((size_t)utt * p.nbest + r) * p.max_len;
+        int *ts = p.out_ts ? p.out_ts + ((size_t)utt * p.nbest + r) * p.max_len : nullptr;
         int len = 0;
         float scv = 0.0f;
         if (r < kept) {
             int nd = wb.node[cur][r];
             const int dpt = wb.depth[cur][r];
             len = dpt;
-            if (p.T == 1 && ((wb.pk[cur][r] >> 8) & 1)) { if (len < p.max_len) out[len] = vch[blank]; len += 1; }
+            if (Tu == 1 && ((wb.pk[cur][r] >> 8) & 1)) { if (len < p.max_len) { out[len] = vch[blank]; if (ts) ts[len] = 0; } len += 1; }
             for (int pos = dpt - 1; pos >= 0; pos--) {
-                if (pos < p.max_len) out[pos] = vch[meta[nd] & 0xff];
+                if (pos < p.max_len) { out[pos] = vch[meta[nd] & 0xff]; if (ts) ts[pos] = born[nd]; }
                 nd = parent[nd];
             }
             scv = wb.sc[cur][r];
@@ -1260,12 +1281,16 @@ __global__ void __launch_bounds__(128) ctc_beam_cta_kernel(const CtcParams p) {
 
     int *parent = p.parent + (size_t)utt * p.cap;
     int *meta = p.meta + (size_t)utt * p.cap;
+    int *born = p.born ? p.born + (size_t)utt * p.cap : nullptr;
     int *child = p.child + (size_t)utt * p.cap * Vp;
     const float *S = p.scores + (size_t)utt * p.ld;
     const size_t frame_stride = (size_t)p.frame_rows * p.ld;
     int4 *gstate = reinterpret_cast<int4 *>(p.state + (size_t)utt * p.state_stride);
     constexpr int kStateVec = (int)(sizeof(CtaBeam<BMAX>) / sizeof(int4));
 
+    const int Tu = utt_frames(p, utt);
+    if (p.t0 > 0 && p.t0 >= Tu) return;                  // this utterance ended in an earlier chunk (its result is written)
+    const int t_end = p.t1 < Tu ? p.t1 : Tu;
     if (tid < V) vch_s[tid] = p.vocab[tid];
     int cur = 0;
     int stat_surv = 0, stat_fallback = 0;
@@ -1319,13 +1344,13 @@ __global__ void __launch_bounds__(128) ctc_beam_cta_kernel(const CtcParams p) {
     __syncthreads();
     int kept = cb.kept;
 
-    for (int t = p.t0; t < p.t1; t++) {
+    for (int t = p.t0; t < t_end; t++) {
         const float lp = lp_next;
-        if (t + 1 < p.t1) {
+        if (t + 1 < t_end) {
             if (streaming) frames_ready(t + 1);
             if (active) lp_next = __ldcg(S + (size_t)(t + 1) * frame_stride + lane);
         }
-        const bool last_frame = (t == p.T - 1) && (t > 0);
+        const bool last_frame = (t == Tu - 1) && (t > 0);
         const int k = kept;
         const float *sc = cb.sc[cur];
         const int *node = cb.node[cur], *pnode = cb.pnode[cur], *pk = cb.pk[cur], *depth = cb.depth[cur];
@@ -1629,6 +1654,7 @@ __global__ void __launch_bounds__(128) ctc_beam_cta_kernel(const CtcParams p) {
                 nd = nodes + __popc(nb & ((1u << lane) - 1u));
                 parent[nd] = pn;
                 meta[nd] = (dp << 8) | v;
+                if (born) born[nd] = t;
                 child[(size_t)pn * Vp + v] = nd;
                 int4 *row = reinterpret_cast<int4 *>(child + (size_t)nd * Vp);
                 for (int q = 0; q < Vp / 4; q++) row[q] = make_int4(0, 0, 0, 0);
@@ -1672,7 +1698,7 @@ __global__ void __launch_bounds__(128) ctc_beam_cta_kernel(const CtcParams p) {
         if (p.t0 == 0) { p.out_stats[2 * utt] = stat_fallback; p.out_stats[2 * utt + 1] = stat_surv; }
         else { p.out_stats[2 * utt] += stat_fallback; p.out_stats[2 * utt + 1] += stat_surv; }
     }
-    if (p.t1 < p.T) {
+    if (p.t1 < Tu) {
         const int4 *src = reinterpret_cast<const int4 *>(&cb);
         for (int i = tid; i < kStateVec; i += 128) gstate[i] = src[i];
         if (tid == 0) gstate[kStateVec] = make_int4(cur, 0, 0, 0);
@@ -1682,15 +1708,16 @@ __global__ void __launch_bounds__(128) ctc_beam_cta_kernel(const CtcParams p) {
     if (tid == 0 && p.out_counts) p.out_counts[utt] = kept;
     for (int r = tid; r < p.nbest; r += 128) {
         char *out = p.out_paths + ((size_t)utt * p.nbest + r) * p.max_len;
+        int *ts = p.out_ts ? p.out_ts + ((size_t)utt * p.nbest + r) * p.max_len : nullptr;
         int len = 0;
         float scv = 0.0f;
         if (r < kept) {
             int nd = cb.node[cur][r];
             const int dpt = cb.depth[cur][r];
             len = dpt;
-            if (p.T == 1 && ((cb.pk[cur][r] >> 8) & 1)) { if (len < p.max_len) out[len] = vch[blank]; len += 1; }
+            if (Tu == 1 && ((cb.pk[cur][r] >> 8) & 1)) { if (len < p.max_len) { out[len] = vch[blank]; if (ts) ts[len] = 0; } len += 1; }
             for (int pos = dpt - 1; pos >= 0; pos--) {
-                if (pos < p.max_len) out[pos] = vch[meta[nd] & 0xff];
+                if (pos < p.max_len) { out[pos] = vch[meta[nd] & 0xff]; if (ts) ts[pos] = born[nd]; }
                 nd = parent[nd];
             }
             scv = cb.sc[cur][r];
@@ -1750,7 +1777,7 @@ __global__ void __launch_bounds__(MW * 32 + 64) ctc_beam_cta2_kernel(const CtcPa
     __shared__ char vch_s[32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int utt = blockIdx.x;
-    const int V = p.V, B = p.beam, blank = p.blank, Vp = p.Vp, T = p.T;
+    const int V = p.V, B = p.beam, blank = p.blank, Vp = p.Vp, T = utt_frames(p, (int)blockIdx.x);   // this utterance's frames
     constexpr unsigned FULL = 0xffffffffu;
     const bool active = lane < V;
     const char *vch = vch_s;
@@ -1758,6 +1785,7 @@ __global__ void __launch_bounds__(MW * 32 + 64) ctc_beam_cta2_kernel(const CtcPa
 
     int *parent = p.parent + (size_t)utt * p.cap;
     int *meta = p.meta + (size_t)utt * p.cap;
+    int *born = p.born ? p.born + (size_t)utt * p.cap : nullptr;
     int *anc = p.anc + (size_t)utt * p.cap;
     int *child = p.child + (size_t)utt * p.cap * Vp;
     const float *S = p.scores + (size_t)utt * p.ld;
@@ -1857,6 +1885,7 @@ __global__ void __launch_bounds__(MW * 32 + 64) ctc_beam_cta2_kernel(const CtcPa
                 nd = nodes + __popc(nb & ((1u << lane) - 1u));
                 parent[nd] = pn;
                 meta[nd] = (dp << 8) | v;
+                if (born) born[nd] = t;
                 anc[nd] = an;
                 child[(size_t)pn * Vp + v] = nd;
                 int4 *row = reinterpret_cast<int4 *>(child + (size_t)nd * Vp);
@@ -1878,13 +1907,14 @@ __global__ void __launch_bounds__(MW * 32 + 64) ctc_beam_cta2_kernel(const CtcPa
         constexpr int ENDS_CAP = BMAX * 32;
         for (int r = 0; r < p.nbest; r++) {
             char *out = p.out_paths + ((size_t)utt * p.nbest + r) * p.max_len;
+            int *ts = p.out_ts ? p.out_ts + ((size_t)utt * p.nbest + r) * p.max_len : nullptr;
             int len = 0;
             float scv = 0.0f;
             if (r < kept) {
                 const int nd0 = cb.node[cur][r];
                 const int dpt = cb.depth[cur][r];
                 len = dpt;
-                if (T == 1 && ((cb.pk[cur][r] >> 8) & 1)) { if (lane == 0 && len < p.max_len) out[len] = vch[blank]; len += 1; }
+                if (T == 1 && ((cb.pk[cur][r] >> 8) & 1)) { if (lane == 0 && len < p.max_len) { out[len] = vch[blank]; if (ts) ts[len] = 0; } len += 1; }
                 const int nblk = (dpt + 31) >> 5;
                 if (nblk <= ENDS_CAP) {
                     if (lane == 0) {
@@ -1896,7 +1926,7 @@ __global__ void __launch_bounds__(MW * 32 + 64) ctc_beam_cta2_kernel(const CtcPa
                         int nd = ends[j];
                         const int top = min(dpt, 32 * (j + 1));
                         for (int pos = top - 1; pos >= 32 * j; pos--) {
-                            if (pos < p.max_len) out[pos] = vch[meta[nd] & 0xff];
+                            if (pos < p.max_len) { out[pos] = vch[meta[nd] & 0xff]; if (ts) ts[pos] = born[nd]; }
                             nd = parent[nd];
                         }
                     }
@@ -1904,7 +1934,7 @@ __global__ void __launch_bounds__(MW * 32 + 64) ctc_beam_cta2_kernel(const CtcPa
                 } else if (lane == 0) {
                     int nd = nd0;
                     for (int pos = dpt - 1; pos >= 0; pos--) {
-                        if (pos < p.max_len) out[pos] = vch[meta[nd] & 0xff];
+                        if (pos < p.max_len) { out[pos] = vch[meta[nd] & 0xff]; if (ts) ts[pos] = born[nd]; }
                         nd = parent[nd];
                     }
                 }
@@ -2293,7 +2323,7 @@ static size_t ctc_rel_bytes(int B) { return sizeof(unsigned short) * 2 * (size_t
 struct CtcLayout {
     int Vp, n_pad, cap, threads;
     size_t smem, off_vocab, off_parent, off_meta, off_anc, off_child, off_state, state_stride, off_paths, off_lens, off_scores,
-        off_counts, off_stats, total;
+        off_counts, off_stats, off_born, off_ts, total;
     size_t out_bytes;
 };
 
@@ -2314,6 +2344,7 @@ static int ctc_layout(const CtcArgs &a, CtcLayout &L) {
     L.off_child = o; o = align_up(o + sizeof(int) * (size_t)a.N * L.cap * L.Vp, 256);
     L.state_stride = align_up((sizeof(CtaBeam<32>) > sizeof(WarpBeam<32>) ? sizeof(CtaBeam<32>) : sizeof(WarpBeam<32>)) + sizeof(int4), 256);
     L.off_state = o; o = align_up(o + L.state_stride * (size_t)a.N, 256);
+    L.off_born = o; if (a.out_timesteps) o = align_up(o + sizeof(int) * (size_t)a.N * L.cap, 256);
     L.total = o;
     size_t q = 0;
     L.off_paths = q; q = align_up(q + (size_t)a.N * a.nbest * a.max_len, 256);
@@ -2321,6 +2352,7 @@ static int ctc_layout(const CtcArgs &a, CtcLayout &L) {
     L.off_scores = q; q = align_up(q + sizeof(float) * (size_t)a.N * a.nbest, 256);
     L.off_counts = q; q = align_up(q + sizeof(int) * (size_t)a.N, 256);
     L.off_stats = q; q = align_up(q + 2 * sizeof(int) * (size_t)a.N, 256);
+    L.off_ts = q; if (a.out_timesteps) q = align_up(q + sizeof(int) * (size_t)a.N * a.nbest * a.max_len, 256);
     L.out_bytes = q;
     return GASR_OK;
 }
@@ -2385,6 +2417,8 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
     if (t0 == 0 && !a.vocab_resident) GASR_CUDA(cudaMemcpyAsync(ws + L.off_vocab, a.vocab_host, a.V, cudaMemcpyHostToDevice, st));
 
     CtcParams p;
+    p.lens = a.lens_dev;
+    p.born = nullptr; p.out_ts = nullptr;
     p.scores = a.scores; p.T = a.T; p.N = a.N; p.V = a.V; p.ld = a.ld; p.beam = a.beam; p.blank = a.blank;
     p.frame_rows = a.frame_rows > 0 ? a.frame_rows : a.N;
     GASR_CHECK(p.frame_rows >= a.N, "ctc_decode: frame_rows %d < N %d", p.frame_rows, a.N);
@@ -2399,6 +2433,7 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
     p.out_scores = reinterpret_cast<float *>(wo + L.off_scores);
     p.out_counts = reinterpret_cast<int *>(wo + L.off_counts);
     p.out_stats = reinterpret_cast<int *>(wo + L.off_stats);
+    if (a.out_timesteps) { p.born = reinterpret_cast<int *>(ws + L.off_born); p.out_ts = reinterpret_cast<int *>(wo + L.off_ts); }
     if (!fast) GASR_CUDA(cudaMemsetAsync(p.out_stats, 0, 2 * sizeof(int) * (size_t)a.N, st));
     p.t0 = t0; p.t1 = t1; p.use_rel = general_rel ? 1 : 0;
     p.state = ws + L.off_state; p.state_stride = L.state_stride;
@@ -2424,7 +2459,8 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
             if (p.cell_i[c] < 32 && p.cell_j[c] < 32) p.cellmap[p.cell_i[c] * 32 + p.cell_j[c]] = (unsigned char)c;
     }
 
-    if (t1 == a.T) GASR_CUDA(cudaMemsetAsync(wo + L.off_paths, 0, (size_t)a.N * a.nbest * a.max_len, st));
+    if (t0 == 0) GASR_CUDA(cudaMemsetAsync(wo + L.off_paths, 0, (size_t)a.N * a.nbest * a.max_len, st));
+    if (t0 == 0 && a.out_timesteps) GASR_CUDA(cudaMemsetAsync(wo + L.off_ts, 0, sizeof(int) * (size_t)a.N * a.nbest * a.max_len, st));
     const bool whole = t0 == 0 && t1 == a.T;
     if (use_cta && whole && !(force_k && force_k[0] == 'c')) {
         // latency path, second generation: 8 main warps + fetch warp + trie warp per utterance, whole sequence.  No
@@ -2501,6 +2537,7 @@ int ctc_decode_finish(gasr_ctx *ctx, const CtcArgs &a) {
     memcpy(a.out_lens, h + L.off_lens, sizeof(int) * (size_t)a.N * a.nbest);
     memcpy(a.out_scores, h + L.off_scores, sizeof(float) * (size_t)a.N * a.nbest);
     if (a.out_counts) memcpy(a.out_counts, h + L.off_counts, sizeof(int) * (size_t)a.N);
+    if (a.out_timesteps) memcpy(a.out_timesteps, h + L.off_ts, sizeof(int) * (size_t)a.N * a.nbest * a.max_len);
     {
         const int *stt = reinterpret_cast<const int *>(h + L.off_stats);
         ctx->ctc_fallback_frames = 0; ctx->ctc_survivors = 0;

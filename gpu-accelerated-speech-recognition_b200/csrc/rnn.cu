@@ -444,7 +444,7 @@ int launch_rnn_recurrence(gasr_ctx *ctx, const RnnLayerArgs &a, cudaStream_t st)
             RnnWideRun r = {};
             r.s0 = 0; r.s1 = a.T; r.xp = a.xproj; r.ldxp = a.ldxp; r.xp_rows_per_frame = a.N;
             r.out = a.out; r.ldo = a.ldo; r.col0 = a.col0; r.out_rows_per_frame = a.N;
-            r.groups_per_cluster = ctx->opt.rnn_groups; r.multicast = ctx->opt.rnn_mc;
+            r.groups_per_cluster = ctx->opt.rnn_groups > 0 ? ctx->opt.rnn_groups : 2; r.multicast = ctx->opt.rnn_mc;
             return pair ? launch_rnn_wide2(ctx, pl, r, st) : launch_rnn_wide(ctx, pl, r, st);
         }
     }

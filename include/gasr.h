@@ -121,6 +121,17 @@ int gasr_rnn_forward(gasr_ctx *ctx, int cell, int bidirectional, int T, int N, i
 int gasr_ctc_decode(gasr_ctx *ctx, const float *scores, int domain, int T, int N, int V, int ld, int beam,
                     int blank, const char *vocab, int max_len, int nbest, char *out_paths, int *out_lens,
                     float *out_scores, int *out_counts);
+/*
+ * The same decoder with the two optional features baseline/main.py:45-46 takes from its decoder
+ * (decoder.decode(output, out_lens) -> output, scores, timesteps, out_seq_len):
+ *   lens_host [N] (may be NULL): frames of each utterance, 1..T.  Utterance n is decoded as if T were lens_host[n]:
+ *       frames beyond it are never read and the last-frame rule (CTCBeamSearch.cu:452-456) applies at frame lens[n]-1.
+ *   out_timesteps [N, nbest, max_len] (host, may be NULL): for output character j, the frame at which the prefix
+ *       path[0..j] first entered the kept beam (0-based; entries beyond the path's length are 0).
+ */
+int gasr_ctc_decode_ex(gasr_ctx *ctx, const float *scores, int domain, int T, int N, int V, int ld, int beam,
+                       int blank, const char *vocab, int max_len, int nbest, const int *lens_host, char *out_paths,
+                       int *out_lens, float *out_scores, int *out_counts, int *out_timesteps);
 /* Diagnostics of the last decode on this ctx: utterance-frames whose prune exceeded the 64-survivor fast path,
  * and the sum of prune survivors over all utterance-frames (mean survivors = that / (N*T)).             */
 int gasr_ctc_last_stats(gasr_ctx *ctx, long long *fallback_frames, long long *survivors);
@@ -175,6 +186,14 @@ int gasr_asr_stage_launches(gasr_asr *asr, int *n4, int *chunk_frames);
 int gasr_asr_submit_host(gasr_asr *asr, const float *x_host);
 int gasr_asr_submit_device(gasr_asr *asr, const float *x_dev);
 int gasr_asr_collect(gasr_asr *asr, char *out_paths, int *out_lens, float *out_scores);
+/* Variable-length batches (baseline/main.py:45 out_lens): lens_host [N], 1..T, applies to every later run; NULL switches it off.
+ * The acoustic model still runs all T frames of the padded batch (a unidirectional stack never looks ahead, so frames
+ * < lens[n] are unaffected; bidirectional stacks are GASR_ERR_INVALID); the decoder stops at lens[n].                  */
+int gasr_asr_set_lengths(gasr_asr *asr, const int *lens_host);
+/* Per-token timesteps (see gasr_ctc_decode_ex) of later runs on / off; gasr_asr_timesteps copies those of the last run,
+ * out_timesteps [N, nbest, max_len].                                                                               */
+int gasr_asr_enable_timesteps(gasr_asr *asr, int on);
+int gasr_asr_timesteps(gasr_asr *asr, int *out_timesteps);
 /* Per-launch stage timing on/off (two event records per kernel launch; off by default) and the device time of the last
  * batch, first kernel to last result copy, measured with CUDA events.                                                 */
 int gasr_asr_profile(gasr_asr *asr, int on);

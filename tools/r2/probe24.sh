@@ -1,0 +1,7 @@
+#!/bin/bash
+# full GPU suite, then the round-2 ncu captures
+cd "$(dirname "$0")/../.."
+mkdir -p gpurun_out
+( time timeout 900 python -m pytest tests -x -q -m gpu ) > gpurun_out/probe24_tests.log 2>&1
+tail -5 gpurun_out/probe24_tests.log
+bash tools/r2/capture_profiles.sh
