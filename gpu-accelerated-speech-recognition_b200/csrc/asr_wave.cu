@@ -411,6 +411,7 @@ int wave_collect(gasr_asr *a, char *out_paths, int *out_lens, float *out_scores)
                 for (int l = 0; l < a->cfg.L; l++)
                     busy += " gemm" + std::to_string(l) + " " + std::to_string(first_open(w->ev_g[l])) + " recurrence" + std::to_string(l) + " " + std::to_string(first_open(w->ev_r[l]));
                 busy += " output-layer " + std::to_string(first_open(w->ev_fc)) + " of " + std::to_string(w->C);
+                gemm_pair_trace_dump();
                 set_error("wave engine: no completion after %.0f s; streams still busy: %s", limit_s, busy.c_str());
                 return GASR_ERR_CUDA;
             }

@@ -18,6 +18,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm_pair.cuh"
@@ -37,7 +39,17 @@ struct GemmPairParams {
     int n_ct, kblocks, terms;     // column tiles of 256, K / 64, 3 (fp32-grade) or 1 (bf16)
     float *C; int ldc;            // C already points at row row0
     const float *bias;
+    volatile unsigned *trace;     // instrumented build only (make TRACE=1): progress words in mapped host memory
 };
+
+#ifdef GASR_RW_TRACE
+// [slot][CTA][8]: word 0 setup (1 entered, 2 TMEM allocated, 3 pair synchronised, 9 exited), 1 producer (4 waits for an empty
+// stage, 5 issued), 2 MMA issuer (6 waits for a drained accumulator, 7 waits for a full stage, 8 committed a tile),
+// 3-6 epilogue warps (10 waits for the accumulator, 11 stored a tile); low 24 bits = iteration / tile counter
+#define GP_MARK(role, code, it) do { if (p.trace) p.trace[blockIdx.x * 8 + (role)] = ((unsigned)(code) << 24) | ((unsigned)(it) & 0xffffffu); } while (0)
+#else
+#define GP_MARK(role, code, it) do { } while (0)
+#endif
 
 __device__ __forceinline__ void gp_arrive_remote(uint32_t local_bar, uint32_t cta) {
     uint32_t remote;
@@ -65,17 +77,23 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     const int n_tiles = (p.M / 256) * p.n_ct;
 
     if (threadIdx.x == 0) {
+        GP_MARK(0, 1, 0);
         for (int s = 0; s < GP_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         for (int a = 0; a < 2; a++) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 8); }   // 4 epilogue warps x 2 CTAs
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {                                                   // pair-collective allocation: one warp of each CTA
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)), "n"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0) GP_MARK(0, 2, 0);
     rw_cluster_sync();
+    if (threadIdx.x == 0) GP_MARK(0, 3, 0);
+    // The permit is given up only after BOTH CTAs of the pair have allocated (the cluster barrier above): with cta_group::2 the
+    // permit is the pair's, and a peer that had not reached its tcgen05.alloc yet when the other CTA relinquished never got
+    // its columns (an intermittent hang of the whole pipeline; found with the progress words of `make TRACE=1`).
+    if (warp == 1) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t own_base = *tmem_slot;
     uint32_t tmem_base;
@@ -97,6 +115,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                 const int arow = p.row0 + rb * 256 + (int)e * 128, brow = ct * 256 + (int)e * 128;
                 for (int kb = 0; kb < p.kblocks; kb++, it++) {
                     const int s = it % GP_STAGES;
+                    GP_MARK(1, 4, it);
                     rw_wait(empty0 + 8 * s, ((uint32_t)(it / GP_STAGES) & 1u) ^ 1u);
                     const uint32_t st = tiles + (uint32_t)s * GP_STAGE_BYTES;
                     if (e == 0) mbar_expect_tx(full0 + 8 * s, 2 * per_cta);
@@ -106,6 +125,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                         rw2_tma_load_to_leader(st + TC_TILE_BYTES, &map_a_lo, leader_full0 + 8 * s, kb * TC_BK, arow);
                         rw2_tma_load_to_leader(st + 3 * TC_TILE_BYTES, &map_b_lo, leader_full0 + 8 * s, kb * TC_BK, brow);
                     }
+                    GP_MARK(1, 5, it);
                 }
             }
         }
@@ -117,11 +137,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             int it = 0, q = 0;
             for (int tile = pair; tile < n_tiles; tile += n_pairs, q++) {
                 const int acc = q & 1;
+                GP_MARK(2, 6, q);
                 rw_wait(tempty0 + 8 * acc, (((uint32_t)q >> 1) & 1u) ^ 1u);   // both CTAs' epilogues drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
                 for (int kb = 0; kb < p.kblocks; kb++, it++) {
                     const int s = it % GP_STAGES;
+                    GP_MARK(2, 7, it);
                     rw_wait(full0 + 8 * s, (uint32_t)(it / GP_STAGES) & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t st = tiles + (uint32_t)s * GP_STAGE_BYTES;
@@ -139,6 +161,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                     rw2_commit_pair(empty0 + 8 * s, pair_mask);
                 }
                 rw2_commit_pair(tfull0 + 8 * acc, pair_mask);
+                GP_MARK(2, 8, q);
             }
         }
     } else {
@@ -149,6 +172,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         for (int tile = pair; tile < n_tiles; tile += n_pairs, q++) {
             const int rb = tile / p.n_ct, ct = tile - rb * p.n_ct;
             const int acc = q & 1;
+            if (lane == 0) GP_MARK(warp + 1, 10, q);
             rw_wait(tfull0 + 8 * acc, ((uint32_t)q >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int row0 = rb * 256 + (int)e * 128 + qd * 32;       // first row (inside this launch) of this warp's 32 rows
@@ -182,16 +206,46 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                 }
                 __syncwarp();
             }
+            if (lane == 0) GP_MARK(warp + 1, 11, q);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0) GP_MARK(0, 8, 0);
     rw_cluster_sync();                       // the peer may still arrive on this CTA's barriers / read its operand tiles
+    if (threadIdx.x == 0) GP_MARK(0, 9, 0);
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(own_base), "n"(512) : "memory");
     }
 }
+
+#ifdef GASR_RW_TRACE
+static unsigned *g_gp_trace_host = nullptr, *g_gp_trace_dev = nullptr;
+static int g_gp_slot = 0;
+static int g_gp_info[16][4];
+constexpr int GP_TRACE_CTAS = 160;
+void gemm_pair_trace_dump() {
+    if (!g_gp_trace_host) return;
+    for (int sl = 0; sl < 16; sl++) {
+        const int ctas = g_gp_info[sl][0];
+        int open = 0;
+        for (int c = 0; c < ctas; c++) if ((g_gp_trace_host[(sl * GP_TRACE_CTAS + c) * 8] >> 24) != 9) open++;
+        if (!open) continue;
+        fprintf(stderr, "[gemm_pair trace] slot %d: %d CTAs, M=%d row0=%d tiles=%d -- %d CTAs not exited\n", sl, ctas, g_gp_info[sl][1],
+                g_gp_info[sl][2], g_gp_info[sl][3], open);
+        for (int c = 0; c < ctas; c++) {
+            const unsigned *w = g_gp_trace_host + (sl * GP_TRACE_CTAS + c) * 8;
+            if ((w[0] >> 24) == 9) continue;
+            fprintf(stderr, "  cta %3d:", c);
+            for (int r = 0; r < 7; r++) fprintf(stderr, " %u/%u", w[r] >> 24, w[r] & 0xffffffu);
+            fprintf(stderr, "\n");
+        }
+    }
+}
+#else
+void gemm_pair_trace_dump() {}
+#endif
 
 bool gemm_pair_supported(const gasr_ctx *ctx, int M, int H) { return ctx->cluster_ok && M >= 256 && M % 256 == 0 && H % 256 == 0; }
 
@@ -210,10 +264,23 @@ int launch_gemm_pair(gasr_ctx *ctx, const CUtensorMap maps[4], int row0, int M, 
     GASR_TRY(gemm_pair_prepare(ctx));
     GemmPairParams p;
     p.M = M; p.row0 = row0; p.n_ct = H / 256; p.kblocks = ceil_div(K, TC_BK); p.terms = precision == GASR_PREC_BF16 ? 1 : 3;
-    p.C = C; p.ldc = ldc; p.bias = bias;
+    p.C = C; p.ldc = ldc; p.bias = bias; p.trace = nullptr;
     const int n_tiles = (M / 256) * p.n_ct;
     int pairs = ctx->sm_count / 2;
     if (pairs > n_tiles) pairs = n_tiles;
+#ifdef GASR_RW_TRACE
+    if (getenv("GASR_GP_TRACE")) {
+        if (!g_gp_trace_host) {
+            GASR_CUDA(cudaHostAlloc((void **)&g_gp_trace_host, sizeof(unsigned) * 16 * GP_TRACE_CTAS * 8, cudaHostAllocMapped));
+            GASR_CUDA(cudaHostGetDevicePointer((void **)&g_gp_trace_dev, g_gp_trace_host, 0));
+            for (int i = 0; i < 16 * GP_TRACE_CTAS * 8; i++) g_gp_trace_host[i] = 9u << 24;
+        }
+        const int sl = g_gp_slot++ & 15;
+        g_gp_info[sl][0] = 2 * pairs; g_gp_info[sl][1] = M; g_gp_info[sl][2] = row0; g_gp_info[sl][3] = n_tiles;
+        for (int i = 0; i < 2 * pairs * 8; i++) g_gp_trace_host[sl * GP_TRACE_CTAS * 8 + i] = 0;
+        p.trace = g_gp_trace_dev + sl * GP_TRACE_CTAS * 8;
+    }
+#endif
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(GP_THREADS);

@@ -13,4 +13,6 @@ int gemm_pair_prepare(gasr_ctx *ctx);            // function attributes (call be
 int launch_gemm_pair(gasr_ctx *ctx, const CUtensorMap maps[4], int row0, int M, int K, int H, float *C, int ldc, const float *bias,
                      int precision, cudaStream_t st);
 
+void gemm_pair_trace_dump();                     // instrumented build (make TRACE=1, GASR_GP_TRACE=1): where every unfinished CTA stands
+
 }  // namespace gasr

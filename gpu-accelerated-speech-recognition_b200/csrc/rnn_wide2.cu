@@ -65,7 +65,6 @@ rnn_wide2_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_cons
     }
     if (warp == 1) {                                                        // pair-collective: one warp of EACH CTA
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)), "n"(256) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     __syncthreads();
     if (warp == 0 && lane == 0) {                                           // the resident W_hh^T slice of this CTA
@@ -79,6 +78,8 @@ rnn_wide2_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_cons
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     rw_cluster_sync();                       // ... and so is the peer's (the leader's MMAs read both), and all barriers exist
+    // the pair's allocation permit is given up only now that both CTAs have allocated (see gemm_pair.cu)
+    if (warp == 1) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t own_base = *tmem_slot;    // what this CTA's warp allocated (and frees)
     uint32_t tmem_base;                      // the accumulator address the leader's MMAs write in BOTH CTAs

@@ -53,9 +53,10 @@ EXPORTS = [
     "gasr_free_device", "gasr_malloc_host", "gasr_free_host", "gasr_memcpy_h2d_on_stream", "gasr_memcpy_h2d",
     "gasr_memcpy_d2h", "gasr_memcpy_h2d_async", "gasr_memcpy_d2h_async", "gasr_memset_device", "gasr_memory_stats",
     "gasr_matmul", "gasr_matadd", "gasr_xproj_gemm", "gasr_linear_forward", "gasr_log_softmax", "gasr_rnn_cell_forward",
-    "gasr_rnn_forward", "gasr_ctc_decode", "gasr_ctc_last_stats", "gasr_ctc_decode_host", "gasr_asr_create", "gasr_asr_destroy",
+    "gasr_rnn_forward", "gasr_ctc_decode", "gasr_ctc_decode_ex", "gasr_ctc_last_stats", "gasr_ctc_decode_host", "gasr_asr_create", "gasr_asr_destroy",
     "gasr_asr_set_weights", "gasr_asr_run_host", "gasr_asr_run_device", "gasr_asr_logprobs", "gasr_asr_stage_times", "gasr_asr_stage_launches",
-    "gasr_asr_submit_host", "gasr_asr_submit_device", "gasr_asr_collect", "gasr_asr_profile", "gasr_asr_last_ms",
+    "gasr_asr_submit_host", "gasr_asr_submit_device", "gasr_asr_collect", "gasr_asr_set_lengths", "gasr_asr_enable_timesteps",
+    "gasr_asr_timesteps", "gasr_asr_profile", "gasr_asr_last_ms",
     "gasr_job_create", "gasr_job_destroy", "gasr_job_set_weights", "gasr_job_run_host", "gasr_job_run_device", "gasr_job_last_ms",
     "gasr_job_launch_count", "gasr_job_lane", "gasr_job_profile", "gasr_job_stage_times", "gasr_synth_spectrogram",
 ]
@@ -196,20 +197,39 @@ class Context:
     def log_softmax(self, x, ldx, y, ldy, rows, cols):
         _check(_lib.gasr_log_softmax(self._h, x, ldx, y, ldy, rows, cols))
 
-    def ctc_decode(self, scores_dev, domain, T, N, V, ld, beam, blank, vocab, max_len=None, nbest=1):
+    def ctc_decode(self, scores_dev, domain, T, N, V, ld, beam, blank, vocab, max_len=None, nbest=1, lens=None, timesteps=False):
+        """lens: frames per utterance (baseline/main.py:45 out_lens); timesteps=True also returns, per utterance (and per kept
+        path when nbest > 1), the frame at which each output character's prefix first entered the beam."""
         max_len = T + 1 if max_len is None else max_len
         paths = np.zeros((N, nbest, max(max_len, 1)), dtype=np.uint8)
-        lens = np.zeros((N, nbest), dtype=np.int32)
+        out_lens = np.zeros((N, nbest), dtype=np.int32)
         scores = np.zeros((N, nbest), dtype=np.float32)
         counts = np.zeros((N,), dtype=np.int32)
-        _check(_lib.gasr_ctc_decode(self._h, scores_dev, domain, T, N, V, ld, beam, blank, bytes(vocab), max_len,
-                                    nbest, paths.ctypes.data_as(ctypes.c_char_p), lens.ctypes.data_as(c_int_p),
-                                    _fp(scores), counts.ctypes.data_as(c_int_p)))
-        return _unpack(paths, lens, scores, counts, nbest, max_len)
+        if lens is None and not timesteps:
+            _check(_lib.gasr_ctc_decode(self._h, scores_dev, domain, T, N, V, ld, beam, blank, bytes(vocab), max_len,
+                                        nbest, paths.ctypes.data_as(ctypes.c_char_p), out_lens.ctypes.data_as(c_int_p),
+                                        _fp(scores), counts.ctypes.data_as(c_int_p)))
+            return _unpack(paths, out_lens, scores, counts, nbest, max_len)
+        lens_a = None if lens is None else np.ascontiguousarray(lens, dtype=np.int32)
+        ts = np.zeros((N, nbest, max(max_len, 1)), dtype=np.int32) if timesteps else None
+        _check(_lib.gasr_ctc_decode_ex(self._h, scores_dev, domain, T, N, V, ld, beam, blank, bytes(vocab), max_len, nbest,
+                                       None if lens_a is None else lens_a.ctypes.data_as(c_int_p),
+                                       paths.ctypes.data_as(ctypes.c_char_p), out_lens.ctypes.data_as(c_int_p), _fp(scores),
+                                       counts.ctypes.data_as(c_int_p), None if ts is None else ts.ctypes.data_as(c_int_p)))
+        res = _unpack(paths, out_lens, scores, counts, nbest, max_len)
+        if not timesteps:
+            return res
+        return res + (_unpack_ts(ts, out_lens, counts, nbest, max_len),)
 
-    def ctc_decode_host(self, scores, domain, beam, blank, vocab, max_len=None, nbest=1):
+    def ctc_decode_host(self, scores, domain, beam, blank, vocab, max_len=None, nbest=1, lens=None, timesteps=False):
         s = _f32(scores)
         T, N, V = s.shape
+        if lens is not None or timesteps:
+            d = self.to_device(s)
+            try:
+                return self.ctc_decode(d, domain, T, N, V, V, beam, blank, vocab, max_len, nbest, lens, timesteps)
+            finally:
+                self.free(d)
         max_len = T + 1 if max_len is None else max_len
         paths = np.zeros((N, nbest, max(max_len, 1)), dtype=np.uint8)
         lens = np.zeros((N, nbest), dtype=np.int32)
@@ -237,6 +257,13 @@ def _unpack(paths, lens, scores, counts, nbest, max_len):
         out_p.append([bytes(paths[n, r, : min(int(lens[n, r]), max_len)]) for r in range(k)])
         out_s.append([float(scores[n, r]) for r in range(k)])
     return out_p, out_s
+
+
+def _unpack_ts(ts, lens, counts, nbest, max_len):
+    N = ts.shape[0]
+    if nbest == 1:
+        return [[int(v) for v in ts[n, 0, : min(int(lens[n, 0]), max_len)]] for n in range(N)]
+    return [[[int(v) for v in ts[n, r, : min(int(lens[n, r]), max_len)]] for r in range(min(int(counts[n]), nbest))] for n in range(N)]
 
 
 _default_ctx = None
@@ -475,6 +502,26 @@ class AsrPipeline:
         _check(_lib.gasr_asr_collect(self._h, self._paths.ctypes.data_as(ctypes.c_char_p),
                                      self._lens.ctypes.data_as(c_int_p), _fp(self._scores)))
         return self._result()
+
+    def set_lengths(self, lens):
+        """Frames per utterance of the batches that follow (baseline/main.py:45 out_lens); None = all T."""
+        if lens is None:
+            _check(_lib.gasr_asr_set_lengths(self._h, None))
+        else:
+            a = np.ascontiguousarray(lens, dtype=np.int32)
+            assert a.shape == (self.cfg.N,)
+            _check(_lib.gasr_asr_set_lengths(self._h, a.ctypes.data_as(c_int_p)))
+
+    def enable_timesteps(self, on=True):
+        _check(_lib.gasr_asr_enable_timesteps(self._h, int(on)))
+
+    def timesteps(self):
+        """Per-token timesteps of the last run: [N][len] (nbest = 1) or [N][nbest][len]."""
+        c = self.cfg
+        ts = np.zeros((c.N, c.nbest, max(c.max_len, 1)), dtype=np.int32)
+        _check(_lib.gasr_asr_timesteps(self._h, ts.ctypes.data_as(c_int_p)))
+        counts = np.full((c.N,), c.nbest, dtype=np.int32)
+        return _unpack_ts(ts, self._lens.reshape(c.N, c.nbest), counts, c.nbest, c.max_len)
 
     def profile(self, on=True):
         _check(_lib.gasr_asr_profile(self._h, int(on)))

@@ -109,6 +109,41 @@ def ctc_trace(scores, vocab, blank, beam, domain="prob", merge="identity"):
     return frames, bytes(op[: ol.value]), float(osc.value)
 
 
+def ctc_decode_lens(scores, lens, vocab, blank, beam, domain="log", nbest=1):
+    """Variable-length batch (baseline/main.py:45 `decoder.decode(output, out_lens)`): utterance n is decoded over its first
+    lens[n] frames only, i.e. exactly CTC-REF on scores[:lens[n], n].  Returns what ctc_decode returns."""
+    s = _f32(scores)
+    res_p, res_s = [], []
+    for n in range(s.shape[1]):
+        p1, s1 = ctc_decode(s[: int(lens[n]), n : n + 1], vocab, blank, beam, domain=domain, nbest=nbest)
+        res_p.append(p1[0]); res_s.append(s1[0])
+    return res_p, res_s
+
+
+def ctc_timesteps(scores, vocab, blank, beam, domain="log", nbest=1):
+    """Per-token timesteps of one utterance [T, V] (the `timesteps` output baseline/main.py:45 takes from its decoder; ctcdecode is
+    not vendored, so the definition is this package's): for output character j of a kept path, the first frame at which the label
+    prefix path[0..j] was a kept beam state.  Derived from the per-frame kept beams of CTC-REF (ctc_trace).
+    Returns (paths, timesteps): the nbest kept paths of the last frame, best first, and one list of frames per path."""
+    vocab = bytes(vocab)
+    frames, _, _ = ctc_trace(scores, vocab, blank, beam, domain=domain)
+    T = len(frames)
+    blank_ch = vocab[blank : blank + 1]
+    first = {}
+    for t, kept in enumerate(frames):
+        for raw, _ in kept:
+            first.setdefault(raw[:-1] if raw.endswith(blank_ch) else raw, t)
+    paths, stamps = [], []
+    for raw, _ in frames[-1][:nbest]:
+        if T == 1:                      # the initial path is returned as is, blank included (SURVEY.md 8c step 5)
+            paths.append(raw); stamps.append([0] * len(raw))
+            continue
+        lab = raw[:-1] if raw.endswith(blank_ch) else raw
+        paths.append(lab)
+        stamps.append([first[lab[: j + 1]] for j in range(len(lab))])
+    return paths, stamps
+
+
 def matmul(x, y):
     x, y = _f32(x), _f32(y)
     z = np.zeros((x.shape[0], y.shape[1]), dtype=np.float32)

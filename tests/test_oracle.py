@@ -156,3 +156,30 @@ def test_deepspeech_baseline_model_golden():
     h = O.linear(h, g["fc3_w"], g["fc3_b"], act="relu")
     logp = O.linear(h, g["fc4_w"], g["fc4_b"], act="logsoftmax")
     assert np.abs(logp.reshape(T, B, -1) - g["logp_tnv"]).max() < 1e-5
+
+
+def test_ctc_lengths_and_timesteps_definitions():
+    """Oracle-side definitions of the two decoder options of baseline/main.py:45-46 (out_lens in, timesteps out)."""
+    from oracle import oracle as O
+    vocab = b"$ab"
+    # a a - b  ->  "ab".  Beam 1: 'a' is kept from frame 0, "ab" from frame 3; a wider beam keeps "ab" (as a low-ranked
+    # state) from frame 1 on -- a timestep is the first frame at which the prefix was a kept state
+    P = np.array([[0.1, 0.8, 0.1], [0.1, 0.8, 0.1], [0.8, 0.1, 0.1], [0.1, 0.1, 0.8]], dtype=np.float32)
+    assert O.ctc_timesteps(P, vocab, 0, 1, domain="prob") == ([b"ab"], [[0, 3]])
+    assert O.ctc_timesteps(P, vocab, 0, 3, domain="prob") == ([b"ab"], [[0, 1]])
+    # T == 1: the initial path comes back as is
+    paths, stamps = O.ctc_timesteps(P[:1], vocab, 0, 3, domain="prob")
+    assert paths == [b"a"] and stamps == [[0]]
+    # lengths: utterance n is CTC-REF on its first lens[n] frames; stamps are increasing and inside the utterance
+    rng = np.random.default_rng(3)
+    lp = np.log(rng.dirichlet(np.ones(5), size=(30, 4)).astype(np.float32))
+    lens = [30, 1, 17, 2]
+    voc = b"$abcd"
+    gp, gs = O.ctc_decode_lens(lp, lens, voc, 0, 4, domain="log")
+    for n, ln in enumerate(lens):
+        p, s = O.ctc_decode(lp[:ln, n : n + 1], voc, 0, 4, domain="log")
+        assert (gp[n], gs[n]) == (p[0], s[0])
+        tp, ts = O.ctc_timesteps(lp[:ln, n], voc, 0, 4, domain="log", nbest=4)
+        assert tp[0] == p[0]
+        for path, st in zip(tp, ts):
+            assert len(st) == len(path) and all(0 <= a < b < ln for a, b in zip(st, st[1:])) and all(0 <= a < ln for a in st)
