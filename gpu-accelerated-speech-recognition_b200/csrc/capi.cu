@@ -119,7 +119,7 @@ int gasr_ctx_create(int device, gasr_ctx **out) {
         o.bidir_serial = getenv("GASR_BIDIR_SERIAL") != nullptr; o.linear_simt = getenv("GASR_LINEAR_SIMT") != nullptr;
         o.xproj = chr("GASR_XPROJ"); o.chunk = num("GASR_CHUNK", -1); o.stream = num("GASR_STREAM", -1); o.wave = num("GASR_WAVE", -1);
         o.stream_gemm_ctas = num("GASR_STREAM_GEMM_CTAS", 24); o.rnn_nsub = num("GASR_RNN_NSUB", -1);
-        o.gemm_stages = num("GASR_GEMM_STAGES", 3); o.ctc_warps = num("GASR_CTC_WARPS", 8); o.gemm_bn = num("GASR_GEMM_BN", 256); o.gemm_pair = num("GASR_GEMM_PAIR", 0);
+        o.gemm_stages = num("GASR_GEMM_STAGES", 3); o.ctc_warps = num("GASR_CTC_WARPS", 8); o.gemm_bn = num("GASR_GEMM_BN", 256); o.gemm_pair = num("GASR_GEMM_PAIR", 1);
         o.wave_serial = getenv("GASR_WAVE_SERIAL") != nullptr; o.wave_timeout_s = num("GASR_WAVE_TIMEOUT_S", 60);
     }
     ctx->device = device;
@@ -393,6 +393,7 @@ static int rnn_layer_direction(gasr_ctx *ctx, int cell, int T, int N, int in_l, 
     RnnLayerArgs a;
     a.cell = cell; a.T = T; a.N = N; a.H = H; a.reverse = reverse;
     a.xproj = xproj; a.ldxp = G * H; a.w_hh = w_hh; a.b_hh = b_hh; a.out = out; a.ldo = ldo; a.col0 = col0;
+    a.precision = precision;
     GASR_TRY(launch_rnn_recurrence(ctx, a, st));
     if (prof) GASR_TRY(prof->mark(1, st));
     return GASR_OK;

@@ -55,7 +55,7 @@ struct gasr_options {
     char ctc_kernel = 0;     // GASR_CTC_KERNEL
     int ctc_mw = 8;          // GASR_CTC_MW
     int ctc_pad = 0;         // GASR_CTC_PAD
-    char gru = 0;            // GASR_GRU
+    char gru = 0;            // GASR_GRU: t = per-timestep tcgen05 kernel even in bf16 mode, g = three launches per step, s = SIMT step kernel
     bool gru_no_pdl = false, no_graph = false, bidir_serial = false, linear_simt = false;
     char xproj = 0;          // GASR_XPROJ
     int chunk = -1;          // GASR_CHUNK (-1: default)
@@ -64,7 +64,7 @@ struct gasr_options {
     int stream_gemm_ctas = 24;
     int rnn_nsub = -1;
     int gemm_stages = 3;     // GASR_GEMM_STAGES: ring depth of the wave engine's GEMM launches (2 or 3)
-    int gemm_pair = 0;       // GASR_GEMM_PAIR: projection GEMMs on CTA pairs (256 x 256 tiles); opt-in, see DESIGN.md 4.2
+    int gemm_pair = 1;       // GASR_GEMM_PAIR: projection GEMMs on CTA pairs (256 x 256 tiles); 0 = one-CTA tile engine
     int gemm_bn = 256;       // GASR_GEMM_BN: tile width of the wave engine's projection GEMMs (128 or 256)
     int wave_timeout_s = 60;  // GASR_WAVE_TIMEOUT_S: a batch that has not completed after this many seconds is reported as an error
     bool wave_serial = false; // GASR_WAVE_SERIAL: diagnostic, all stages of the wave engine on one stream
@@ -155,8 +155,14 @@ struct RnnLayerArgs {
     float *out;           // [T*N, ldo] written at column offset col0
     int ldo, col0;
     int s0 = 0, s1 = 0;   // steps [s0, s1) only (s1 = 0: all T); h before step s0 is read back from `out`
+    int precision = GASR_PREC_FP32;   // GASR_PREC_BF16: the GRU recurrence may use single-plane fp16 operands (gru_seq.cu)
 };
 int launch_rnn_recurrence(gasr_ctx *ctx, const RnnLayerArgs &a, cudaStream_t st);
+
+// persistent GRU recurrence with W_hh resident in shared memory (gru_seq.cu; GASR_PREC_BF16 mode)
+bool gru_seq_supported(const gasr_ctx *ctx, int T, int N, int H, int ldxp, int ldo, int col0);
+size_t gru_seq_ws_bytes(int N, int H);
+int launch_gru_seq(gasr_ctx *ctx, const RnnLayerArgs &a, void *ws, cudaStream_t st);
 
 struct CtcArgs {
     const float *scores; int domain, T, N, V, ld, beam, blank; const char *vocab_host; int max_len, nbest;

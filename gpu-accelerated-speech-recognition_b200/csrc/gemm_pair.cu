@@ -40,6 +40,8 @@ struct GemmPairParams {
     float *C; int ldc;            // C already points at row row0
     const float *bias;
     volatile unsigned *trace;     // instrumented build only (make TRACE=1): progress words in mapped host memory
+    volatile unsigned *tlog;      // instrumented build only: per-SM TMEM allocator event ring
+    int variant;                  // instrumented build only: where the allocation permit is given up (0 = after the alloc, as in the product)
 };
 
 #ifdef GASR_RW_TRACE
@@ -82,18 +84,38 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         for (int a = 0; a < 2; a++) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 8); }   // 4 epilogue warps x 2 CTAs
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // Both CTAs of the pair must be running before either issues the pair-collective tcgen05.alloc (as CUTLASS does: cluster
+    // sync first).  A CTA that allocated while its peer was still being launched left the peer's own alloc blocked for good --
+    // an intermittent stall of the whole pipeline (found with the progress words of `make TRACE=1`).
+    __syncthreads();
+    rw_cluster_sync();
     if (warp == 1) {                                                   // pair-collective allocation: one warp of each CTA
+#ifdef GASR_RW_TRACE
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (lane == 0) GP_MARK(7, 20, smid);
+#endif
+        GASR_TLOG(p.tlog, 1, 1);
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)), "n"(512) : "memory");
+        GASR_TLOG(p.tlog, 1, 2);
+#ifdef GASR_RW_TRACE
+        if (lane == 0) GP_MARK(7, 21, smid);
+        if (p.variant == 0) {
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+            if (lane == 0) GP_MARK(7, 22, smid);
+        }
+#else
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+#endif
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (threadIdx.x == 0) GP_MARK(0, 2, 0);
     rw_cluster_sync();
     if (threadIdx.x == 0) GP_MARK(0, 3, 0);
-    // The permit is given up only after BOTH CTAs of the pair have allocated (the cluster barrier above): with cta_group::2 the
-    // permit is the pair's, and a peer that had not reached its tcgen05.alloc yet when the other CTA relinquished never got
-    // its columns (an intermittent hang of the whole pipeline; found with the progress words of `make TRACE=1`).
-    if (warp == 1) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+#ifdef GASR_RW_TRACE
+    if (warp == 1 && p.variant == 3) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+#endif
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t own_base = *tmem_slot;
     uint32_t tmem_base;
@@ -216,16 +238,50 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     if (threadIdx.x == 0) GP_MARK(0, 9, 0);
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#ifdef GASR_RW_TRACE
+        if (p.variant == 2) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+#endif
+        GASR_TLOG(p.tlog, 1, 3);
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(own_base), "n"(512) : "memory");
+        GASR_TLOG(p.tlog, 1, 4);
     }
 }
 
 #ifdef GASR_RW_TRACE
+static unsigned *g_tlog_host = nullptr, *g_tlog_dev = nullptr;
+unsigned *trace_tmem_log() {
+    if (!getenv("GASR_GP_TRACE")) return nullptr;
+    if (!g_tlog_host) {
+        if (cudaHostAlloc((void **)&g_tlog_host, sizeof(unsigned) * 160 * 16, cudaHostAllocMapped) != cudaSuccess) return nullptr;
+        cudaHostGetDevicePointer((void **)&g_tlog_dev, g_tlog_host, 0);
+        for (int i = 0; i < 160 * 16; i++) g_tlog_host[i] = 0;
+    }
+    return g_tlog_dev;
+}
+void trace_tmem_log_dump() {
+    if (!g_tlog_host) return;
+    static const char *kn[] = {"?", "gemm_pair", "rnn_wide2", "xproj_stream", "rnn_wide"};
+    static const char *en[] = {"?", "alloc..", "alloc ok", "dealloc..", "dealloc ok"};
+    for (int sm = 0; sm < 160; sm++) {
+        const unsigned *l = g_tlog_host + sm * 16;
+        const unsigned n = l[8];
+        if (!n) continue;
+        const unsigned last = l[(n - 1) & 7];
+        if (((last >> 24) & 15) == 4) continue;                    // the last event on this SM is a completed dealloc
+        fprintf(stderr, "[tmem log] SM %3d (%u events):", sm, n);
+        for (unsigned k = n >= 8 ? n - 8 : 0; k < n; k++) {
+            const unsigned e = l[k & 7];
+            fprintf(stderr, " %s#%u:%s", kn[(e >> 28) & 7], e & 0xffffffu, en[(e >> 24) & 15]);
+        }
+        fprintf(stderr, "\n");
+    }
+}
 static unsigned *g_gp_trace_host = nullptr, *g_gp_trace_dev = nullptr;
 static int g_gp_slot = 0;
 static int g_gp_info[16][4];
 constexpr int GP_TRACE_CTAS = 160;
 void gemm_pair_trace_dump() {
+    trace_tmem_log_dump();
     if (!g_gp_trace_host) return;
     for (int sl = 0; sl < 16; sl++) {
         const int ctas = g_gp_info[sl][0];
@@ -238,7 +294,7 @@ void gemm_pair_trace_dump() {
             const unsigned *w = g_gp_trace_host + (sl * GP_TRACE_CTAS + c) * 8;
             if ((w[0] >> 24) == 9) continue;
             fprintf(stderr, "  cta %3d:", c);
-            for (int r = 0; r < 7; r++) fprintf(stderr, " %u/%u", w[r] >> 24, w[r] & 0xffffffu);
+            for (int r = 0; r < 8; r++) fprintf(stderr, " %u/%u", w[r] >> 24, w[r] & 0xffffffu);
             fprintf(stderr, "\n");
         }
     }
@@ -264,11 +320,13 @@ int launch_gemm_pair(gasr_ctx *ctx, const CUtensorMap maps[4], int row0, int M, 
     GASR_TRY(gemm_pair_prepare(ctx));
     GemmPairParams p;
     p.M = M; p.row0 = row0; p.n_ct = H / 256; p.kblocks = ceil_div(K, TC_BK); p.terms = precision == GASR_PREC_BF16 ? 1 : 3;
-    p.C = C; p.ldc = ldc; p.bias = bias; p.trace = nullptr;
+    p.C = C; p.ldc = ldc; p.bias = bias; p.trace = nullptr; p.variant = 0; p.tlog = nullptr;
     const int n_tiles = (M / 256) * p.n_ct;
     int pairs = ctx->sm_count / 2;
     if (pairs > n_tiles) pairs = n_tiles;
 #ifdef GASR_RW_TRACE
+    if (const char *e = getenv("GASR_GP_VARIANT")) p.variant = atoi(e);
+    p.tlog = trace_tmem_log();
     if (getenv("GASR_GP_TRACE")) {
         if (!g_gp_trace_host) {
             GASR_CUDA(cudaHostAlloc((void **)&g_gp_trace_host, sizeof(unsigned) * 16 * GP_TRACE_CTAS * 8, cudaHostAllocMapped));

@@ -500,6 +500,13 @@ int launch_rnn_recurrence(gasr_ctx *ctx, const RnnLayerArgs &a, cudaStream_t st)
     const bool gru_fused = gru_batched && !(force_g && force_g[0] == 'g') && gru_tc_supported(a.N, a.H, a.ldxp, a.ldo, a.col0) &&
                            ((reinterpret_cast<uintptr_t>(a.xproj) | reinterpret_cast<uintptr_t>(a.out) |
                              reinterpret_cast<uintptr_t>(a.b_hh)) & 15) == 0;
+    if (gru_fused && a.precision == GASR_PREC_BF16 && !(force_g && force_g[0] == 't') &&
+        gru_seq_supported(ctx, a.T, a.N, a.H, a.ldxp, a.ldo, a.col0)) {
+        // bf16 mode: ONE persistent launch for the whole sequence, W_hh (fp16) resident in shared memory (gru_seq.cu)
+        Workspace &wsg = ctx->ws_sel ? ctx->ws_gru_b : ctx->ws_gru;
+        GASR_TRY(ws_reserve(ctx, wsg, gru_seq_ws_bytes(a.N, a.H)));
+        return launch_gru_seq(ctx, a, wsg.ptr, st);
+    }
     if (gru_fused || (gru_batched && xproj_tc_supported(a.N, a.H, 3 * a.H))) {
         // GRU with a real batch, one launch per timestep (gru_tc.cu): tcgen05 GEMM h_{t-1} * W_hh (fp32-grade 3 x bf16
         // split, permuted W_hh^T prepared once, TMA descriptors reused) with the gate math in its epilogue, which also

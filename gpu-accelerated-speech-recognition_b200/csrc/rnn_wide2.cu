@@ -32,6 +32,7 @@ struct RnnWide2Params {
     const float *xp; int ldxp, xp_rpf;
     float *out; int ldo, col0, out_rpf;
     __nv_bfloat16 *hi, *lo;
+    volatile unsigned *tlog;                      // instrumented build only
 };
 
 __global__ void __launch_bounds__(RW_THREADS, 1)
@@ -63,8 +64,13 @@ rnn_wide2_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_cons
         mbar_init(wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncthreads();
+    rw_cluster_sync();                                                      // the peer is running before the pair-collective alloc (see gemm_pair.cu)
     if (warp == 1) {                                                        // pair-collective: one warp of EACH CTA
+        GASR_TLOG(p.tlog, 2, 1);
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)), "n"(256) : "memory");
+        GASR_TLOG(p.tlog, 2, 2);
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     __syncthreads();
     if (warp == 0 && lane == 0) {                                           // the resident W_hh^T slice of this CTA
@@ -78,8 +84,6 @@ rnn_wide2_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_cons
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     rw_cluster_sync();                       // ... and so is the peer's (the leader's MMAs read both), and all barriers exist
-    // the pair's allocation permit is given up only now that both CTAs have allocated (see gemm_pair.cu)
-    if (warp == 1) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t own_base = *tmem_slot;    // what this CTA's warp allocated (and frees)
     uint32_t tmem_base;                      // the accumulator address the leader's MMAs write in BOTH CTAs
@@ -248,7 +252,9 @@ rnn_wide2_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_cons
     rw_cluster_sync();                       // no CTA leaves while a peer may still arrive on its barriers / read its operands
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        GASR_TLOG(p.tlog, 2, 3);
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(own_base), "n"(256) : "memory");
+        GASR_TLOG(p.tlog, 2, 4);
     }
 }
 
@@ -272,6 +278,10 @@ int launch_rnn_wide2(gasr_ctx *ctx, const RnnWidePlan &pl, const RnnWideRun &r, 
                "rnn_wide2: output must be 16-byte aligned");
     GASR_TRY(rnn_wide2_prepare(ctx));
     RnnWide2Params p;
+    p.tlog = nullptr;
+#ifdef GASR_RW_TRACE
+    p.tlog = trace_tmem_log();
+#endif
     p.T = pl.T; p.N = pl.N; p.Npad = pl.Npad; p.KB = pl.H / 64; p.s0 = r.s0; p.s1 = r.s1;
     p.n_groups = pl.Npad / 256;
     p.G = r.groups_per_cluster >= 2 ? 2 : 1;

@@ -32,6 +32,7 @@ struct XsParams {
     int wide;                 // 1: targets may use 256-column tiles (96 KB stages, two of them; 2 x 256 TMEM columns)
     int *error;               // mapped host word: watchdog code
     volatile unsigned *abort; // device word: any persistent kernel of the pipeline gave up -> everybody stops waiting
+    volatile unsigned *tlog;  // instrumented build only (make TRACE=1)
     XsTarget target[XS_MAX_TARGETS];
 };
 

@@ -59,3 +59,14 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 int tc_make_map(CUtensorMap *map, const void *base, int rows, int Kp, int box_rows);
 
 }  // namespace gasr
+
+// Instrumented build only (make TRACE=1): per-SM ring of the last eight TMEM allocator events in mapped host memory
+// (kernel id << 28 | event << 24 | CTA): events 1 = before alloc, 2 = after alloc, 3 = before dealloc, 4 = after dealloc.
+#ifdef GASR_RW_TRACE
+namespace gasr { unsigned *trace_tmem_log(); void trace_tmem_log_dump(); }
+#define GASR_TLOG(ptr, kid, ev) do { if ((ptr) && (threadIdx.x & 31) == 0) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); \
+    volatile unsigned *l_ = (ptr) + sm_ * 16; const unsigned i_ = l_[8]; l_[i_ & 7] = ((unsigned)(kid) << 28) | ((unsigned)(ev) << 24) | (blockIdx.x & 0xffffffu); l_[8] = i_ + 1; } } while (0)
+#else
+#define GASR_TLOG(ptr, kid, ev) do { } while (0)
+#endif
+

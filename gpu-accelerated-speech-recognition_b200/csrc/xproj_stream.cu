@@ -121,8 +121,10 @@ xproj_stream_kernel(const __grid_constant__ XsMaps maps, const XsParams p) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
+        GASR_TLOG(p.tlog, 3, 1);
         if (p.wide) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)), "n"(512) : "memory");
         else asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)), "n"(2 * TC_BN) : "memory");
+        GASR_TLOG(p.tlog, 3, 2);
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -301,8 +303,10 @@ xproj_stream_kernel(const __grid_constant__ XsMaps maps, const XsParams p) {
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        GASR_TLOG(p.tlog, 3, 3);
         if (p.wide) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
         else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * TC_BN) : "memory");
+        GASR_TLOG(p.tlog, 3, 4);
     }
 }
 
@@ -323,6 +327,10 @@ int launch_xproj_stream(gasr_ctx *ctx, const XsMaps &maps, const XsParams &p, in
     if (ctas == 0) return GASR_OK;      // preparation call
     GASR_CHECK(p.stages == 0 || p.stages == 2 || p.stages == 3, "xproj_stream: ring depth must be 2 or 3");
     XsParams q = p;
+    q.tlog = nullptr;
+#ifdef GASR_RW_TRACE
+    q.tlog = trace_tmem_log();
+#endif
     if (q.stages == 0) q.stages = TC_STAGES;
     if (q.wide) q.stages = 2;              // 96 KB stages: two fit
     xproj_stream_kernel<<<ctas, TC_THREADS, xs_smem_bytes(q.stages, q.wide), st>>>(maps, q);

@@ -47,12 +47,12 @@ def _assert_same(gp, gs, op, os_):
     assert (_bits(gs) == _bits(os_)).all(), (gs, os_)
 
 
-def _run_rnn(gasr, ctx, cell, bidir, T, N, D, H, L, x, w_ih, w_hh, b_ih, b_hh):
+def _run_rnn(gasr, ctx, cell, bidir, T, N, D, H, L, x, w_ih, w_hh, b_ih, b_hh, precision=0):
     Dn = 2 if bidir else 1
     dx = ctx.to_device(x)
     dw = [[ctx.to_device(a) for a in lst] for lst in (w_ih, w_hh, b_ih, b_hh)]
     hid = [ctx.malloc(T * N * Dn * H * 4) for _ in range(L)]
-    ctx.rnn_forward(cell, bidir, T, N, D, H, L, dw[0], dw[1], dw[2], dw[3], dx, hid)
+    ctx.rnn_forward(cell, bidir, T, N, D, H, L, dw[0], dw[1], dw[2], dw[3], dx, hid, precision)
     out = [ctx.to_host(h, (T * N, Dn * H)) for h in hid]
     for p in [dx] + sum(dw, []) + hid:
         ctx.free(p)
@@ -155,6 +155,32 @@ def test_cfg3_gru_at_batch_256(gasr, ctx, O):
     ref = O.gru_forward(x, T, N, H, L, True, w_ih, w_hh, b_ih, b_hh)
     for l in range(L):
         assert np.abs(out[l] - ref[l]).max() < AM_TOL, f"layer {l}"
+
+
+@pytest.mark.parametrize("T,N,D,H,L", [(12, 256, 161, 800, 2), (300, 130, 40, 100, 1), (65, 33, 24, 64, 2)])
+def test_cfg3_bf16_mode_persistent_gru_recurrence(gasr, O, monkeypatch, T, N, D, H, L):
+    """GASR_PREC_BF16 (cfg3's mode): the recurrence of a (layer, direction) is ONE persistent launch with W_hh resident in shared
+    memory as fp16 (gru_seq.cu).  Against the fp32 oracle within the mode's stated 2e-2; against the per-timestep kernel of the
+    same mode (GASR_GRU=t: fp32-grade recurrence on the same bf16 projection) within 2e-3 -- what the fp16 operands cost.
+    Shapes: cfg3's layer at cfg3's batch; 300 steps over ragged row blocks / a partial unit tile; a small two-layer stack."""
+    import synth
+    x = synth.spectrogram_batch(91, T, N, D)
+    w_ih, w_hh, b_ih, b_hh = synth.rnn_weights(92, D, H, L, cell_gates=3, bidir=True)
+    ref = O.gru_forward(x, T, N, H, L, True, w_ih, w_hh, b_ih, b_hh)
+    outs, launches = {}, {}
+    for force in ("", "t"):
+        if force:
+            monkeypatch.setenv("GASR_GRU", force)
+        c = gasr.Context(0)
+        n0 = c.launch_count()
+        outs[force] = _run_rnn(gasr, c, gasr.CELL_GRU, True, T, N, D, H, L, x, w_ih, w_hh, b_ih, b_hh, precision=gasr.PREC_BF16)
+        launches[force] = c.launch_count() - n0
+        c.close()
+    # one recurrence launch per (layer, direction) instead of T
+    assert launches["t"] - launches[""] >= 2 * L * (T - 2), launches
+    for l in range(L):
+        assert np.abs(outs[""][l] - ref[l]).max() < 2e-2, f"layer {l} vs oracle"
+        assert np.abs(outs[""][l] - outs["t"][l]).max() < 2e-3, f"layer {l} vs the per-timestep kernel"
 
 
 # ------------------------------------------------------------------------------------------------ cfg4
