@@ -49,6 +49,8 @@ struct Workspace {
 // Environment switches, read ONCE when the context is created (never on a per-call path).
 struct gasr_options {
     char rnn = 0;            // GASR_RNN: w = wide tcgen05 recurrence, f / m / ... = the round-1 kernels (first letter)
+    int gru_pp = 0;          // GASR_GRU_PP: row blocks per CTA of the persistent GRU recurrence (1 or 2; 0 = by batch size)
+    int gru_units = 0;       // GASR_GRU_UNITS: hidden units per CTA of the persistent GRU recurrence (16 or 32; 0 = automatic)
     int rnn_mc = 1;          // GASR_RNN_MC: TMA multicast of the h boxes in the wide recurrence
     int rnn_groups = 0;      // GASR_RNN_G: groups of utterances per cluster (1 or 2; 0 = by batch size)
     int rnn_pair = 1;        // GASR_RNN_PAIR: CTA-pair recurrence (tcgen05.mma.cta_group::2, groups of 256 utterances)
