@@ -118,7 +118,7 @@ int gasr_ctx_create(int device, gasr_ctx **out) {
         o.gru = chr("GASR_GRU"); o.gru_pp = num("GASR_GRU_PP", 0); o.gru_units = num("GASR_GRU_UNITS", 0); o.gru_no_pdl = getenv("GASR_GRU_NO_PDL") != nullptr; o.no_graph = getenv("GASR_NO_GRAPH") != nullptr;
         o.bidir_serial = getenv("GASR_BIDIR_SERIAL") != nullptr; o.linear_simt = getenv("GASR_LINEAR_SIMT") != nullptr;
         o.xproj = chr("GASR_XPROJ"); o.chunk = num("GASR_CHUNK", -1); o.stream = num("GASR_STREAM", -1); o.wave = num("GASR_WAVE", -1);
-        o.stream_gemm_ctas = num("GASR_STREAM_GEMM_CTAS", 24); o.rnn_nsub = num("GASR_RNN_NSUB", -1);
+        o.stream_gemm_ctas = num("GASR_STREAM_GEMM_CTAS", 24);
         o.gemm_stages = num("GASR_GEMM_STAGES", 3); o.ctc_warps = num("GASR_CTC_WARPS", 8); o.gemm_bn = num("GASR_GEMM_BN", 256); o.gemm_pair = num("GASR_GEMM_PAIR", 1);
         o.wave_serial = getenv("GASR_WAVE_SERIAL") != nullptr; o.wave_timeout_s = num("GASR_WAVE_TIMEOUT_S", 60);
     }
@@ -575,8 +575,21 @@ int gasr_asr_create(gasr_ctx *ctx, const gasr_asr_config *cfg, const char *vocab
         // streaming envelope: whole blocks of 128 rows, the persistent recurrence's cluster budget, one output tile
         const int want_stream = ctx->opt.stream == 1;          // opt-in: persistent kernels that wait for each other
         const int N = cfg->N, L = cfg->L;
-        if (want_stream && cfg->beam <= 32 && cfg->V <= 32 && N % 16 == 0 && 128 % N == 0 && L + 1 <= XS_MAX_TARGETS && L <= RS_MAX_LAYERS &&
-            rnn_stream_supported(ctx, H, N, L) && H % 128 == 0 && ((size_t)cfg->T * N) % 128 == 0 && ctx->sm_count >= 132) {
+        // Residency is computed, not assumed: every cluster of the recurrence kernel (whole SMs), the GEMM CTAs and one decoder
+        // CTA per utterance must be co-resident, or the kernels would wait for each other until their watchdogs fire.
+        bool fits = false;
+        if (want_stream && (H == 512 || H == 256 || H == 128) && ctx->cluster_ok) {
+            int max_clusters = 0, cs = 1;
+            if (rnn_stream_max_clusters(ctx, H, &max_clusters, &cs) == GASR_OK) {
+                const int rec_clusters = ceil_div(N, 16) * L;
+                const int other_sms = ctx->sm_count - rec_clusters * cs;             // SMs left for the GEMM and decoder CTAs
+                fits = rec_clusters <= max_clusters && other_sms >= ctx->opt.stream_gemm_ctas &&
+                       N <= 2 * (other_sms - ctx->opt.stream_gemm_ctas) + ctx->opt.stream_gemm_ctas;   // two decoder CTAs per free SM, one next to a GEMM CTA
+            }
+            cudaGetLastError();
+        }
+        if (want_stream && fits && cfg->beam <= 32 && cfg->V <= 32 && N % 16 == 0 && 128 % N == 0 && L + 1 <= XS_MAX_TARGETS && L <= RS_MAX_LAYERS &&
+            rnn_stream_supported(ctx, H, N, L) && H % 128 == 0 && ((size_t)cfg->T * N) % 128 == 0) {
             a->stream_fpb = 128 / N;
             a->stream_blocks = (int)(rows / 128);
             a->stream_gemm_ctas = ctx->opt.stream_gemm_ctas;
@@ -821,8 +834,8 @@ static int asr_run_streaming(gasr_asr *a, const float *x_dev, const float *x_hos
     cudaStream_t main_st = ctx->stream, rec_st = ctx->side[0], gemm_st = ctx->side[1], dec_st = ctx->side[3];
     unsigned *h_done = a->flags, *xp_ready = a->flags + (size_t)L * nb, *lp_ready = a->flags + (size_t)2 * L * nb;
     unsigned *x_ready = lp_ready + nb, *misc = x_ready + nb;
-    const int rec_nsub = rnn_stream_default_nsub(N);
-    const int rec_groups = rec_nsub == 4 ? ceil_div(N, 32) : ceil_div(N, 16);
+    const int rec_nsub = 0;
+    const int rec_groups = ceil_div(N, 16);
     const int rec_ctas_per_layer = rec_groups * (H / 64);
     a->epoch += 1;
     a->host_words[1] = 0;
@@ -862,7 +875,6 @@ static int asr_run_streaming(gasr_asr *a, const float *x_dev, const float *x_hos
         cudaPointerAttributes at = {};
         if (cudaPointerGetAttributes(&at, x_host) != cudaSuccess || at.type != cudaMemoryTypeHost) { cudaGetLastError(); slices_first = slices; }
     }
-    if (const char *e = getenv("GASR_STREAM_FIRST_SLICES")) slices_first = atoi(e) < slices ? atoi(e) : slices;
     auto issue_slices = [&](int s_begin, int s_end) -> int {
         cudaStream_t cp_st = ctx->side[2];
         for (int sidx = s_begin; sidx < s_end; sidx++) {
@@ -877,7 +889,11 @@ static int asr_run_streaming(gasr_asr *a, const float *x_dev, const float *x_hos
         return GASR_OK;
     };
     GASR_TRY(issue_slices(0, slices_first));
-    const bool dbg = getenv("GASR_STREAM_DEBUG") != nullptr;
+#ifdef GASR_STREAM_HOOKS
+    const bool dbg = getenv("GASR_STREAM_DEBUG") != nullptr;   // instrumented build only (make TRACE=1): stage-by-stage diagnosis
+#else
+    constexpr bool dbg = false;
+#endif
     if (dbg) { GASR_CUDA(cudaStreamSynchronize(main_st)); fprintf(stderr, "[stream] prep ok\n"); }
 
     // ---- recurrence: all layers, one launch ------------------------------------------------------------------------
@@ -914,11 +930,13 @@ static int asr_run_streaming(gasr_asr *a, const float *x_dev, const float *x_hos
         cudaError_t q = cudaStreamQuery(rec_st);
         fprintf(stderr, "[stream] recurrence resident, query: %s\n", cudaGetErrorString(q));
         if (q != cudaSuccess && q != cudaErrorNotReady) { set_error("recurrence kernel failed: %s", cudaGetErrorString(q)); return GASR_ERR_CUDA; }
+#ifdef GASR_STREAM_HOOKS
         if (getenv("GASR_STREAM_DEBUG")[0] == '2') {
             q = cudaStreamSynchronize(rec_st);
             fprintf(stderr, "[stream] recurrence alone: %s, error word %d\n", cudaGetErrorString(q), a->host_words[1]);
             return GASR_ERR_CUDA;
         }
+#endif
     }
     // ---- projection + output-layer GEMM -------------------------------------------------------------------------------
     XsParams xp = {};
@@ -955,6 +973,7 @@ static int asr_run_streaming(gasr_asr *a, const float *x_dev, const float *x_hos
             t.C = a->logp; t.ldc = a->ldp; t.bias = a->fc_b_pad; t.dst_ready = lp_ready;
         }
     }
+#ifdef GASR_STREAM_HOOKS   // ablation / alone-timing paths of the instrumented build (tools/capture_profiles.sh)
     if (dbg && getenv("GASR_DEBUG_TERMS")) for (int tg = 0; tg <= L; tg++) xp.target[tg].terms = atoi(getenv("GASR_DEBUG_TERMS"));
     if (dbg && getenv("GASR_DEBUG_SAMEMAP")) for (int tg = 0; tg <= L; tg++) xp.target[tg].kind |= 32;
     if (dbg && getenv("GASR_DEBUG_PRINT")) for (int tg = 0; tg <= L; tg++) xp.target[tg].kind |= 64;
@@ -993,9 +1012,12 @@ static int asr_run_streaming(gasr_asr *a, const float *x_dev, const float *x_hos
         }
         return GASR_ERR_CUDA;
     }
+#endif
     GASR_CUDA(cudaStreamWaitEvent(gemm_st, a->ev_go, 0));
     GASR_CUDA(cudaEventRecord(a->ev_g0, gemm_st));
-    if (!getenv("GASR_STREAM_INJECT_LOST_PRODUCER"))     // (test hook: the GEMM kernel never starts -> watchdogs -> fallback)
+#ifdef GASR_STREAM_HOOKS
+    if (!getenv("GASR_STREAM_INJECT_LOST_PRODUCER"))     // (test hook of the instrumented build: the GEMM kernel never starts -> watchdogs -> fallback)
+#endif
         GASR_TRY(launch_xproj_stream(ctx, a->xs_maps, xp, gemm_ctas, gemm_st));
     GASR_CUDA(cudaEventRecord(a->ev_g1, gemm_st));
     if (dbg) {
@@ -1033,8 +1055,7 @@ static int asr_run_streaming(gasr_asr *a, const float *x_dev, const float *x_hos
 // the time-chunked mode -- still the same kernels' siblings on the GPU, never a CPU path -- and says so once.
 static bool asr_stream_recover(gasr_asr *a, int rc) {
     if (rc != GASR_ERR_CUDA || cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) return false;
-    fprintf(stderr, "libgasr: streaming pipeline unavailable (%s); falling back to the time-chunked pipeline\n", gasr_last_error());
-    a->stream_ok = false;
+    a->stream_ok = false;            // visible to the caller: gasr_asr_stage_launches reports the chunked mode from now on
     return true;
 }
 
@@ -1050,7 +1071,10 @@ int gasr_asr_run_device(gasr_asr *a, const float *x_dev, char *out_paths, int *o
     }
     if (a->stream_ok) {
         const int rc = asr_run_streaming(a, x_dev, nullptr, out_paths, out_lens, out_scores);
-        if (rc == GASR_OK || getenv("GASR_STREAM_DEBUG")) return rc;
+        if (rc == GASR_OK) return rc;
+#ifdef GASR_STREAM_HOOKS
+        if (getenv("GASR_STREAM_DEBUG")) return rc;
+#endif
         if (!asr_stream_recover(a, rc)) return rc;
     }
     if (a->chunk > 0) return asr_run_pipelined(a, x_dev, out_paths, out_lens, out_scores);
@@ -1071,7 +1095,10 @@ int gasr_asr_run_host(gasr_asr *a, const float *x_host, char *out_paths, int *ou
     }
     if (a->stream_ok) {
         const int rc = asr_run_streaming(a, a->x_dev, x_host, out_paths, out_lens, out_scores);
-        if (rc == GASR_OK || getenv("GASR_STREAM_DEBUG")) return rc;
+        if (rc == GASR_OK) return rc;
+#ifdef GASR_STREAM_HOOKS
+        if (getenv("GASR_STREAM_DEBUG")) return rc;
+#endif
         if (!asr_stream_recover(a, rc)) return rc;
     }
     GASR_CUDA(cudaMemcpyAsync(a->x_dev, x_host, sizeof(float) * (size_t)c.T * c.N * c.in, cudaMemcpyHostToDevice,

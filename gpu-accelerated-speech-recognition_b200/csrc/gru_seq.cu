@@ -2,7 +2,7 @@
 // (GASR_PREC_BF16 mode; BASELINE.json cfg3: 5-layer bidirectional GRU, H = 800, 256 utterances).
 //
 // Stands behind the time loop of RNN::forward (reference RNN.cu:9-30, one cell call per timestep); the GRU equations are
-// torch.nn.GRU's, as in oracle/am_ref.c (gate order r, z, n).  The per-timestep kernel (gru_tc.cu) costs 14 us per step
+// torch.nn.GRU's (gate order r, z, n; the test oracle restates them).  The per-timestep kernel (gru_tc.cu) costs 14 us per step
 // at cfg3 widths: every launch re-reads its slice of W_hh^T (hi + lo planes, 320 KB per CTA) through L2 and pays the
 // launch / dependency gap.  Here
 //   * a CTA owns UNITS hidden units (the r, z and n columns of W_hh for them: a [3 UNITS x Kp] K-major slice of the permuted

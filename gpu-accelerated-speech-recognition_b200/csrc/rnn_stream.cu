@@ -357,298 +357,12 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rnn_stream_kernel(const RnnStre
     cluster.sync();
 }
 
-// =====================================================================================================================
-// Second generation: NSUB (2 or 4) sub-batches of 8 utterances per cluster, processed in GROUPS of two: the MMAs of both
-// sub-batches of a group are issued back to back, then one joint epilogue runs their two independent dependency chains
-// interleaved (see the comment at the main loop).  With 4 sub-batches a cluster serves 32 utterances: cfg2's layer stack
-// needs 48 SMs instead of 96 -- the SMs the decoder needs to run one CTA per SM.
-// =====================================================================================================================
-__device__ __forceinline__ void rs_mma_nv(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-template <int H, int NSUB>
-struct Rs2Layout {
-    static constexpr int HSB = H * 2 + 16;
-    static constexpr int PLANE = RS_SUB * HSB;
-    static constexpr int HBUF = 2 * PLANE;
-    static constexpr int OFF_H = 0;                                  // [sub NSUB][parity 2][plane 2][8][HSB]
-    static constexpr int OFF_XCH = OFF_H + NSUB * 2 * HBUF;          // [sub NSUB][ch 4][kh 2][32] float2
-    static constexpr int OFF_STG = OFF_XCH + NSUB * 2048;            // [warp 8][plane 2][utt 8][16 B]
-    static constexpr int OFF_BAR = OFF_STG + 2 * RS_MATH_WARPS * 256;  // (two staging tiles per warp) mbar[sub NSUB][parity 2]
-    static constexpr int OFF_CTL = OFF_BAR + NSUB * 2 * 8;           // int: [0], [1] warp arrivals by block parity, [2] abort, [4..11] per-warp sequence numbers
-    static constexpr int BYTES = OFF_CTL + 48;
-    static constexpr uint32_t TX = 2u * RS_SUB * H * 2u;
-};
-
-template <int H, int NSUB>
-__global__ void __launch_bounds__(RS_THREADS, 1) rnn_stream2_kernel(const RnnStreamParams p) {
-    using LT = Rs2Layout<H, NSUB>;
-    constexpr int CS = H / RS_HC;
-    constexpr int KSW = H / 32;                          // k-steps (of 16) per warp: half of K
-    constexpr int KP = KSW / 2;                          // ldmatrix.x4 pairs per sub-step
-    extern __shared__ __align__(128) unsigned char smem[];
-    cg::cluster_group cluster = cg::this_cluster();
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, tg = lane & 3;
-    const int rank = (int)cluster.block_rank();
-    const int cid = blockIdx.x / CS;
-    const int layer = cid / p.groups, group = cid % p.groups;
-    const int n0 = group * RS_SUB * NSUB;
-    const int colbase = rank * RS_HC;
-    const RnnStreamLayer &L = p.layer[layer];
-    volatile int *ctl = reinterpret_cast<volatile int *>(smem + LT::OFF_CTL);
-    const uint32_t sbase = rs_smem_u32(smem);
-    const int T = p.T, N = p.N, fpb = p.frames_per_block;
-
-    for (int i = tid; i < (NSUB * 2 * LT::HBUF) / 16; i += RS_THREADS) reinterpret_cast<uint4 *>(smem + LT::OFF_H)[i] = make_uint4(0, 0, 0, 0);
-    if (tid == 0) {
-        for (int b = 0; b < NSUB * 2; b++) rs_mbar_init(sbase + LT::OFF_BAR + 8 * b, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        ctl[0] = 0; ctl[1] = 0; ctl[2] = 0;
-        for (int i = 4; i < 12; i++) ctl[i] = 0;
-    }
-    __syncthreads();
-    if (tid == 0)
-        for (int b = 0; b < NSUB * 2; b++) rs_mbar_expect_tx(sbase + LT::OFF_BAR + 8 * b, LT::TX);
-
-    const int ch = warp & 3, kh = warp >> 2;
-    uint32_t ahi[KSW][4], alo[KSW][4];
-    {
-        const float *wc = L.w_hh + colbase + 16 * ch + g;
-#pragma unroll
-        for (int ks = 0; ks < KSW; ks++) {
-            const int k = kh * (H / 2) + 16 * ks + 2 * tg;
-            rs_split_pair(__ldg(wc + (size_t)k * H), __ldg(wc + (size_t)(k + 1) * H), ahi[ks][0], alo[ks][0]);
-            rs_split_pair(__ldg(wc + (size_t)k * H + 8), __ldg(wc + (size_t)(k + 1) * H + 8), ahi[ks][1], alo[ks][1]);
-            rs_split_pair(__ldg(wc + (size_t)(k + 8) * H), __ldg(wc + (size_t)(k + 9) * H), ahi[ks][2], alo[ks][2]);
-            rs_split_pair(__ldg(wc + (size_t)(k + 8) * H + 8), __ldg(wc + (size_t)(k + 9) * H + 8), ahi[ks][3], alo[ks][3]);
-        }
-    }
-    const uint32_t lm_off = (uint32_t)((lane & 7) * LT::HSB + (kh * (H / 2) + 8 * (lane >> 3)) * 2);
-    const int jcol = colbase + 16 * ch + 8 * kh + g;     // the column this thread finalises, utterances (2tg, 2tg+1) of a sub-batch
-    // CTA-uniform bases (registers, not repeated parameter-space loads) + 32-bit element offsets advancing one frame per step
-    const float *const xp_base = L.xproj;
-    float *const out_base = L.out;
-    unsigned *const hdone = L.h_done;
-    const int ldxp1 = L.ldxp, ldo1 = L.ldo;
-    const int xstep = N * L.ldxp, ostep = N * L.ldo, pstep = N * L.ldp;
-    const int ldxp8 = RS_SUB * L.ldxp, ldo8 = RS_SUB * L.ldo, ldp8 = RS_SUB * L.ldp;
-    const int nA = n0 + 2 * tg;                          // + 8 sub: this thread's first utterance in sub-batch sub
-    int xoff = nA * L.ldxp + jcol;                       // frame of the sub-step being ISSUED
-    int ooff = nA * L.ldo + jcol;                        // frame of the sub-step being FINISHED
-    const int cpl = (lane >> 3) & 1, cu = lane & 7;      // this lane's plane chunk: (plane, utterance), 8 columns
-    __nv_bfloat16 *const plane_base = cpl ? L.out_lo : L.out_hi;
-    int poff = (n0 + cu) * L.ldp + colbase + 16 * ch + 8 * kh;
-    const bool plane_lane = lane < 16 && plane_base != nullptr;
-    // projection progress (see rnn_stream_kernel)
-    const volatile unsigned *xr = L.xp_ready;
-    const int nblocks = (T + fpb - 1) / fpb;
-    const int fsh = (fpb & (fpb - 1)) == 0 ? __ffs(fpb) - 1 : -1;        // frames per block is a power of two in the pipeline
-    int ready_blocks = xr == nullptr ? nblocks : 0;
-    unsigned flag_next = 0;
-    auto advance_blocks = [&](int t) {
-        const int before = ready_blocks;
-        if (__shfl_sync(0xffffffffu, flag_next, 0) >= (unsigned)p.xp_need) ready_blocks++;
-        const int need = (fsh >= 0 ? (t >> fsh) : t / fpb) + 1;
-        while (ready_blocks < need) {
-            const unsigned long long t0 = rs_now_ns();
-            unsigned v;
-            do {
-                v = 0;
-                if (lane == 0) v = xr[ready_blocks];
-                v = __shfl_sync(0xffffffffu, v, 0);
-                if (v < (unsigned)p.xp_need) {
-                    if (ctl[2] || (p.abort && *p.abort) || rs_now_ns() - t0 > RS_TIMEOUT_NS) {
-                        if (p.abort) *p.abort = 1u;
-                        ctl[2] = 1;
-                        if (p.error) { *reinterpret_cast<volatile int *>(p.error) = 1; __threadfence_system(); }
-                        v = 0xffffffffu;
-                    } else __nanosleep(40);
-                }
-            } while (v < (unsigned)p.xp_need);
-            ready_blocks++;
-        }
-        if (ready_blocks != before) __threadfence();     // acquire side of the counters
-        flag_next = 0;
-        if (ready_blocks < nblocks && lane == 0) flag_next = xr[ready_blocks];
-    };
-    unsigned char *const stg = smem + LT::OFF_STG + warp * 256;
-    __nv_bfloat16 *const sg = reinterpret_cast<__nv_bfloat16 *>(stg) + (2 * tg) * 8 + g;
-    const uint4 *const chunk_src = reinterpret_cast<const uint4 *>(stg + (lane & 15) * 16);
-    float2 *const xch_mine = reinterpret_cast<float2 *>(smem + LT::OFF_XCH) + (ch * 2 + kh) * 32 + lane;
-    const float2 *const xch_peer = reinterpret_cast<const float2 *>(smem + LT::OFF_XCH) + (ch * 2 + (kh ^ 1)) * 32 + lane;
-    const uint32_t dst_local0 = sbase + LT::OFF_H + cpl * LT::PLANE + cu * LT::HSB + (colbase + 16 * ch + 8 * kh) * 2;
-    const uint32_t bar0 = sbase + LT::OFF_BAR;
-    const int r0 = (lane >> 4) * (CS / 2);
-    uint32_t phase_bits = 0;
-    int pend_hi = -1;                                    // lane 0: block whose completion this warp still has to publish
-    int fcnt = 0, blk = 0;                               // frames finished in the current block, current block
-
-    cluster.sync();
-    if (p.started != nullptr && tid == 0) {
-        if (atomicAdd(p.started, 1u) == gridDim.x - 1) { *p.host_go = p.epoch; __threadfence_system(); }
-    }
-
-    // Grouped schedule: the sub-batches of a step are processed in groups of GP = 2.  A group first issues the MMAs of both
-    // of its sub-batches back to back (the tensor pipe stays busy for 2 x 48 MMAs per warp), then runs ONE joint epilogue
-    // whose two independent dependency chains (K-half exchange, tanh, bf16 split, staging, stores, DSMEM send) interleave.
-    // With NSUB = 4 a step is two such groups, and the h a group sends has a whole other group's time to cross DSMEM.
-    constexpr int GP = 2, NG = NSUB / GP;
-    unsigned char *const stg2[GP] = {stg, smem + LT::OFF_STG + RS_MATH_WARPS * 256 + warp * 256};
-    for (int s = 0; s < T; s++) {
-        const int par = s & 1;
-        const bool more = s + 1 < T;
-        if (ready_blocks < nblocks) advance_blocks(s);
-#pragma unroll
-        for (int grp = 0; grp < NG; grp++) {
-            float c[GP][4], xn[GP][2];
-            // ---- MMA phase of the group ----
-#pragma unroll
-            for (int u = 0; u < GP; u++) {
-                const int sub = grp * GP + u;
-                const int n = nA + RS_SUB * sub;
-                xn[u][0] = 0.f; xn[u][1] = 0.f;
-                if (n < N) xn[u][0] = __ldcg(xp_base + xoff + sub * ldxp8);
-                if (n + 1 < N) xn[u][1] = __ldcg(xp_base + xoff + sub * ldxp8 + ldxp1);
-                const int bi = sub * 2 + par;
-                const uint32_t bar = bar0 + 8 * bi;
-                if (s > 0) {
-                    const uint32_t ph = (phase_bits >> bi) & 1u;
-                    if (!rs_mbar_try(bar, ph)) {
-                        const unsigned long long t0 = rs_now_ns();
-                        int spins = 0;
-                        while (!rs_mbar_try(bar, ph))
-                            if (ctl[2] || ((++spins & 255) == 0 && ((p.abort && *p.abort) || rs_now_ns() - t0 > RS_TIMEOUT_NS))) {
-                                ctl[2] = 1; if (p.abort) *p.abort = 1u; break;
-                            }
-                    }
-                    phase_bits ^= 1u << bi;
-                    if (tid == 0) rs_mbar_expect_tx(bar, LT::TX);
-                }
-                const uint32_t hb = sbase + LT::OFF_H + bi * LT::HBUF + lm_off;
-                float cm0[4] = {0.f, 0.f, 0.f, 0.f}, cm1[4] = {0.f, 0.f, 0.f, 0.f};
-                float cs0[4] = {0.f, 0.f, 0.f, 0.f}, cs1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int kp = 0; kp < KP; kp++) {
-                    uint32_t bh[4], bl[4];
-                    rs_ldmatrix_x4(bh, hb + kp * 64);
-                    rs_ldmatrix_x4(bl, hb + LT::PLANE + kp * 64);
-                    rs_mma_nv(cm0, ahi[2 * kp], bh[0], bh[1]);
-                    rs_mma_nv(cm1, ahi[2 * kp + 1], bh[2], bh[3]);
-                    rs_mma_nv(cs0, ahi[2 * kp], bl[0], bl[1]);
-                    rs_mma_nv(cs1, ahi[2 * kp + 1], bl[2], bl[3]);
-                    rs_mma_nv(cs0, alo[2 * kp], bh[0], bh[1]);
-                    rs_mma_nv(cs1, alo[2 * kp + 1], bh[2], bh[3]);
-                }
-#pragma unroll
-                for (int i = 0; i < 4; i++) c[u][i] = (cm0[i] + cm1[i]) + (cs0[i] + cs1[i]);
-                xch_mine[sub * 256] = kh == 0 ? make_float2(c[u][2], c[u][3]) : make_float2(c[u][0], c[u][1]);
-            }
-            rs_bar_sync(RS_BAR_PAIR0 + ch, 64);
-            // ---- joint epilogue of the group: two independent chains ----
-            float v[GP][2];
-#pragma unroll
-            for (int u = 0; u < GP; u++) {
-                const float2 o = xch_peer[(grp * GP + u) * 256];
-                v[u][0] = xn[u][0] + (kh == 0 ? c[u][0] + o.x : o.x + c[u][2]);
-                v[u][1] = xn[u][1] + (kh == 0 ? c[u][1] + o.y : o.y + c[u][3]);
-            }
-#pragma unroll
-            for (int u = 0; u < GP; u++) { v[u][0] = rs_tanh(v[u][0]); v[u][1] = rs_tanh(v[u][1]); }
-            if (grp == 0 && pend_hi >= 0) {               // deferred progress fence (lane 0 of one warp, once per RS_SIGNAL_BLOCKS)
-                __threadfence();
-                for (int b2 = pend_hi - (RS_SIGNAL_BLOCKS - 1); b2 <= pend_hi; b2++) atomicAdd(hdone + b2, 1u);
-                pend_hi = -1;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int u = 0; u < GP; u++) {
-                const int sub = grp * GP + u;
-                const int n = nA + RS_SUB * sub;
-                if (out_base != nullptr) {
-                    if (n < N) out_base[ooff + sub * ldo8] = v[u][0];
-                    if (n + 1 < N) out_base[ooff + sub * ldo8 + ldo1] = v[u][1];
-                }
-                __nv_bfloat16 h0, l0, h1, l1;
-                rs_split(v[u][0], h0, l0);
-                rs_split(v[u][1], h1, l1);
-                __nv_bfloat16 *sgu = reinterpret_cast<__nv_bfloat16 *>(stg2[u]) + (2 * tg) * 8 + g;
-                sgu[0] = h0; sgu[8] = h1; sgu[64] = l0; sgu[72] = l1;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int u = 0; u < GP; u++) {
-                const int sub = grp * GP + u;
-                const uint4 chunk = *reinterpret_cast<const uint4 *>(stg2[u] + (lane & 15) * 16);
-                if (plane_lane && n0 + RS_SUB * sub + cu < N) *reinterpret_cast<uint4 *>(plane_base + poff + sub * ldp8) = chunk;
-                if (more) {
-                    const uint32_t nb_off = (uint32_t)(sub * 2 + (par ^ 1));
-                    const uint32_t dst_local = dst_local0 + nb_off * LT::HBUF, bar_local = bar0 + 8 * nb_off;
-#pragma unroll
-                    for (int r = 0; r < CS / 2; r++)
-                        rs_st_async_v4(rs_mapa(dst_local, r0 + r), chunk, rs_mapa(bar_local, r0 + r));
-                }
-            }
-        }
-        // ---- frame s is finished ----
-        xoff += xstep;
-        ooff += ostep;
-        poff += pstep;
-        if (++fcnt == fpb || !more) {
-            if (hdone != nullptr && ((blk + 1) % RS_SIGNAL_BLOCKS == 0 || !more)) {
-                __syncwarp();
-                if (lane == 0) {
-                    __threadfence_block();
-                    const int grp_par = (blk / RS_SIGNAL_BLOCKS) & 1;
-                    const int last = (atomicAdd(const_cast<int *>(ctl + grp_par), 1) & (RS_MATH_WARPS - 1)) == RS_MATH_WARPS - 1;
-                    if (last) {
-                        if (more) pend_hi = blk;
-                        else {
-                            __threadfence();
-                            for (int b2 = blk - blk % RS_SIGNAL_BLOCKS; b2 <= blk; b2++) atomicAdd(hdone + b2, 1u);
-                        }
-                    }
-                }
-            }
-            fcnt = 0;
-            blk++;
-        }
-    }
-    cluster.sync();
-}
-
 bool rnn_stream_supported(const gasr_ctx *ctx, int H, int N, int L) {
     if (!ctx->cluster_ok) return false;
     if (H != 512 && H != 256 && H != 128) return false;
     if (N < 1 || L < 1 || L > RS_MAX_LAYERS) return false;
     const int groups = ceil_div(N, RS_NB);
     return groups * L <= 16;            // clusters of 8 that are co-resident on a B200 (2 per GPC)
-}
-
-template <int H, int NSUB>
-static int launch_rs2(gasr_ctx *ctx, const RnnStreamParams &p, cudaStream_t st) {
-    size_t smem = Rs2Layout<H, NSUB>::BYTES;
-    if (smem < 200 * 1024) smem = 200 * 1024;   // one CTA per SM (the register file is full anyway)
-    const unsigned bit = (H == 512 ? 16u : H == 256 ? 32u : 64u) << (NSUB == 4 ? 3 : 0);
-    if (!(ctx->attr_mask & bit)) {
-        GASR_CUDA(cudaFuncSetAttribute(rnn_stream2_kernel<H, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ctx->attr_mask |= bit;
-    }
-    cudaLaunchConfig_t cfg = {};
-    constexpr int CS = H / RS_HC;
-    cfg.gridDim = dim3(p.L * p.groups * CS);
-    cfg.blockDim = dim3(RS_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    GASR_CUDA(cudaLaunchKernelEx(&cfg, rnn_stream2_kernel<H, NSUB>, p));
-    return GASR_OK;
 }
 
 template <int H>
@@ -676,12 +390,33 @@ static int launch_rs(gasr_ctx *ctx, const RnnStreamParams &p, cudaStream_t st) {
     return GASR_OK;
 }
 
-// sub-batches per cluster: 0 = first-generation kernel; GASR_RNN_NSUB=2|4 selects the software-pipelined kernel
-int rnn_stream_default_nsub(int N) {
-    if (const char *e = getenv("GASR_RNN_NSUB")) return atoi(e);
-    (void)N;
-    return 0;       // the software-pipelined kernel (2 / 4) is correct but not yet faster per SM: opt-in
+// How many clusters of the recurrence kernel the device can hold at once (cudaOccupancyMaxActiveClusters): the streaming
+// pipeline needs ALL of its clusters resident next to the GEMM and decoder CTAs, so gasr_asr_create asks before it picks the mode.
+template <int H>
+static int rs_max_clusters(int *out) {
+    size_t smem = RsLayout<H>::BYTES;
+    if (smem < 200 * 1024) smem = 200 * 1024;
+    if (cudaFuncSetAttribute(rnn_stream_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return GASR_ERR_CUDA;
+    cudaLaunchConfig_t cfg = {};
+    constexpr int CS = H / RS_HC;
+    cfg.gridDim = dim3(CS); cfg.blockDim = dim3(RS_THREADS); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaOccupancyMaxActiveClusters(out, rnn_stream_kernel<H>, &cfg) == cudaSuccess ? GASR_OK : GASR_ERR_CUDA;
 }
+int rnn_stream_max_clusters(gasr_ctx *ctx, int H, int *clusters, int *ctas_per_cluster) {
+    (void)ctx;
+    *ctas_per_cluster = H / RS_HC;
+    if (H == 512) return rs_max_clusters<512>(clusters);
+    if (H == 256) return rs_max_clusters<256>(clusters);
+    if (H == 128) return rs_max_clusters<128>(clusters);
+    *clusters = 0;
+    return GASR_OK;
+}
+
+int rnn_stream_default_nsub(int N) { (void)N; return 0; }
 
 int launch_rnn_stream(gasr_ctx *ctx, const RnnStreamParams &p, int H, cudaStream_t st) {
     GASR_CHECK(rnn_stream_supported(ctx, H, p.N, p.L), "rnn_stream: unsupported shape H=%d N=%d L=%d", H, p.N, p.L);
@@ -698,18 +433,9 @@ int launch_rnn_stream(gasr_ctx *ctx, const RnnStreamParams &p, int H, cudaStream
                                  (reinterpret_cast<uintptr_t>(y.out_lo) & 15) == 0),
                    "rnn_stream: bf16 output planes must be 16-byte aligned");
     }
+    GASR_CHECK(p.nsub == 0, "rnn_stream: sub-batched variant was removed");
     int rc;
-    if (p.nsub == 4) {
-        GASR_CHECK(p.groups == ceil_div(p.N, 32), "rnn_stream: groups must be ceil(N / 32) with 4 sub-batches");
-        if (H == 512) rc = launch_rs2<512, 4>(ctx, p, st);
-        else if (H == 256) rc = launch_rs2<256, 4>(ctx, p, st);
-        else rc = launch_rs2<128, 4>(ctx, p, st);
-    } else if (p.nsub == 2) {
-        GASR_CHECK(p.groups == ceil_div(p.N, 16), "rnn_stream: groups must be ceil(N / 16) with 2 sub-batches");
-        if (H == 512) rc = launch_rs2<512, 2>(ctx, p, st);
-        else if (H == 256) rc = launch_rs2<256, 2>(ctx, p, st);
-        else rc = launch_rs2<128, 2>(ctx, p, st);
-    } else if (H == 512) rc = launch_rs<512>(ctx, p, st);
+    if (H == 512) rc = launch_rs<512>(ctx, p, st);
     else if (H == 256) rc = launch_rs<256>(ctx, p, st);
     else rc = launch_rs<128>(ctx, p, st);
     if (rc == GASR_OK) ctx->launches += 1;

@@ -33,6 +33,7 @@ struct RnnStreamParams {
 
 bool rnn_stream_supported(const gasr_ctx *ctx, int H, int N, int L);
 int rnn_stream_default_nsub(int N);
+int rnn_stream_max_clusters(gasr_ctx *ctx, int H, int *clusters, int *ctas_per_cluster);   // device-wide residency of the recurrence kernel
 int launch_rnn_stream(gasr_ctx *ctx, const RnnStreamParams &p, int H, cudaStream_t st);
 
 }  // namespace gasr

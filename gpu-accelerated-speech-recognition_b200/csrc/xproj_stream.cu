@@ -281,14 +281,22 @@ xproj_stream_kernel(const __grid_constant__ XsMaps maps, const XsParams p) {
                 if (!(t.kind & 16)) {
                     const int c4 = lane & 7, rsub = lane >> 3;                   // this lane: columns 4*c4..+3 of rows rsub + 4i
                     const int row0 = blk * TC_BM + qd * 32;
-                    const int ncols = (t.kind & 15) == XS_KIND_XPROJ ? 32 : (t.ldc < 32 ? t.ldc : 32);
+                    // output layer: kind bit 128 = the caller's matrix is exactly [rows, V] wide inside ldc (gasr_linear_forward):
+                    // nothing beyond column V is touched; otherwise (the pipelines' own padded buffers) 32 columns, zeros beyond V
+                    const int ncols = (t.kind & 15) == XS_KIND_XPROJ ? 32 : ((t.kind & 128) ? t.V : (t.ldc < 32 ? t.ldc : 32));
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const int r = rsub + 4 * i;
                         float4 o = stg4[r * 9 + c4];
                         o.x += badd.x; o.y += badd.y; o.z += badd.z; o.w += badd.w;
-                        if (row0 + r < p.M && 4 * c4 < ncols)
-                            __stcg(reinterpret_cast<float4 *>(t.C + (size_t)(row0 + r) * t.ldc + n0 + c * 32 + 4 * c4), o);
+                        if (row0 + r >= p.M || 4 * c4 >= ncols) continue;
+                        float *dst = t.C + (size_t)(row0 + r) * t.ldc + n0 + c * 32 + 4 * c4;
+                        if (4 * c4 + 4 <= ncols) __stcg(reinterpret_cast<float4 *>(dst), o);
+                        else {                                                   // scalar tail of the last group of four
+                            dst[0] = o.x;
+                            if (4 * c4 + 1 < ncols) dst[1] = o.y;
+                            if (4 * c4 + 2 < ncols) dst[2] = o.z;
+                        }
                     }
                 }
                 __syncwarp();
@@ -345,7 +353,7 @@ int launch_xproj_stream(gasr_ctx *ctx, const XsMaps &maps, const XsParams &p, in
 // persistent GEMM above with a single output-layer target whose dependencies are preset -- TMA-fed, fp32-grade 3-term
 // split, log-softmax in the epilogue.
 bool linear_tc_supported(int rows, int in, int out, int ldy, const float *y, int act) {
-    return act == GASR_ACT_LOGSOFTMAX && out >= 1 && out <= 32 && in >= 1024 && rows >= 4096 && ldy >= 32 && ldy % 4 == 0 &&
+    return act == GASR_ACT_LOGSOFTMAX && out >= 1 && out <= 32 && in >= 1024 && rows >= 4096 && ldy >= out && ldy % 4 == 0 &&
            (reinterpret_cast<uintptr_t>(y) & 15) == 0;
 }
 
@@ -381,7 +389,8 @@ int launch_linear_logsoftmax_tc(gasr_ctx *ctx, const float *x, int ldx, const fl
     p.abort = flags + 2 * (size_t)nb;
     p.error = reinterpret_cast<int *>(flags + 2 * (size_t)nb + 8);
     XsTarget &t = p.target[0];
-    t.kind = XS_KIND_LOGSOFTMAX; t.cta0 = 0; t.nctas = nb < ctx->sm_count ? nb : ctx->sm_count;
+    t.kind = XS_KIND_LOGSOFTMAX | 128; t.cta0 = 0; t.nctas = nb < ctx->sm_count ? nb : ctx->sm_count;   // 128: columns >= out of y stay untouched
+    // (every dependency of this launch is preset, so its bounded waits cannot expire; the abort / error words are not read back)
     t.n_tiles = 1; t.bn = 32; t.kblocks = Kp / TC_BK; t.terms = 3; t.V = out;
     t.C = y; t.ldc = ldy; t.bias = bpad;
     t.src_done = flags; t.src_need = 1; t.dst_ready = flags + nb;
