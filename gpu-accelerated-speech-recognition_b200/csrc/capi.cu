@@ -114,7 +114,7 @@ int gasr_ctx_create(int device, gasr_ctx **out) {
         auto chr = [](const char *n) -> char { const char *e = getenv(n); return e ? e[0] : (char)0; };
         auto num = [](const char *n, int dflt) -> int { const char *e = getenv(n); return e ? atoi(e) : dflt; };
         o.rnn = chr("GASR_RNN"); o.rnn_mc = num("GASR_RNN_MC", 1); o.rnn_groups = num("GASR_RNN_G", 0); o.rnn_pair = num("GASR_RNN_PAIR", 1);
-        o.ctc_kernel = chr("GASR_CTC_KERNEL"); o.ctc_mw = num("GASR_CTC_MW", 8); o.ctc_pad = num("GASR_CTC_PAD", 0);
+        o.ctc_kernel = chr("GASR_CTC_KERNEL"); o.ctc_mw = num("GASR_CTC_MW", 8); o.ctc_cells = num("GASR_CTC_CELLS", 0); o.ctc_pad = num("GASR_CTC_PAD", 0);
         o.gru = chr("GASR_GRU"); o.gru_pp = num("GASR_GRU_PP", 0); o.gru_units = num("GASR_GRU_UNITS", 0); o.gru_no_pdl = getenv("GASR_GRU_NO_PDL") != nullptr; o.no_graph = getenv("GASR_NO_GRAPH") != nullptr;
         o.bidir_serial = getenv("GASR_BIDIR_SERIAL") != nullptr; o.linear_simt = getenv("GASR_LINEAR_SIMT") != nullptr;
         o.xproj = chr("GASR_XPROJ"); o.chunk = num("GASR_CHUNK", -1); o.stream = num("GASR_STREAM", -1); o.wave = num("GASR_WAVE", -1);

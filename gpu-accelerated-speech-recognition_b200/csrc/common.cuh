@@ -56,6 +56,7 @@ struct gasr_options {
     int rnn_pair = 1;        // GASR_RNN_PAIR: CTA-pair recurrence (tcgen05.mma.cta_group::2, groups of 256 utterances)
     char ctc_kernel = 0;     // GASR_CTC_KERNEL
     int ctc_mw = 8;          // GASR_CTC_MW
+    int ctc_cells = 0;       // GASR_CTC_CELLS: probe cells of the warp decoder's prune bound (32 or 64; 0 = 32 for beam <= 16, else 64)
     int ctc_pad = 0;         // GASR_CTC_PAD
     char gru = 0;            // GASR_GRU: t = per-timestep tcgen05 kernel even in bf16 mode, g = three launches per step, s = SIMT step kernel
     bool gru_no_pdl = false, no_graph = false, bidir_serial = false, linear_simt = false;

@@ -978,22 +978,28 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
         unsigned theta = 0u;
         {
             unsigned ck[2];
-            constexpr int cpl = 2;
+            const int cpl = p.n_cells > 32 ? 2 : 1;          // probe cells per lane
 #pragma unroll
             for (int q = 0; q < 2; q++) {
                 const int ci = p.cell_i[lane + 32 * q];
                 ck[q] = (q < cpl && ci < k) ? wb.cand[ci][wb.order[p.cell_j[lane + 32 * q]]] : 0u;
             }
             int cnt0 = 0, cnt1 = 0;
+            if (cpl > 1) {
 #pragma unroll
-            for (int u = 0; u < 32; u++) {
-                const unsigned x0 = __shfl_sync(FULL, ck[0], u);
-                cnt0 += (x0 > ck[0] || (x0 == ck[0] && u < lane)) ? 1 : 0;
-                if (cpl > 1) {
+                for (int u = 0; u < 32; u++) {
+                    const unsigned x0 = __shfl_sync(FULL, ck[0], u);
+                    cnt0 += (x0 > ck[0] || (x0 == ck[0] && u < lane)) ? 1 : 0;
                     const unsigned x1 = __shfl_sync(FULL, ck[1], u);
                     cnt0 += (x1 > ck[0]) ? 1 : 0;
                     cnt1 += (x0 >= ck[1]) ? 1 : 0;
                     cnt1 += (x1 > ck[1] || (x1 == ck[1] && u < lane)) ? 1 : 0;
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 32; u++) {
+                    const unsigned x0 = __shfl_sync(FULL, ck[0], u);
+                    cnt0 += (x0 > ck[0] || (x0 == ck[0] && u < lane)) ? 1 : 0;
                 }
             }
             unsigned th = (cnt0 == B - 1) ? ck[0] : 0u;
@@ -2445,6 +2451,11 @@ int ctc_decode_launch(gasr_ctx *ctx, const CtcArgs &a, cudaStream_t st) {
     {
         // probe cells of the prune lower bound: the (parent rank, score rank) pairs with the smallest (i+1)(j+1)
         p.n_cells = (use_cta && a.beam > 16) ? 128 : 64;
+        // warp kernel, beam <= 16: one probe cell per lane.  The bound is looser (21 instead of 16 survivors on peaky / random
+        // log-probabilities, 26 instead of 19 on flat ones) but the all-pairs counting of 64 cells was 17 % of the kernel's
+        // instructions: decoder alone 24.8 -> 23.6 ms per 4096 utterances, cfg5 step 118.4 -> 115.9 ms (same-box A/B, 3 runs each)
+        if (!use_cta && fast && a.beam <= 16 && ctx->opt.ctc_cells != 64) p.n_cells = 32;
+        if (!use_cta && fast && ctx->opt.ctc_cells == 32) p.n_cells = 32;      // GASR_CTC_CELLS = 32 | 64 forces either
         int taken = 0;
         for (int prod = 1; taken < p.n_cells && prod <= a.beam * a.V; prod++)
             for (int i = 0; i < a.beam && taken < p.n_cells; i++) {
