@@ -55,6 +55,16 @@ def measured_peaks():
     return 6650.0, 1400.0, "fallback"
 
 
+def rec_traffic(wave):
+    """DRAM bytes (read + write) of one recurrence launch from the committed `ncu --set full` capture (profiles/), if that
+    capture was taken at this batch size; None otherwise."""
+    path = os.path.join(ROOT, "profiles", "r2_rnn_wide2_traffic.json")
+    if not os.path.exists(path):
+        return None
+    t = json.load(open(path))
+    return t["dram_bytes_per_launch"] if int(t.get("utterances_per_launch", 0)) == int(wave) else None
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -448,10 +458,10 @@ def main():
                     "d2h_bytes_per_step": int(args.utts * (c["T"] + 1 + 8))},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "rnn_wide_kernel (tcgen05 recurrence, one launch per layer and 50-frame chunk of a batch; "
+            "roofline": {"kernel": "rnn_wide2_kernel (tcgen05 CTA-pair recurrence, one launch per layer and 50-frame chunk of a batch; "
                                    "durations measured inside the running pipeline, where it shares the GPU with the GEMM and decoder kernels)",
                          "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_kind,
+                         "traffic": rec_traffic(args.wave), "peak_source": peak_kind,
                          "algorithmic_bytes_per_launch": rec_bytes_total / n_rec, "ms_per_launch": rec_ms_per_launch,
                          "launches_per_step": n_rec},
             "whole_path_hbm": {"achieved": whole, "peak": hbm_peak, "unit": "GB/s", "frac": whole / hbm_peak,
@@ -471,6 +481,37 @@ def main():
         if world == 1 and not args.no_checks:
             job.close()                                      # free the job's buffers before the other configs allocate theirs
             job = None
+            # every stage ALONE: one batch through a pipeline whose stages all run on one stream (GASR_WAVE_SERIAL, read when the
+            # context is created), per-launch CUDA events -- what a stage costs when it does not share the GPU
+            os.environ["GASR_WAVE_SERIAL"] = "1"
+            try:
+                j2 = gasr.Job(local, c["T"], args.wave, c["D"], c["H"], c["L"], c["V"], c["beam"], 0, synth.VOCAB29, lanes=1)
+            finally:
+                del os.environ["GASR_WAVE_SERIAL"]
+            j2.set_weights(*w, fc_w, fc_b)
+            c2 = j2.lane_context(0)
+            d2 = c2.malloc(batch_bytes)
+            c2.synth_spectrogram(d2, SEED_X, c["T"], args.wave, c["D"], first_utt=0)
+            j2.run_device([d2])
+            j2.profile(True)
+            j2.run_device([d2])
+            alone_ms, alone_n = j2.stage_times()
+            j2.close()
+            nb = b_hi - b_lo
+            rows1 = args.wave * c["T"]
+            rec_alone = rows1 * c["H"] * 4 * 2 * c["L"] / (alone_ms[1] * 1e-3) / 1e9
+            line["stages_alone_ms_per_step"] = {
+                "projection_gemm": alone_ms[0] * nb, "recurrence": alone_ms[1] * nb, "linear_logsoftmax": alone_ms[2] * nb,
+                "ctc_decode": alone_ms[3] * nb,
+                "note": f"one batch of {args.wave} utterances with all stages on one stream, sums of per-launch durations x {nb} batches; "
+                        "the recurrence launches occupy 64 of the 148 SMs, the other stages the whole GPU"}
+            line["roofline"]["alone"] = {"achieved": rec_alone, "frac": rec_alone / hbm_peak, "ms_per_launch": alone_ms[1] / max(alone_n[1], 1),
+                                         "note": "the same launches with nothing else on the GPU (64 SMs each)"}
+            line["stage_rooflines_alone"] = {
+                "projection_gemm": rl("tensor", proj_flop / nb, alone_ms[0], tc_peak, "TFLOP/s", 1e12),
+                "linear_logsoftmax": rl("hbm", lin_bytes / nb, alone_ms[2], hbm_peak, "GB/s", 1e9),
+                "ctc_decode": rl("hbm", dec_bytes / nb, alone_ms[3], hbm_peak, "GB/s", 1e9),
+            }
             line["other_configs"] = other_configs(gasr, local)
         if world == 1 and not args.no_cpu_baseline:
             # bounded sample: batches of 64 utterances on all host threads until ~10 s of CPU work are spent

@@ -429,7 +429,7 @@ int rnn_forward_impl(gasr_ctx *ctx, int cell, int bidir, int T, int N, int in, i
         }
         for (int d = 0; d < D && rc == GASR_OK; d++) {
             const int i = l * D + d;
-            GASR_CHECK(w_ih[i] && w_hh[i] && b_ih[i] && b_hh[i] && hiddens[l], "rnn_forward: null layer parameter");
+            if (!(w_ih[i] && w_hh[i] && b_ih[i] && b_hh[i] && hiddens[l])) { set_error("rnn_forward: null layer parameter"); rc = GASR_ERR_INVALID; break; }
             const bool side = fork && d == 1;
             Workspace &wr = side ? ctx->ws_rnn_b : ctx->ws_rnn;
             float *xproj = static_cast<float *>(wr.ptr);
@@ -439,10 +439,16 @@ int rnn_forward_impl(gasr_ctx *ctx, int cell, int bidir, int T, int N, int in, i
                                      hiddens[l], D * H, d * H, precision, xproj, bias, side ? st_b : st, side ? nullptr : prof);
             ctx->ws_sel = 0;
         }
-        if (fork) {
+        if (fork && rc == GASR_OK) {
             GASR_CUDA(cudaEventRecord(ctx->ev_bi[1], st_b));
             GASR_CUDA(cudaStreamWaitEvent(st, ctx->ev_bi[1], 0));
         }
+    }
+    if (rc != GASR_OK && fork) {
+        // a failed layer must not leave the other direction's work running on the side stream behind the caller's back
+        cudaStreamSynchronize(st_b);
+        cudaStreamSynchronize(st);
+        cudaGetLastError();
     }
     return rc;
 }
@@ -839,6 +845,18 @@ static int asr_run_streaming(gasr_asr *a, const float *x_dev, const float *x_hos
     const int rec_ctas_per_layer = rec_groups * (H / 64);
     a->epoch += 1;
     a->host_words[1] = 0;
+    // Any early return below (a failed launch, a CUDA error) must not leave persistent kernels running behind the caller's
+    // back: the guard raises the pipeline's abort word (every in-kernel wait polls it) and joins the pipeline's streams.
+    struct Join {
+        gasr_ctx *ctx; unsigned *abort_word; bool done = false;
+        ~Join() {
+            if (done) return;
+            const unsigned one = 1u;
+            cudaMemcpyAsync(abort_word, &one, sizeof(one), cudaMemcpyHostToDevice, ctx->side[4]);
+            for (cudaStream_t s : {ctx->side[4], ctx->side[0], ctx->side[1], ctx->side[2], ctx->side[3], ctx->stream}) cudaStreamSynchronize(s);
+            cudaGetLastError();
+        }
+    } join{ctx, misc + 1};
     // everything that may synchronise the device (allocations, function attributes) happens before the first persistent
     // kernel starts: once they run they wait for each other, not for the host
     CtcArgs ca = {a->logp, GASR_DOMAIN_LOG, T, N, c.V, a->ldp, c.beam, c.blank, a->vocab.data(), c.max_len,
@@ -1038,6 +1056,7 @@ static int asr_run_streaming(gasr_asr *a, const float *x_dev, const float *x_hos
     GASR_CUDA(cudaStreamWaitEvent(main_st, a->ev_d1, 0));
     if (x_host != nullptr) GASR_CUDA(cudaStreamWaitEvent(main_st, a->ev_cp, 0));
     GASR_CUDA(cudaStreamSynchronize(main_st));
+    join.done = true;                                           // everything has completed (main_st was synchronised)
     if (a->host_words[1] != 0) {
         set_error("streaming pipeline: watchdog fired (code %d): a persistent kernel waited too long for its producer", a->host_words[1]);
         return GASR_ERR_CUDA;
@@ -1047,6 +1066,7 @@ static int asr_run_streaming(gasr_asr *a, const float *x_dev, const float *x_hos
     cudaEventElapsedTime(&a->stage_ms[1], a->ev_r0, a->ev_r1); a->stage_launches[1] = 1;
     cudaEventElapsedTime(&a->stage_ms[3], a->ev_d0, a->ev_d1); a->stage_launches[3] = 1;
     ca.lp_ready = nullptr;
+    join.done = true;
     return ctc_decode_finish(ctx, ca);
 }
 

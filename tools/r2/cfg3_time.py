@@ -1,7 +1,7 @@
 import os, sys, time
 sys.path.insert(0, "gpu-accelerated-speech-recognition_b200"); sys.path.insert(0, ".")
 import numpy as np, gasr, synth
-T, N, D, H, L, V, beam = 1000, 256, 161, 800, 5, 29, 32
+T, N, D, H, L, V, beam = (int(sys.argv[2]) if len(sys.argv) > 2 else 1000), 256, 161, 800, 5, 29, 32
 w = synth.rnn_weights(7, D, H, L, cell_gates=3, bidir=True); fc = synth.fc_weights(8, 2 * H, V)
 ctx = gasr.Context(0)
 pipe = gasr.AsrPipeline(ctx, gasr.CELL_GRU, True, T, N, D, H, L, V, beam, 0, synth.VOCAB29, precision=gasr.PREC_BF16)
