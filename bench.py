@@ -65,6 +65,40 @@ def rec_traffic(wave):
     return t["dram_bytes_per_launch"] if int(t.get("utterances_per_launch", 0)) == int(wave) else None
 
 
+def bind_host_memory_to_gpu_node(local):
+    """Pinned input buffers should live on the NUMA node the GPU hangs off: with one process per GPU and no CPU binding every
+    rank's pages land on the node it happens to run on, and the H2D copies of the GPUs of the other socket cross the socket
+    link.  MPOL_PREFERRED for this process (set_mempolicy) before the buffers are allocated; a no-op on single-node hosts.
+    GASR_BENCH_NUMA=0 switches it off.  Returns the node or None."""
+    if os.environ.get("GASR_BENCH_NUMA", "1") == "0":
+        return None
+    try:
+        import ctypes
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        if len(nodes) < 2:
+            return None
+        idx = str(local)
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",")]
+            if local < len(ids):
+                idx = ids[local]
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", idx],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]                                   # sysfs spells the PCI domain with four digits
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        mask = ctypes.c_ulong(1 << node)
+        libc = ctypes.CDLL("libc.so.6", use_errno=True)
+        if libc.syscall(238, 1, ctypes.byref(mask), 64) != 0:          # SYS_set_mempolicy (x86-64), MPOL_PREFERRED
+            return None
+        return node
+    except Exception:
+        return None
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -341,6 +375,7 @@ def main():
         return d
 
     x_dev = [make_batch(b) for b in range(b_lo, b_hi)]
+    numa_node = bind_host_memory_to_gpu_node(local)
     x_pin = []
     for d in x_dev:
         h = ctx0.pinned((c["T"] * args.wave, c["D"]))
@@ -450,6 +485,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "utterances": args.utts, "utterances_per_batch": args.wave,
                        "batches_in_flight_per_gpu": args.lanes, "batches_per_gpu": b_hi - b_lo,
+                       "pinned_host_memory_numa_node_rank0": numa_node,
                        "l2": "per-batch working set (x, xproj, hidden planes: ~16 MB per utterance) exceeds the 126 MB L2 many times over",
                        "init": "weights U(+-1/sqrt(H)) seed 4321, inputs U[0,1) seed 1234 (splitmix64, generated on the device, "
                                "bit-identical to synth.py)"},
