@@ -369,7 +369,7 @@ namespace gasr {
 static int rnn_layer_direction(gasr_ctx *ctx, int cell, int T, int N, int in_l, int H, const float *src, int ld_src,
                                const float *w_ih, const float *w_hh, const float *b_ih, const float *b_hh, int reverse,
                                float *out, int ldo, int col0, int precision, float *xproj, float *bias,
-                               cudaStream_t st, StageEvents *prof) {
+                               cudaStream_t st, StageEvents *prof, bool concurrent = false) {
     const int G = cell == GASR_CELL_GRU ? 3 : 1;
     if (cell == GASR_CELL_TANH) {
         GASR_TRY(launch_matadd(ctx, b_ih, H, b_hh, H, bias, H, 1, H, 1.0f, st));   // (b_hh + b_ih), RNN_Cell.cu:10
@@ -393,7 +393,7 @@ static int rnn_layer_direction(gasr_ctx *ctx, int cell, int T, int N, int in_l, 
     RnnLayerArgs a;
     a.cell = cell; a.T = T; a.N = N; a.H = H; a.reverse = reverse;
     a.xproj = xproj; a.ldxp = G * H; a.w_hh = w_hh; a.b_hh = b_hh; a.out = out; a.ldo = ldo; a.col0 = col0;
-    a.precision = precision;
+    a.precision = precision; a.concurrent = concurrent;
     GASR_TRY(launch_rnn_recurrence(ctx, a, st));
     if (prof) GASR_TRY(prof->mark(1, st));
     return GASR_OK;
@@ -436,7 +436,7 @@ int rnn_forward_impl(gasr_ctx *ctx, int cell, int bidir, int T, int N, int in, i
             float *bias = reinterpret_cast<float *>(static_cast<unsigned char *>(wr.ptr) + xp_bytes);
             ctx->ws_sel = side ? 1 : 0;
             rc = rnn_layer_direction(ctx, cell, T, N, in_l, H, src, in_l, w_ih[i], w_hh[i], b_ih[i], b_hh[i], d,
-                                     hiddens[l], D * H, d * H, precision, xproj, bias, side ? st_b : st, side ? nullptr : prof);
+                                     hiddens[l], D * H, d * H, precision, xproj, bias, side ? st_b : st, side ? nullptr : prof, fork);
             ctx->ws_sel = 0;
         }
         if (fork && rc == GASR_OK) {

@@ -159,8 +159,13 @@ struct RnnLayerArgs {
     int ldo, col0;
     int s0 = 0, s1 = 0;   // steps [s0, s1) only (s1 = 0: all T); h before step s0 is read back from `out`
     int precision = GASR_PREC_FP32;   // GASR_PREC_BF16: the GRU recurrence may use single-plane fp16 operands (gru_seq.cu)
+    bool concurrent = false;          // another recurrence (the other direction of the layer) runs at the same time
 };
 int launch_rnn_recurrence(gasr_ctx *ctx, const RnnLayerArgs &a, cudaStream_t st);
+
+// wide hidden layer, a handful of utterances: persistent fp32 kernel with W_hh resident in shared memory (rnn_resident.cu)
+bool rnn_resident_supported(const gasr_ctx *ctx, const RnnLayerArgs &a);
+int launch_rnn_resident(gasr_ctx *ctx, const RnnLayerArgs &a, void *ws, cudaStream_t st);
 
 // persistent GRU recurrence with W_hh resident in shared memory (gru_seq.cu; GASR_PREC_BF16 mode)
 bool gru_seq_supported(const gasr_ctx *ctx, int T, int N, int H, int ldxp, int ldo, int col0);

@@ -594,6 +594,13 @@ int launch_rnn_recurrence(gasr_ctx *ctx, const RnnLayerArgs &a, cudaStream_t st)
         GASR_CUDA(cudaGetLastError());
         return GASR_OK;
     }
+    if (a.cell == GASR_CELL_TANH && !(ctx->opt.rnn == 'f') && rnn_resident_supported(ctx, a)) {
+        // wide hidden layer, a few utterances (cfg1: H = 2048, one utterance): W_hh resident in the shared memory of the whole
+        // GPU for the sequence, fp32, one launch (rnn_resident.cu)
+        Workspace &wsg = ctx->ws_sel ? ctx->ws_gru_b : ctx->ws_gru;
+        GASR_TRY(ws_reserve(ctx, wsg, 256));
+        return launch_rnn_resident(ctx, a, wsg.ptr, st);
+    }
     // fallback: one kernel per timestep
     dim3 grid(ceil_div(a.H, 128), a.N);
     for (int s = a.s0; s < (a.s1 > 0 ? a.s1 : a.T); s++) {

@@ -80,6 +80,24 @@ def test_cfg1_baseline_config_hot_path(gasr, ctx, O):
     pipe.close()
 
 
+@pytest.mark.parametrize("T,N,D,H,L", [(40, 1, 64, 2048, 2), (25, 3, 40, 1500, 1), (30, 4, 33, 1024, 2)])
+def test_wide_hidden_layer_small_batch_resident_recurrence(gasr, O, T, N, D, H, L):
+    """cfg1's recurrence shape class (H = 2048, a handful of utterances): one persistent fp32 launch per layer with W_hh resident
+    in the shared memory of the whole GPU (rnn_resident.cu) instead of one kernel per timestep; every layer against the oracle."""
+    import synth
+    x = synth.spectrogram_batch(H + N, T, N, D)
+    w_ih, w_hh, b_ih, b_hh = synth.rnn_weights(H + 1, D, H, L)
+    c = gasr.Context(0)
+    n0 = c.launch_count()
+    out = _run_rnn(gasr, c, gasr.CELL_TANH, False, T, N, D, H, L, x, w_ih, w_hh, b_ih, b_hh)
+    launches = c.launch_count() - n0
+    c.close()
+    assert launches < L * 12, f"{launches} launches: the per-timestep fallback ran"
+    ref = O.rnn_forward(x, T, N, w_ih, w_hh, b_ih, b_hh, nthreads=8)
+    for l in range(L):
+        assert np.abs(out[l] - ref[l]).max() < AM_TOL, f"layer {l}"
+
+
 def test_wide_linear_relu_on_tensor_cores(gasr, ctx, O):
     """The DeepSpeech FC layers (main.cpp:31-45, baseline/model.py:22-35: 2048-wide Linear + ReLU) run on the tcgen05 tile
     engine with bias + ReLU in the epilogue (Linear.cu:3-10,42-49 semantics), fp32-grade."""
