@@ -835,7 +835,10 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
         {
             const unsigned mine = active ? f2ord(lp) : 0u;
             int lr = 0;
-#pragma unroll
+            // (partially unrolled on purpose, here and in the two probe-cell loops below: fully unrolled the kernel was 7008 SASS
+            // instructions and stalled on instruction fetch with 4096 warps in different phases of the frame; 4424 now (with the rolled tie loop),
+            // decoder alone -9 %, cfg5 step -2.5 %, same-box A/B)
+#pragma unroll 4
             for (int u = 0; u < 32; u++) {
                 const unsigned x = __shfl_sync(FULL, mine, u);
                 lr += (x > mine || (x == mine && u < lane)) ? 1 : 0;
@@ -986,7 +989,7 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
             }
             int cnt0 = 0, cnt1 = 0;
             if (cpl > 1) {
-#pragma unroll
+#pragma unroll 4
                 for (int u = 0; u < 32; u++) {
                     const unsigned x0 = __shfl_sync(FULL, ck[0], u);
                     cnt0 += (x0 > ck[0] || (x0 == ck[0] && u < lane)) ? 1 : 0;
@@ -996,7 +999,7 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
                     cnt1 += (x1 > ck[1] || (x1 == ck[1] && u < lane)) ? 1 : 0;
                 }
             } else {
-#pragma unroll
+#pragma unroll 4
                 for (int u = 0; u < 32; u++) {
                     const unsigned x0 = __shfl_sync(FULL, ck[0], u);
                     cnt0 += (x0 > ck[0] || (x0 == ck[0] && u < lane)) ? 1 : 0;
@@ -1043,10 +1046,9 @@ __global__ void __launch_bounds__(256) ctc_beam_warp_kernel(const CtcParams p) {
                         const uint4 k4 = *reinterpret_cast<const uint4 *>(&wb.surv_key[o]);
                         rank += (k4.x > key) + (k4.y > key) + (k4.z > key) + (k4.w > key);
                         if (k4.x == key || k4.y == key || k4.z == key || k4.w == key) {
-                            const unsigned kk[4] = {k4.x, k4.y, k4.z, k4.w};
-#pragma unroll
+#pragma unroll 1
                             for (int j = 0; j < 4; j++) {
-                                if (kk[j] != key || o + j == sidx || o + j >= ns) continue;
+                                if (wb.surv_key[o + j] != key || o + j == sidx || o + j >= ns) continue;
                                 if (t == 0) rank += o + j < sidx;
                                 else {
                                     const int oiv = wb.surv_iv[o + j];
