@@ -53,5 +53,31 @@ public:
             bestResults.push_back(std::make_pair(std::string(paths.data() + (size_t)i * max_len, lens[i]), scores[i]));
         return bestResults;
     }
+
+    /* What baseline/main.py:45-46 takes from its decoder on top of that: per-utterance frame counts in (seqLens[batchSize],
+     * 1..timestep; NULL = all), per-token timesteps out (one vector per utterance: the frame at which the prefix ending in that
+     * character first entered the beam; pass NULL when not wanted). */
+    std::vector<std::pair<std::string, float> > decode(cuMatrix<float> *seqProb, int timestep, int batchSize, const int *seqLens,
+                                                       std::vector<std::vector<int> > *timesteps) {
+        if (seqProb->getCols() != vocabSize) {
+            printf("Error: inconsistent vocabulary size in CTC decoder");
+            exit(1);
+        }
+        const int max_len = timestep + 1;
+        std::vector<char> paths((size_t)batchSize * max_len);
+        std::vector<int> lens(batchSize), ts(timesteps ? (size_t)batchSize * max_len : 0);
+        std::vector<float> scores(batchSize);
+        gasr_cxx::check(gasr_ctc_decode_ex(gasr_cxx::ctx(), seqProb->getDev(), domain, timestep, batchSize, vocabSize,
+                                           seqProb->getCols(), beamWidth, blankID, vocab, max_len, 1, seqLens, paths.data(),
+                                           lens.data(), scores.data(), NULL, timesteps ? ts.data() : NULL),
+                        "CTCBeamSearch::decode");
+        std::vector<std::pair<std::string, float> > bestResults;
+        if (timesteps) timesteps->clear();
+        for (int i = 0; i < batchSize; i++) {
+            bestResults.push_back(std::make_pair(std::string(paths.data() + (size_t)i * max_len, lens[i]), scores[i]));
+            if (timesteps) timesteps->push_back(std::vector<int>(ts.begin() + (size_t)i * max_len, ts.begin() + (size_t)i * max_len + lens[i]));
+        }
+        return bestResults;
+    }
 };
 #endif

@@ -64,6 +64,22 @@ int main() {
     std::vector<std::pair<std::string, float> > best = decoder->decode(seqProb, 10, 1);
     EXPECT(best.size() == 1 && best[0].first == "cbacbc", "ctc path = %s", best[0].first.c_str());
     EXPECT(best[0].second == 1.9566051e-3f, "ctc prob = %.9g", best[0].second);
+    // per-utterance frame counts in, per-token timesteps out (what baseline/main.py:45-46 takes from its decoder)
+    {
+        std::vector<std::vector<int> > ts;
+        int full_len[1] = {10}, short_len[1] = {4};
+        std::vector<std::pair<std::string, float> > b2 = decoder->decode(seqProb, 10, 1, full_len, &ts);
+        EXPECT(b2[0].first == best[0].first && b2[0].second == best[0].second, "lens = T changes nothing");
+        EXPECT(ts.size() == 1 && ts[0].size() == 6, "one timestep per character");
+        for (size_t i = 1; i < ts[0].size(); i++) EXPECT(ts[0][i - 1] < ts[0][i] && ts[0][i] < 10, "timesteps increase");
+        cuMatrix<float> *first4 = new cuMatrix<float>(4, 4, 1);
+        for (int j = 0; j < first4->getLen(); j++) first4->getHost()[j] = test[j];
+        first4->toGpu();
+        std::vector<std::pair<std::string, float> > want = decoder->decode(first4, 4, 1);
+        b2 = decoder->decode(seqProb, 10, 1, short_len, NULL);
+        EXPECT(b2[0].first == want[0].first && b2[0].second == want[0].second, "lens = 4 decodes the first four frames: %s vs %s",
+               b2[0].first.c_str(), want[0].first.c_str());
+    }
 
     // matrixMul / matrixAdd
     float a[4] = {1, 2, 3, 4}, b[4] = {5, 6, 7, 8};
