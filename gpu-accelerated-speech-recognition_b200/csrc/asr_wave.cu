@@ -139,8 +139,18 @@ int wave_create(gasr_asr *a) {
         for (int l = 0; l < L; l++) w->st_g[l] = w->st_r[l] = w->st_in;
         w->serial = true;
     } else {
-        mk(&w->st_in, prio_mid); mk(&w->st_fc, prio_mid); mk(&w->st_dec, prio_lo);
-        for (int l = 0; l < L; l++) { mk(&w->st_g[l], prio_mid); mk(&w->st_r[l], prio_hi); }
+        // Stream priorities.  Favouring the recurrences (the longest dependency chain) is right for a small batch, where the chain
+        // sets the time (1024 utterances: 18.5 ms vs 18.9 with equal priorities); with more utterances the recurrence launches
+        // (64 SMs each, mostly waiting on TMA latency) then take SMs from the stages that use them better: equal priorities give
+        // 2048 utterances 32.4 -> 27.5 ms, 4096 58.6 -> 55.7 ms, the 8192-utterance step 116.5 -> 110.7 ms (same-box A/B).
+        // GASR_WAVE_PRIO: 0 = recurrences > GEMMs > decoder, 1 = all equal, 2 = decoder > GEMMs > recurrences (24.6 ms at 1024),
+        // 3 = GEMMs > recurrences > decoder (117 ms), 4 = decoder > recurrences > GEMMs, 5 = decoder = GEMMs > recurrences
+        const int pm = ctx->opt.wave_prio >= 0 ? ctx->opt.wave_prio : (c.N <= 1024 ? 0 : 1);
+        const int p_rec = pm == 1 ? prio_lo : pm == 2 ? prio_lo : pm == 3 ? prio_mid : pm == 4 ? prio_mid : pm == 5 ? prio_lo : prio_hi;
+        const int p_gemm = pm == 1 ? prio_lo : pm == 3 ? prio_hi : pm == 4 ? prio_lo : pm == 5 ? prio_hi : prio_mid;
+        const int p_dec = (pm == 2 || pm == 4 || pm == 5) ? prio_hi : prio_lo;
+        mk(&w->st_in, p_gemm); mk(&w->st_fc, p_gemm); mk(&w->st_dec, p_dec);
+        for (int l = 0; l < L; l++) { mk(&w->st_g[l], p_gemm); mk(&w->st_r[l], p_rec); }
     }
     auto mkev = [&](cudaEvent_t *e, bool timing) {
         if (st == GASR_OK && cudaEventCreateWithFlags(e, timing ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess) st = GASR_ERR_CUDA;

@@ -120,7 +120,7 @@ int gasr_ctx_create(int device, gasr_ctx **out) {
         o.xproj = chr("GASR_XPROJ"); o.chunk = num("GASR_CHUNK", -1); o.stream = num("GASR_STREAM", -1); o.wave = num("GASR_WAVE", -1);
         o.stream_gemm_ctas = num("GASR_STREAM_GEMM_CTAS", 24);
         o.gemm_stages = num("GASR_GEMM_STAGES", 3); o.ctc_warps = num("GASR_CTC_WARPS", 8); o.gemm_bn = num("GASR_GEMM_BN", 256); o.gemm_pair = num("GASR_GEMM_PAIR", 1);
-        o.wave_serial = getenv("GASR_WAVE_SERIAL") != nullptr; o.wave_timeout_s = num("GASR_WAVE_TIMEOUT_S", 60);
+        o.wave_serial = getenv("GASR_WAVE_SERIAL") != nullptr; o.wave_prio = num("GASR_WAVE_PRIO", -1); o.wave_timeout_s = num("GASR_WAVE_TIMEOUT_S", 60);
     }
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;

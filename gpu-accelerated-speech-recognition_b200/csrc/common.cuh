@@ -70,6 +70,7 @@ struct gasr_options {
     int gemm_pair = 1;       // GASR_GEMM_PAIR: projection GEMMs on CTA pairs (256 x 256 tiles); 0 = one-CTA tile engine
     int gemm_bn = 256;       // GASR_GEMM_BN: tile width of the wave engine's projection GEMMs (128 or 256)
     int wave_timeout_s = 60;  // GASR_WAVE_TIMEOUT_S: a batch that has not completed after this many seconds is reported as an error
+    int wave_prio = -1;       // GASR_WAVE_PRIO: stream priority scheme of the wave engine (-1: by batch size, see asr_wave.cu)
     bool wave_serial = false; // GASR_WAVE_SERIAL: diagnostic, all stages of the wave engine on one stream
     int ctc_warps = 8;       // GASR_CTC_WARPS: utterances (warps) per decoder CTA in the wave engine (0: balanced automatically)
 };
