@@ -520,7 +520,7 @@ def main():
                     "d2h_bytes_per_step": int(args.utts * (c["T"] + 1 + 8))},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "rnn_wide2_kernel (tcgen05 CTA-pair recurrence, one launch per layer and 50-frame chunk of a batch; "
+            "roofline": {"kernel": "rnn_wide2_kernel (tcgen05 CTA-pair recurrence, one launch per layer and time chunk of a batch; "
                                    "durations measured inside the running pipeline, where it shares the GPU with the GEMM and decoder kernels)",
                          "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": rec_traffic(args.wave), "peak_source": peak_kind,
@@ -528,7 +528,7 @@ def main():
                          "launches_per_step": n_rec},
             "whole_path_hbm": {"achieved": whole, "peak": hbm_peak, "unit": "GB/s", "frac": whole / hbm_peak,
                                "note": "25 452 compulsory bytes per frame and utterance (SURVEY.md 8d) over the whole step"},
-            "pipeline": {"mode": "wave", "chunk_frames": 50, "launches_per_stage_per_step": stage_launches,
+            "pipeline": {"mode": "wave", "chunk_frames": 25 if 256 < args.wave <= 1024 else 50, "launches_per_stage_per_step": stage_launches,
                          "note": "stages overlap on separate streams; stage times are sums of per-launch durations (profiled pass) "
                                  "and exceed ms_per_step"},
             "stages_ms_sum_of_launches": {"projection_gemm": stage_ms[0], "recurrence": stage_ms[1],

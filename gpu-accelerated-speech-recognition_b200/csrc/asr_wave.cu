@@ -101,7 +101,9 @@ int wave_create(gasr_asr *a) {
         // cluster gives small batches more clusters but measured slower even at 1024 utterances (22.4 vs 18.9 ms).
         w->rec_groups = ctx->opt.rnn_groups > 0 ? ctx->opt.rnn_groups : 2;
     }
-    w->Tc = ctx->opt.chunk > 0 ? ctx->opt.chunk : 50;
+    // 50-frame time chunks; 25 for batches of 257..1024 utterances, where the pipeline is bound by its dependency chains and the
+    // shorter fill outweighs the extra launches (1024 utterances: 19.5 -> 18.2 ms together with equal stream priorities)
+    w->Tc = ctx->opt.chunk > 0 ? ctx->opt.chunk : ((c.N > 256 && c.N <= 1024) ? 25 : 50);
     if (w->Tc > c.T) w->Tc = c.T;
     w->C = ceil_div(c.T, w->Tc);
     w->Kp0 = ceil_div(c.in, TC_BK) * TC_BK;
@@ -139,13 +141,14 @@ int wave_create(gasr_asr *a) {
         for (int l = 0; l < L; l++) w->st_g[l] = w->st_r[l] = w->st_in;
         w->serial = true;
     } else {
-        // Stream priorities.  Favouring the recurrences (the longest dependency chain) is right for a small batch, where the chain
-        // sets the time (1024 utterances: 18.5 ms vs 18.9 with equal priorities); with more utterances the recurrence launches
+        // Stream priorities.  Favouring the recurrences (the longest dependency chain) is kept for small batches, where the chain
+        // sets the time (1024 utterances with 50-frame chunks: 18.5 ms vs 18.9 with equal priorities; with 25-frame chunks equal
+        // priorities win, 18.2 vs 18.6); with more utterances the recurrence launches
         // (64 SMs each, mostly waiting on TMA latency) then take SMs from the stages that use them better: equal priorities give
         // 2048 utterances 32.4 -> 27.5 ms, 4096 58.6 -> 55.7 ms, the 8192-utterance step 116.5 -> 110.7 ms (same-box A/B).
         // GASR_WAVE_PRIO: 0 = recurrences > GEMMs > decoder, 1 = all equal, 2 = decoder > GEMMs > recurrences (24.6 ms at 1024),
         // 3 = GEMMs > recurrences > decoder (117 ms), 4 = decoder > recurrences > GEMMs, 5 = decoder = GEMMs > recurrences
-        const int pm = ctx->opt.wave_prio >= 0 ? ctx->opt.wave_prio : (c.N <= 1024 ? 0 : 1);
+        const int pm = ctx->opt.wave_prio >= 0 ? ctx->opt.wave_prio : (c.N <= 256 ? 0 : 1);
         const int p_rec = pm == 1 ? prio_lo : pm == 2 ? prio_lo : pm == 3 ? prio_mid : pm == 4 ? prio_mid : pm == 5 ? prio_lo : prio_hi;
         const int p_gemm = pm == 1 ? prio_lo : pm == 3 ? prio_hi : pm == 4 ? prio_lo : pm == 5 ? prio_hi : prio_mid;
         const int p_dec = (pm == 2 || pm == 4 || pm == 5) ? prio_hi : prio_lo;
