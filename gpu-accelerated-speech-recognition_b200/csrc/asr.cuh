@@ -26,6 +26,18 @@ struct StageEvents {
 
 struct WaveState;                               // asr_wave.cu
 
+// the calling thread's current device is switched to the context's for the duration of an entry point
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// stacked recurrent forward on a given stream (capi.cu; gasr_rnn_forward and the fused pipeline's sequential mode)
+int rnn_forward_impl(gasr_ctx *ctx, int cell, int bidir, int T, int N, int in, int H, int L, const float *const *w_ih,
+                     const float *const *w_hh, const float *const *b_ih, const float *const *b_hh, const float *x,
+                     float *const *hiddens, int precision, cudaStream_t st, StageEvents *prof = nullptr);
+
 }  // namespace gasr
 
 struct gasr_asr {
@@ -86,3 +98,7 @@ int wave_chunk_frames(const gasr_asr *a);
 float wave_last_ms(const gasr_asr *a);
 
 }  // namespace gasr
+
+#define GASR_ENTER(ctx)                                              \
+    if ((ctx) == nullptr) { gasr::set_error("null gasr_ctx"); return GASR_ERR_INVALID; } \
+    gasr::DeviceGuard guard__((ctx)->device)
