@@ -102,8 +102,11 @@ int gasr_rnn_cell_forward(gasr_ctx *ctx, const float *x, const float *h_prev, co
  * Parameter arrays hold device pointers indexed [l * D + d] (D = 2 when bidirectional):
  *   w_ih [in_l, G*H], w_hh [H, G*H], b_ih/b_hh [G*H]   (G = 1 tanh, 3 GRU with gate order r,z,n)
  * hiddens[l]: device [T*N, D*H], every layer's full hidden sequence (RNN.h:18); the last one is
- * what RNN::forward returns.  h_0 = 0 (RNN.h:16-17).  precision selects the input-projection
- * arithmetic (GASR_PREC_FP32: fp32-grade; GASR_PREC_BF16: bf16 operands, fp32 accumulate).
+ * what RNN::forward returns.  h_0 = 0 (RNN.h:16-17).  precision selects the tensor-core arithmetic:
+ * GASR_PREC_FP32: fp32-grade everywhere (three-term bf16 split, 2^-16 per product);
+ * GASR_PREC_BF16: input projections with bf16 operands and, for GRU stacks, the recurrence with fp16
+ * operands (one persistent launch per layer and direction); fp32 accumulation, gates and state.  Stated
+ * tolerance of that mode: 2e-2 on the log-probabilities.
  */
 int gasr_rnn_forward(gasr_ctx *ctx, int cell, int bidirectional, int T, int N, int in, int H, int L,
                      const float *const *w_ih, const float *const *w_hh, const float *const *b_ih,
