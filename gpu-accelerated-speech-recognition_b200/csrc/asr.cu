@@ -687,6 +687,7 @@ int gasr_asr_set_lengths(gasr_asr *a, const int *lens_host) {
     gasr_ctx *ctx = a->ctx;
     GASR_ENTER(ctx);
     const gasr_asr_config &c = a->cfg;
+    GASR_CHECK(!wave_pending(a), "gasr_asr_set_lengths: a batch is in flight (collect it first)");
     if (lens_host == nullptr) {
         if (a->lens_dev) { GASR_CUDA(cudaStreamSynchronize(ctx->stream)); gasr_free_device(ctx, a->lens_dev); a->lens_dev = nullptr; }
         return GASR_OK;

@@ -94,6 +94,7 @@ int wave_submit(gasr_asr *a, const float *x_dev, const float *x_host);   // enqu
 int wave_collect(gasr_asr *a, char *out_paths, int *out_lens, float *out_scores);   // wait + unpack the results
 int wave_logprobs(gasr_asr *a, const float **logp_dev, int *ldp);
 int wave_refresh_decoder(gasr_asr *a);           // decoder workspaces after lengths / timesteps were switched on
+bool wave_pending(const gasr_asr *a);            // a submitted batch has not been collected yet
 int wave_chunk_frames(const gasr_asr *a);
 float wave_last_ms(const gasr_asr *a);
 

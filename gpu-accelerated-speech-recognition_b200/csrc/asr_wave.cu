@@ -477,6 +477,8 @@ int wave_refresh_decoder(gasr_asr *a) {
     return GASR_OK;
 }
 
+bool wave_pending(const gasr_asr *a) { return a->wave && a->wave->pending; }
+
 int wave_chunk_frames(const gasr_asr *a) { return a->wave ? a->wave->Tc : 0; }
 float wave_last_ms(const gasr_asr *a) { return a->wave ? a->wave->last_ms : 0.0f; }
 
